@@ -1,0 +1,398 @@
+// ORACLE (test infrastructure only -- never linked into the product path).
+// CPU restatement of erlamsa's per-case pipeline: erlamsa_main:fuzzer/1
+// (src/erlamsa_main.erl:124-252), erlamsa_gen (src/erlamsa_gen.erl:43-56,152-199),
+// erlamsa_patterns (src/erlamsa_patterns.erl:45-443) and the `return` output
+// (src/erlamsa_out.erl:46-77,642-676), over the mutators in mutations.hpp.
+//
+// PARITY STATUS: the reference cannot run in the build container (no Erlang/OTP)
+// and its own tests hold no byte-level golden vectors, so this
+// oracle is pinned by: the public AS183 known-answer values, the one fixed-seed
+// reference test (st_line_ins_test, src/erlamsa_mutations_test.erl:223-230) and
+// the 31 property tests mirrored in tests/.  Beyond that: "parity unpinned".
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may load this library.
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <pthread.h>
+#include "mutations.hpp"
+
+namespace eo {
+
+static int64_t erl_round(double x) { return (int64_t)(x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5)); }
+
+struct CaseRunner {
+    Rng& rng; const Opts& opts; Mutations& muts; std::vector<MutNode> fs; Meta& meta;
+    const std::vector<std::pair<int, int>>& sorted_pats;   // {pri, PatId} after sort_by_priority
+    int pat_sum;
+    using Cont = std::function<Blocks(const Blocks&)>;
+
+    // split/1 :45-60 -- oversize head blocks are cut up (with draws)
+    void split_big(Bin& th, Blocks& rest) {
+        if (th.size() <= ABSMAX_BINARY_BLOCK) return;
+        std::vector<Bin> pieces; Bin cur = th;
+        while (cur.size() > ABSMAX_BINARY_BLOCK) {
+            uint64_t s = ABSMAXHALF_BINARY_BLOCK;
+            uint64_t as = s + rng.rand(s) - 1;
+            pieces.push_back(cur.substr(0, as)); cur = cur.substr(as);
+        }
+        pieces.push_back(cur);
+        th = pieces[0];
+        rest.insert(rest.begin(), pieces.begin() + 1, pieces.end());
+    }
+    // mutate_once_loop/6 :283-296
+    Blocks mutate_once_loop(const Cont& cont, uint64_t ip, Bin th, Blocks ll) {
+        Blocks out;
+        for (;;) {
+            uint64_t n = rng.rand(ip);
+            if (n == 0 || ll.empty()) {
+                Blocks arg; arg.push_back(th); arg.insert(arg.end(), ll.begin(), ll.end());
+                Blocks l = muts.mux_fuzzers(fs, arg, &meta);
+                Blocks rest = cont(l);
+                out.insert(out.end(), rest.begin(), rest.end());
+                return out;
+            }
+            out.push_back(th); th = ll[0]; ll.erase(ll.begin());
+        }
+    }
+    // mutate_once/4 :267-278
+    Blocks mutate_once(const Blocks& ll, const Cont& cont) {
+        if (ll.size() == 1 && ll[0].empty()) return Blocks();   // {Mutator, Meta}: nothing is written
+        uint64_t ip = rng.rand(INITIAL_IP);
+        if (ll.empty()) return cont(Blocks());
+        Bin th = ll[0]; Blocks rest(ll.begin() + 1, ll.end());
+        split_big(th, rest);
+        return mutate_once_loop(cont, ip, th, rest);
+    }
+    Cont cont_od() { return [](const Blocks& l) { return l; }; }
+    Cont cont_nd() {   // pat_many_dec_cont :315-321
+        return [this](const Blocks& l) -> Blocks {
+            if (rng.rand_occurs_fixed(4, 5)) return mutate_once(l, cont_nd());
+            return l;
+        };
+    }
+    Cont cont_bu() {   // pat_burst_cont :332-343
+        return [this](const Blocks& l0) -> Blocks {
+            Blocks l = l0;
+            for (int n = 1;; n++) {
+                bool p = rng.rand_occurs_fixed(4, 5);
+                if (!(p || n < 2)) return l;
+                l = muts.mux_fuzzers(fs, l, &meta);
+            }
+        };
+    }
+    Cont cont_pat(int pat) { return [this, pat](const Blocks& l) { return run_pattern(pat, l); }; }
+
+    static uint32_t crc32_of(const uint8_t* p, size_t n) { return (uint32_t)::crc32(0L, p, (uInt)n); }
+    struct Csum { bool crc; uint64_t plen, blen; };
+    std::vector<Csum> get_possible_csum_locations(const Bin& bin) {   // src/erlamsa_field_predict.erl:154-161
+        std::vector<Csum> out; uint64_t len = bin.size();
+        if (len == 0) return out;
+        uint64_t maxa = std::min<uint64_t>((uint64_t)std::trunc(2.0 * (double)len / 3.0), 30 * PREAMBLE_MAX_BYTES);
+        const uint8_t* d = (const uint8_t*)bin.data();
+        // xor8 of [A, Len-1) via suffix xors
+        std::vector<uint8_t> sx(len + 1, 0);
+        for (uint64_t i = len - 1; i-- > 0;) sx[i] = sx[i + 1] ^ d[i];   // xor over [i, len-1)
+        for (uint64_t a = 0; a <= maxa; a++) if (sx[a] == d[len - 1]) out.push_back({false, a, len - a - 1});
+        for (uint64_t a = 0; a <= maxa; a++) {
+            if (len - a < 4 || a > len) continue;
+            uint32_t c = ((uint32_t)d[len - 4] << 24) | ((uint32_t)d[len - 3] << 16) | ((uint32_t)d[len - 2] << 8) | d[len - 1];
+            if (crc32_of(d + a, len - a - 4) == c) out.push_back({true, a, len - a - 4});
+        }
+        return out;
+    }
+    static bool looks_like_zip(const Bin& b) { return b.find(std::string("PK\x05\x06", 4)) != Bin::npos; }
+    static bool maybe_compressed(const Bin& b) {
+        if (b.size() >= 2 && (uint8_t)b[0] == 0x1f && (uint8_t)b[1] == 0x8b) return true;   // gzip magic
+        if (b.size() >= 2) { unsigned cmf = (uint8_t)b[0], flg = (uint8_t)b[1]; if ((cmf & 15) == 8 && (cmf >> 4) <= 7 && ((cmf << 8) | flg) % 31 == 0) return true; }
+        return false;
+    }
+
+    Blocks run_pattern(int pat, const Blocks& ll) {
+        switch (pat) {
+        case P_OD: return mutate_once(ll, cont_od());
+        case P_ND: return mutate_once(ll, cont_nd());
+        case P_BU: return mutate_once(ll, cont_bu());
+        case P_CO: if (rng.erand(2) == 1) return run_pattern(P_NU, ll); return run_pattern(P_OD, ll);
+        case P_NU: { Blocks o = ll; if (!o.empty()) { Bin th = o[0]; Blocks rest(o.begin() + 1, o.end()); split_big(th, rest); o.clear(); o.push_back(th); o.insert(o.end(), rest.begin(), rest.end()); } return o; }
+        default: break;
+        }
+        // make_complex_pat :352-357: the continuation is drawn uniformly from all ten patterns
+        int next = (int)rng.rand_elem_idx(P_COUNT);
+        uint64_t ip = rng.rand(INITIAL_IP);
+        if (ll.empty()) throw CaseDied("complex pattern on an empty block list");
+        Bin bin = ll[0]; Blocks rest(ll.begin() + 1, ll.end());
+        if (pat == P_SK) {   // mutate_once_skipper :148-161
+            uint64_t len = rng.rand((uint64_t)std::trunc((double)bin.size() / 2.0));
+            Bin head = bin.substr(0, len), th = bin.substr(len);
+            split_big(th, rest);
+            Blocks res = mutate_once_loop(cont_pat(next), ip, th, rest);
+            res.insert(res.begin(), head); return res;
+        }
+        if (pat == P_SZ) {   // mutate_once_sizer :83-111
+            auto els = muts.get_possible_simple_lens(bin);
+            int64_t ei = rng.rand_elem_idx(els.size());
+            if (ei < 0) { split_big(bin, rest); return mutate_once_loop(cont_pat(next), ip, bin, rest); }
+            auto e = els[ei]; int fb = e.size / 8;
+            Bin h = bin.substr(0, e.a), blob = bin.substr(e.a + fb, e.len), tail = bin.substr(e.a + fb + e.len);
+            split_big(blob, rest);
+            Blocks inner = mutate_once_loop(cont_pat(next), ip, blob, rest);
+            Bin nb; for (auto& b : inner) nb += b;
+            Blocks o; o.push_back(h + Mutations::enc(nb.size(), e.size, e.big) + nb); o.push_back(tail); return o;
+        }
+        if (pat == P_CS) {   // mutate_once_csum :117-144
+            auto els = get_possible_csum_locations(bin);
+            int64_t ei = rng.rand_elem_idx(els.size());
+            if (ei < 0) { split_big(bin, rest); return mutate_once_loop(cont_pat(next), ip, bin, rest); }
+            auto e = els[ei];
+            Bin p = bin.substr(0, e.plen), blob = bin.substr(e.plen, e.blen);
+            split_big(blob, rest);
+            Blocks inner = mutate_once_loop(cont_pat(next), ip, blob, rest);
+            Bin nb; for (auto& b : inner) nb += b;
+            Bin c;
+            if (e.crc) { uint32_t v = crc32_of((const uint8_t*)nb.data(), nb.size()); c = Mutations::enc(v, 32, true); }
+            else { uint8_t x = 0; for (char ch : nb) x ^= (uint8_t)ch; c.push_back((char)x); }
+            Blocks o; o.push_back(p + nb + c); return o;
+        }
+        if (pat == P_AR) {   // mutate_once_archiver :167-214, non-archive input only
+            Bin all = bin; for (auto& b : rest) all += b;
+            if (looks_like_zip(all)) throw Unsupported("ar pattern on ZIP-looking data");
+            Blocks none; split_big(all, none);
+            return mutate_once_loop(cont_pat(next), ip, all, none);
+        }
+        // P_CP: mutate_once_compressed :217-260, non-compressed input only
+        if (maybe_compressed(bin)) throw Unsupported("cp pattern on compressed-looking data");
+        split_big(bin, rest);
+        return mutate_once_loop(cont_pat(next), ip, bin, rest);
+    }
+};
+
+struct Fuzzer {
+    Opts opts; Rng parent; Mutations muts; std::vector<MutNode> fs0;
+    std::vector<std::pair<int, int>> sorted_pats; int pat_sum = 0;
+    int generator = 0;   // 0 direct, 1 random
+
+    explicit Fuzzer(const Opts& o) : opts(o), muts(parent, opts) {
+        parent.seed(opts.seed[0], opts.seed[1], opts.seed[2]);   // :134
+        muts.build_table_draws();                                  // make_mutator -> mutations/1
+        fs0 = muts.make_mutator_nodes();                           // mutators_mutator/1
+        // make_generator :233-236 + mux_generators :194-199 for paths == [direct]
+        std::vector<std::pair<int, int>> gs;                       // {pri, kind}; option order: random, ..., direct
+        if (opts.gen_random_pri >= 0) gs.push_back({opts.gen_random_pri, 1});
+        if (opts.gen_direct_pri >= 0) gs.push_back({opts.gen_direct_pri, 0});
+        if (gs.empty()) throw Unsupported("no generators");
+        generator = choose_pri(sort_by_priority(gs), parent, true);
+        // make_pattern :409-422: foldl prepends -> reversed table order, then sort_by_priority
+        std::vector<std::pair<int, int>> ps;
+        for (int i = P_COUNT; i-- > 0;) if (opts.pat_pri[i] >= 0) ps.push_back({opts.pat_pri[i], i});
+        sorted_pats = sort_by_priority(ps);
+        for (auto& p : sorted_pats) pat_sum += p.first;
+    }
+    static std::vector<std::pair<int, int>> sort_by_priority(const std::vector<std::pair<int, int>>& l) {   // src/erlamsa_utils.erl:114-117
+        ErlSort<std::pair<int, int>> s([](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+        return s.sort(l);
+    }
+    static int choose_pri(const std::vector<std::pair<int, int>>& sorted, Rng& rng, bool) {   // :155-160
+        int sum = 0; for (auto& p : sorted) sum += p.first;
+        int64_t n = (int64_t)rng.rand((uint64_t)sum);
+        for (auto& p : sorted) { if (n == 0) return p.second; if (n < p.first) return p.second; n -= p.first; }
+        throw CaseDied("choose_pri: function_clause");
+    }
+    // finish/1 :43-51
+    void finish(Rng& rng, uint64_t len, Blocks& out) {
+        uint64_t n = rng.rand(len + 1);
+        if (n != len) return;
+        uint64_t bits = (uint64_t)rng.rand_range(1, 16);
+        uint64_t nlen = rng.rand(1ull << bits);
+        Bin t = rng.random_numbers_256(nlen);
+        if (!t.empty()) out.push_back(t);
+    }
+    uint64_t rand_block_size(Rng& rng) {   // :55-56
+        return std::max<uint64_t>(rng.rand((uint64_t)erl_round(MAX_BLOCK_SIZE * opts.blockscale)), (uint64_t)erl_round(MIN_BLOCK_SIZE * opts.blockscale));
+    }
+    Blocks generate(Rng& rng, const Bin& input) {
+        Blocks ll;
+        if (generator == 0) {   // direct_generator :161-164 (split_binary's first clause never matches)
+            (void)rand_block_size(rng);
+            ll.push_back(input); finish(rng, input.size(), ll);
+        } else {                // random_stream :168-178
+            for (;;) {
+                uint64_t n = (uint64_t)rng.rand_range(32, erl_round(MAX_BLOCK_SIZE * opts.blockscale));
+                ll.push_back(rng.random_block(n));
+                uint64_t ip = (uint64_t)rng.rand_range(1, 100);
+                if (rng.rand(ip) == 0) break;
+            }
+        }
+        return ll;
+    }
+    // one iteration of FuzzingLoopFun :166-243; the parent stream advances by three draws
+    Bin run_case(const Bin& input, Meta& meta) {
+        int64_t ts[3]; parent.gen_predictable_seed(ts);
+        return run_case_seeded(input, ts, meta);
+    }
+    Bin run_case_seeded(const Bin& input, const int64_t ts[3], Meta& meta) {
+        Rng rng; rng.seed(ts[0], ts[1], ts[2]);
+        meta.thread_seed[0] = ts[0]; meta.thread_seed[1] = ts[1]; meta.thread_seed[2] = ts[2];
+        meta.generator = generator;
+        Mutations m(rng, opts); m.snand_kind = muts.snand_kind;
+        Bin out;
+        try {
+            Blocks ll = generate(rng, input);
+            CaseRunner cr{rng, opts, m, fs0, meta, sorted_pats, pat_sum};
+            int pat = choose_pri(sorted_pats, rng, false);
+            meta.pattern = pat;
+            Blocks res = cr.run_pattern(pat, ll);
+            for (auto& b : res) out += b;
+        } catch (const Unsupported&) { meta.status = 1; out.clear(); }
+        catch (const CaseDied&) { meta.status = 2; out.clear(); }
+        meta.draws = rng.draws;
+        return out;
+    }
+};
+
+}  // namespace eo
+
+// ------------------------------------------------------------------ C API (ctypes)
+extern "C" {
+
+struct eo_opts_c {
+    int64_t seed[3];
+    double blockscale;
+    int32_t muta_pri[41];
+    int32_t pat_pri[10];
+    int32_t gen_direct_pri, gen_random_pri;
+    char ssrf_host[64];
+    int32_t ssrf_port;
+};
+struct eo_meta_c {
+    int32_t pattern, generator, n_used, n_failed;
+    int32_t used[16];
+    uint64_t draws;
+    int32_t status; int32_t pad;
+    int64_t thread_seed[3];
+};
+
+static eo::Opts conv(const eo_opts_c* c) {
+    eo::Opts o; for (int i = 0; i < 3; i++) o.seed[i] = c->seed[i];
+    o.blockscale = c->blockscale;
+    for (int i = 0; i < eo::M_COUNT; i++) o.muta_pri[i] = c->muta_pri[i];
+    for (int i = 0; i < eo::P_COUNT; i++) o.pat_pri[i] = c->pat_pri[i];
+    o.gen_direct_pri = c->gen_direct_pri; o.gen_random_pri = c->gen_random_pri;
+    o.ssrf_host = std::string(c->ssrf_host, strnlen(c->ssrf_host, 64)); o.ssrf_port = c->ssrf_port;
+    return o;
+}
+static void conv_meta(const eo::Meta& m, eo_meta_c* c) {
+    c->pattern = m.pattern; c->generator = m.generator; c->n_used = m.n_used; c->n_failed = m.n_failed;
+    for (int i = 0; i < 16; i++) c->used[i] = m.used[i];
+    c->draws = m.draws; c->status = m.status; c->pad = 0;
+    for (int i = 0; i < 3; i++) c->thread_seed[i] = m.thread_seed[i];
+}
+
+void eo_default_opts(eo_opts_c* c) {
+    eo::Opts o; memset(c, 0, sizeof(*c));
+    for (int i = 0; i < 3; i++) c->seed[i] = o.seed[i];
+    c->blockscale = 1.0;
+    for (int i = 0; i < eo::M_COUNT; i++) c->muta_pri[i] = o.muta_pri[i];
+    for (int i = 0; i < eo::P_COUNT; i++) c->pat_pri[i] = o.pat_pri[i];
+    c->gen_direct_pri = 500; c->gen_random_pri = 1;
+    strcpy(c->ssrf_host, "localhost"); c->ssrf_port = 51234;
+}
+
+// Runs cases first_case .. first_case+n_cases-1 (1-based, as the I of FuzzingLoopFun) of ONE
+// fuzzer/1 call; case I reads corpus blob (I-1) mod n_blobs. Outputs are packed; out_off has n_cases+1 entries.
+// Everything runs on a thread with a large stack (tree mutators recurse by nesting depth).
+struct RunArgs {
+    const eo_opts_c* opts; const uint8_t* data; const uint64_t* off; uint64_t n_blobs; uint64_t first_case, n_cases;
+    std::string* out; uint64_t* out_off; eo_meta_c* meta; int rc;
+};
+static void* run_thread(void* p) {
+    RunArgs* a = (RunArgs*)p;
+    try {
+        eo::Fuzzer f(conv(a->opts));
+        eo::Meta skip;
+        for (uint64_t i = 1; i < a->first_case; i++) { int64_t ts[3]; f.parent.gen_predictable_seed(ts); }
+        a->out_off[0] = 0;
+        for (uint64_t k = 0; k < a->n_cases; k++) {
+            uint64_t b = (a->first_case - 1 + k) % a->n_blobs;
+            eo::Bin in((const char*)a->data + a->off[b], a->off[b + 1] - a->off[b]);
+            eo::Meta m; eo::Bin o = f.run_case(in, m);
+            a->out->append(o); a->out_off[k + 1] = a->out->size();
+            if (a->meta) conv_meta(m, &a->meta[k]);
+        }
+        a->rc = 0;
+    } catch (const std::exception&) { a->rc = -1; }
+    return nullptr;
+}
+static int on_big_stack(void* (*fn)(void*), void* arg) {
+    pthread_attr_t at; pthread_attr_init(&at); pthread_attr_setstacksize(&at, (size_t)4 << 30);
+    pthread_t th; if (pthread_create(&th, &at, fn, arg)) return -1;
+    pthread_join(th, nullptr); pthread_attr_destroy(&at); return 0;
+}
+
+static thread_local std::string g_out;
+int eo_fuzzer(const eo_opts_c* opts, const uint8_t* data, const uint64_t* off, uint64_t n_blobs,
+              uint64_t first_case, uint64_t n_cases, const uint8_t** out_data, uint64_t* out_off, eo_meta_c* meta) {
+    g_out.clear();
+    RunArgs a{opts, data, off, n_blobs, first_case, n_cases, &g_out, out_off, meta, -1};
+    if (on_big_stack(run_thread, &a)) return -2;
+    *out_data = (const uint8_t*)g_out.data();
+    return a.rc;
+}
+
+// ---- unit hooks (mirror the reference's eunit style: seed, run one mutator on one block)
+struct UnitArgs { const eo_opts_c* opts; int muta; const int64_t* seed; const uint8_t* in; uint64_t len; const uint8_t* next; uint64_t next_len; int rounds; std::string* out; double delta; int rc; };
+static void* unit_thread(void* p) {
+    UnitArgs* a = (UnitArgs*)p;
+    try {
+        eo::Opts o = conv(a->opts); eo::Rng rng; rng.seed(a->seed[0], a->seed[1], a->seed[2]);
+        eo::Mutations m(rng, o); m.snand_kind = 0;
+        if (a->muta == eo::M_SNAND || a->muta == eo::M_SRND) m.build_table_draws();
+        eo::MutNode node; node.name = node.fn = a->muta; node.pri = 1; node.score = 10;
+        eo::Blocks ll; ll.push_back(eo::Bin((const char*)a->in, a->len));
+        if (a->next) ll.push_back(eo::Bin((const char*)a->next, a->next_len));
+        eo::MutRes r;
+        for (int i = 0; i < a->rounds; i++) { r = m.apply(node, ll); ll = r.ll; }
+        a->out->clear(); for (auto& b : r.ll) a->out->append(b);
+        a->delta = r.delta; a->rc = 0;
+    } catch (const eo::Unsupported&) { a->rc = 1; } catch (const eo::CaseDied&) { a->rc = 2; } catch (...) { a->rc = -1; }
+    return nullptr;
+}
+static thread_local std::string g_unit;
+// Applies mutator `muta` `rounds` times (closure state carried) to [in | next?]; returns concatenated blocks.
+int eo_run_mutator(const eo_opts_c* opts, int muta, const int64_t seed[3], const uint8_t* in, uint64_t len,
+                   const uint8_t* next, uint64_t next_len, int rounds, const uint8_t** out, uint64_t* out_len, double* delta) {
+    UnitArgs a{opts, muta, seed, in, len, next, next_len, rounds, &g_unit, 0, -1};
+    if (on_big_stack(unit_thread, &a)) return -2;
+    *out = (const uint8_t*)g_unit.data(); *out_len = g_unit.size(); if (delta) *delta = a.delta;
+    return a.rc;
+}
+
+// raw RNG access for known-answer tests
+static thread_local eo::Rng g_rng;
+void eo_rnd_seed(int64_t a, int64_t b, int64_t c) { g_rng.seed(a, b, c); g_rng.draws = 0; }
+void eo_rnd_seed0(void) { g_rng = eo::Rng(); }
+double eo_rnd_uniform(void) { return g_rng.uniform(); }
+uint64_t eo_rnd_rand(uint64_t n) { return g_rng.rand(n); }
+uint64_t eo_rnd_erand(uint64_t n) { return g_rng.erand(n); }
+void eo_rnd_state(int64_t s[3]) { s[0] = g_rng.a1; s[1] = g_rng.a2; s[2] = g_rng.a3; }
+
+// lists:sort/2 restatement on integer keys: cmp 0 => A =< B ... see tests. `kind`: 0 strict '>' on key, 1 '>=' on key
+void eo_lists_sort(const int32_t* keys, int32_t n, int32_t kind, int32_t* perm_out) {
+    std::vector<std::pair<int, int>> v; for (int i = 0; i < n; i++) v.push_back({keys[i], i});
+    eo::ErlSort<std::pair<int, int>> s(kind == 0
+        ? eo::ErlSort<std::pair<int, int>>::Fun([](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; })
+        : eo::ErlSort<std::pair<int, int>>::Fun([](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first >= b.first; }));
+    auto r = s.sort(v); for (int i = 0; i < n; i++) perm_out[i] = r[i].second;
+}
+
+// strlex round trip
+int eo_lex_unlex(const uint8_t* in, uint64_t len, const uint8_t** out, uint64_t* out_len, int32_t* n_chunks) {
+    eo::Chunks cs = eo::lex(eo::Bin((const char*)in, len)); g_unit = eo::unlex(cs);
+    *out = (const uint8_t*)g_unit.data(); *out_len = g_unit.size(); if (n_chunks) *n_chunks = (int32_t)cs.size(); return 0;
+}
+int eo_funny_unicode_count(void) { return (int)eo::Mutations::funny_unicode().size(); }
+const char* eo_mutator_code(int i) { return (i >= 0 && i < eo::M_COUNT) ? eo::MUT_CODES[i] : nullptr; }
+const char* eo_pattern_code(int i) { return (i >= 0 && i < eo::P_COUNT) ? eo::PAT_CODES[i] : nullptr; }
+
+}  // extern "C"
