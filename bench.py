@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- mutated test cases / s of the erlamsa hot path on B200 (BASELINE.json metric).
+
+A "step" = one pass of the hot path (decide kernel -> prefix sum -> apply kernel) over one batch of
+synthetic seeds resident in HBM. Default workload = BASELINE config C3 (the one the 1e7 cases/s target
+is quoted on): 100 000 x 65 536 B uniform-random seeds, mutators bd,bei,bed,bf,bi,ber,br,num at
+priority 1, pattern od, AS183-exact RNG. Every step mutates the NEXT window of case ids (first_case
+advances), so no step repeats work and the 6.5 GB corpus + 6.5 GB of outputs per step never fit L2.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3num|c2]
+
+Under torchrun (N > 1) every rank owns one GPU and its own shard of case ids (weak scaling: per-GPU work
+fixed; cases are independent, so there is no data-path collective); timing = max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (n_cases, seed_bytes, corpus kind, mutators, patterns, description)
+    "c3": (100000, 65536, "bin", ["bd", "bei", "bed", "bf", "bi", "ber", "br", "num"], {"od": 1},
+           "C3: 100000 x 65536 B uniform-random seeds; bd,bei,bed,bf,bi,ber,br,num; pattern od"),
+    "c3num": (100000, 65536, "num", ["bd", "bei", "bed", "bf", "bi", "ber", "br", "num"], {"od": 1},
+              "C3(ii): 100000 x 65536 B numeric text; bd,bei,bed,bf,bi,ber,br,num; pattern od"),
+    "c2": (10000, 4096, "bin", None, {"od": 1, "nd": 2, "bu": 1},
+           "C2: 10000 x 4096 B uniform-random seeds; device-supported part of the default mutator mix; od,nd,bu"),
+}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.lines = []
+        self.idx = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_corpus_device(torch, kind, n, size, dev, seed):
+    """synthetic seeds of the configured shape, generated on the device (uniform bytes) or on the host (text)"""
+    if kind == "bin":
+        g = torch.Generator(device=dev); g.manual_seed(seed)
+        data = torch.randint(0, 256, (n * size + 64,), dtype=torch.uint8, device=dev, generator=g)
+    else:
+        import corpus
+        import numpy as np
+        r = corpus.rng(seed)
+        base = np.frombuffer(b"".join(corpus.numeric_text(r, size) for _ in range(256)), dtype=np.uint8)
+        t = torch.from_numpy(base.copy()).to(dev)
+        reps = (n + 255) // 256
+        data = torch.cat([t.repeat(reps)[: n * size], torch.zeros(64, dtype=torch.uint8, device=dev)])
+    off = torch.arange(0, (n + 1) * size, size, dtype=torch.int64, device=dev)
+    return data, off
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import erlamsa_b200
+    from erlamsa_b200 import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n_cases, size, kind, muts, pats, desc = WORKLOADS[args.workload]
+    if args.cases:
+        n_cases = args.cases
+    if muts is None:
+        muts = {c: p for c, p in erlamsa_b200.default_mutations() if c in erlamsa_b200.supported_mutations()}
+    else:
+        muts = {c: 1 for c in muts}
+    eng = erlamsa_b200.Engine(local)
+    data, off = make_corpus_device(torch, kind, n_cases, size, dev, 0xE21A0003 + rank)
+    data_bytes = n_cases * size
+    out_cap = data_bytes + 64 * n_cases + (64 << 20)
+    d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
+    d_out_off = torch.empty(n_cases + 1, dtype=torch.int64, device=dev)
+    d_out_len = torch.empty(n_cases, dtype=torch.int64, device=dev)
+    base_opts = {"mutations": muts, "patterns": pats, "seed": (1, 2, 3), "rng": args.rng, "scratch_bytes": 512 << 20}
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        o = dict(base_opts)
+        o["first_case"] = 1 + (rank + world * i) * n_cases       # every rank / step gets its own window of case ids
+        return eng.fuzz_batch_device(o, data.data_ptr(), off.data_ptr(), n_cases, data_bytes, n_cases, d_out.data_ptr(), out_cap,
+                                     d_out_off.data_ptr(), d_out_len.data_ptr(), 0, stream.cuda_stream)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    apply_ms, decide_ms, scan_ms, launches, bytes_out = [], [], [], 0, 0
+    for i in range(args.steps):
+        st = step(args.warmup + i)
+        apply_ms.append(st.ms_apply); decide_ms.append(st.ms_decide); scan_ms.append(st.ms_scan)
+        launches += st.kernels_launched; bytes_out += st.bytes_out
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        dist.barrier()
+    out_len_sum = int(d_out_len.sum().item())
+
+    # ---- e2e: the C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e_cases = min(n_cases, args.e2e_cases)
+        hb = torch.empty(e2e_cases * size + 64, dtype=torch.uint8, pin_memory=True)
+        hb[: e2e_cases * size].copy_(data[: e2e_cases * size])
+        hoff = (C.c_uint64 * (e2e_cases + 1))(*[i * size for i in range(e2e_cases + 1)])
+        hout = torch.empty(e2e_cases * size + 64 * e2e_cases + (1 << 20), dtype=torch.uint8, pin_memory=True)
+        ho_off = (C.c_uint64 * (e2e_cases + 1))(); ho_len = (C.c_uint64 * e2e_cases)()
+        st2 = N.Stats()
+        o = erlamsa_b200.make_opts(base_opts)
+        times = []
+        for i in range(args.e2e_steps + 1):
+            o.first_case = 1 + (10_000 + rank + world * i) * n_cases
+            t0 = time.perf_counter()
+            rc = N.lib().eb200_fuzz_batch_into(eng._ctx, C.byref(o), hb.data_ptr(), C.cast(hoff, C.c_void_p), e2e_cases, e2e_cases,
+                                               hout.data_ptr(), hout.numel(), C.cast(ho_off, C.c_void_p), C.cast(ho_len, C.c_void_p), None, C.byref(st2))
+            t1 = time.perf_counter()
+            assert rc == 0, rc
+            if i > 0:
+                times.append(t1 - t0)
+            launches_e2e = st2.kernels_launched
+        dt = max(times)
+        if world > 1:
+            t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        e2e = {"value": e2e_cases * world / dt, "unit": "cases/s", "h2d_bytes_per_step": e2e_cases * size + 8 * (e2e_cases + 1),
+               "d2h_bytes_per_step": int(sum(ho_len)) + 16 * e2e_cases + 8, "cases_per_step": e2e_cases * world,
+               "note": "eb200_fuzz_batch_into: pinned host corpus -> H2D -> decide/scan/apply -> D2H of packed outputs, offsets and lengths"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_cases = n_cases * world * args.steps
+    peak, peak_src = peak_hbm()
+    # algorithmic bytes of the apply kernel per launch: len_in + len_out + 16 per case
+    alg_bytes = data_bytes + out_len_sum + 16 * n_cases
+    avg_apply = sum(apply_ms) / len(apply_ms)
+    achieved = alg_bytes / (avg_apply * 1e-3) / 1e9
+    line = {
+        "metric": "mutated testcases/sec", "value": total_cases / (ms * 1e-3), "unit": "cases/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": desc, "cases_per_gpu_per_step": n_cases, "seed_bytes": size, "rng": args.rng,
+                   "l2_policy": "inputs larger than L2 (%.2f GB in + %.2f GB out per step, 126 MB L2)" % (data_bytes / 1e9, out_len_sum / 1e9),
+                   "parallelism": "cases sharded by id, no collective"},
+        "gb_per_s_mutated": (data_bytes + out_len_sum) * world * args.steps / (ms * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "kernel": "eb_apply_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": avg_apply},
+        "kernel_ms": {"decide": sum(decide_ms) / len(decide_ms), "scan": sum(scan_ms) / len(scan_ms), "apply": avg_apply},
+        "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args, size, kind, muts, pats, threads=1, budget_s=12.0)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_corpus(kind, n, size, seed):
+    import corpus
+    return corpus.uniform_corpus(seed, n, size, kind)
+
+
+def cpu_run(blobs, muts, pats, n_cases, first_case, threads):
+    """oracle (CPU restatement of the reference path) over n_cases cases, split across host threads"""
+    import oracle_lib
+    opts = oracle_lib.make_opts(seed=(1, 2, 3), mutations=muts, patterns=pats)
+    oracle_lib.lib()
+    per = (n_cases + threads - 1) // threads
+    res = [0] * threads
+
+    def work(t):
+        lo = t * per
+        cnt = max(0, min(per, n_cases - lo))
+        if cnt:
+            outs, _ = oracle_lib.fuzzer(blobs, opts=opts, n_cases=cnt, first_case=first_case + lo)
+            res[t] = sum(len(o) for o in outs)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return time.perf_counter() - t0, sum(res)
+
+
+def cpu_baseline(args, size, kind, muts, pats, threads, budget_s):
+    blobs = cpu_corpus(kind, 64, size, 0xE21A0003)
+    dt, _ = cpu_run(blobs, muts, pats, 64 * threads, 1, threads)           # calibration
+    rate = 64 * threads / dt
+    n = max(64 * threads, int(rate * budget_s))
+    dt, _ = cpu_run(blobs, muts, pats, n, 1000, threads)
+    return {"value": n / dt, "unit": "cases/s", "cores": threads, "kind": "port",
+            "sample": "%d cases of the same workload (64 distinct %d-byte seeds reused), oracle C++ restatement, %d thread(s), %.1f s"
+                      % (n, size, threads, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path. The reference is Erlang and OTP is not in
+    this image, so this arm times the oracle port with all host threads on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    n_cases, size, kind, muts, pats, desc = WORKLOADS[args.workload]
+    if muts is None:
+        import erlamsa_b200
+        muts = {c: p for c, p in erlamsa_b200.default_mutations() if c in erlamsa_b200.supported_mutations()}
+    else:
+        muts = {c: 1 for c in muts}
+    threads = os.cpu_count() or 1
+    blobs = cpu_corpus(kind, 64, size, 0xE21A0003)
+    dt, _ = cpu_run(blobs, muts, pats, 16 * threads, 1, threads)
+    rate = 16 * threads / dt
+    per_step = max(threads, int(rate * 4.0))          # ~4 s of CPU work per step
+    for i in range(args.warmup):
+        cpu_run(blobs, muts, pats, max(threads, per_step // 8), 1 + i * per_step, threads)
+    t_total = 0.0
+    for i in range(args.steps):
+        dt, _ = cpu_run(blobs, muts, pats, per_step, 1 + (args.warmup + i) * per_step, threads)
+        t_total += dt
+    v = per_step * args.steps / t_total
+    sample = "%d cases/step of the same workload (64 distinct %d-byte seeds reused), %d host threads" % (per_step, size, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "mutated testcases/sec", "value": v, "unit": "cases/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": {"workload": desc, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "cases/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "cases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cases", type=int, default=0, help="override cases per GPU per step")
+    ap.add_argument("--rng", default="as183", choices=["as183", "philox"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-cases", type=int, default=20000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,336 @@
+// erlamsa_b200 -- the decide kernel: one warp runs one test case's whole decision pipeline.
+//
+// Mirrors, per case I (reference file:line):
+//   thread seed        erlamsa_main.erl:179-183   gen_predictable_seed on the parent stream (jump-ahead)
+//   generator          erlamsa_gen.erl:43-56,152-178   direct (+ finish tail) or random stream
+//   pattern            erlamsa_patterns.erl:266-443   od / nd / bu / sk / co / nu state machine
+//   scheduler          erlamsa_mutations.erl:1234-1280   weighted permutation, try until hd(Ll) changes
+// and leaves an edit script (list of Seg) + output length per case. No payload bytes are moved
+// here except when a later mutation round needs the previous round's result materialised.
+#pragma once
+#include "eb_mutators.cuh"
+
+namespace eb {
+
+// ------------------------------------------------------------------ active block list
+EB_DEV uint32_t active_count(const WarpState* ws) {
+    uint32_t n = 0;
+    if (ws->vhead) n += ws->vchunked ? ws->vlen / AVG_BLOCK_SIZE + 1 : 1;
+    for (int i = 0; i < ws->nruns; i++) n += ws->runs[i].cnt;
+    return n;
+}
+EB_DEV bool active_is_single_empty(const WarpState* ws) {   // Ll =:= [<<>>]
+    if (active_count(ws) != 1) return false;
+    return ws->vhead ? ws->vlen == 0 : ws->runs[0].len == 0;
+}
+EB_DEV void runs_insert_front(WarpState* ws, Blk b) {
+    if (b.cnt == 0) return;
+    if (ws->nruns >= MAX_RUNS) { ws->status = CASE_OVERFLOW; ws->reason = 4; return; }
+    for (int i = ws->nruns; i > 0; i--) ws->runs[i] = ws->runs[i - 1];
+    ws->runs[0] = b; ws->nruns++;
+}
+EB_DEV void runs_push_back(WarpState* ws, Blk b) {
+    if (b.cnt == 0) return;
+    if (ws->nruns >= MAX_RUNS) { ws->status = CASE_OVERFLOW; ws->reason = 4; return; }
+    ws->runs[ws->nruns++] = b;
+}
+EB_DEV void pop_head(WarpState* ws) {
+    if (ws->runs[0].cnt > 1) { ws->runs[0].p += ws->runs[0].len; ws->runs[0].cnt--; return; }
+    for (int i = 1; i < ws->nruns; i++) ws->runs[i - 1] = ws->runs[i];
+    ws->nruns--;
+}
+// materialise the virtual head into scratch and put its block(s) at the front of the run table
+EB_DEV void realize_virtual(CaseCtx& c) {
+    WarpState* ws = c.ws;
+    if (!ws->vhead) return;
+    uint8_t* buf = scratch_alloc(c, ws->vlen);
+    ws->vhead = 0;
+    if (!buf) return;
+    segs_write(ws->vseg, ws->nvseg, buf);
+    if (ws->vchunked) {
+        uint32_t k = ws->vlen / AVG_BLOCK_SIZE, r = ws->vlen - k * AVG_BLOCK_SIZE;
+        Blk last; last.p = buf + (uint64_t)k * AVG_BLOCK_SIZE; last.len = r; last.cnt = 1; runs_insert_front(ws, last);
+        Blk full; full.p = buf; full.len = AVG_BLOCK_SIZE; full.cnt = k; runs_insert_front(ws, full);
+    } else {
+        Blk b; b.p = buf; b.len = ws->vlen; b.cnt = 1; runs_insert_front(ws, b);
+    }
+}
+EB_DEV void emit_head(CaseCtx& c) {
+    WarpState* ws = c.ws;
+    if (ws->vhead && !ws->vchunked) { for (int i = 0; i < ws->nvseg; i++) o_push(c, ws->vseg[i]); ws->vhead = 0; return; }
+    realize_virtual(c);
+    if (ws->status != CASE_OK || ws->nruns == 0) return;
+    o_push(c, seg_copy(ws->runs[0].p, ws->runs[0].len));
+    pop_head(ws);
+}
+EB_DEV void emit_all(CaseCtx& c) {
+    WarpState* ws = c.ws;
+    if (ws->vhead) { for (int i = 0; i < ws->nvseg; i++) o_push(c, ws->vseg[i]); ws->vhead = 0; }
+    for (int i = 0; i < ws->nruns; i++) {
+        uint64_t tot = (uint64_t)ws->runs[i].len * ws->runs[i].cnt; const uint8_t* p = ws->runs[i].p;
+        while (tot) { uint32_t ch = tot > 0x40000000ull ? 0x40000000u : (uint32_t)tot; o_push(c, seg_copy(p, ch)); p += ch; tot -= ch; }
+    }
+    ws->nruns = 0;
+}
+// split/1, reference src/erlamsa_patterns.erl:45-60: an oversize head block is cut into pieces (with draws)
+EB_DEV void split_big(CaseCtx& c) {
+    WarpState* ws = c.ws;
+    realize_virtual(c);
+    if (ws->status != CASE_OK || ws->nruns == 0) return;
+    if (ws->runs[0].len <= ABSMAX_BINARY_BLOCK) return;
+    const uint8_t* p = ws->runs[0].p; uint32_t left = ws->runs[0].len;
+    pop_head(ws);
+    Blk pieces[16]; int np = 0;
+    while (left > ABSMAX_BINARY_BLOCK) {
+        uint32_t as = ABSMAXHALF_BINARY_BLOCK + (uint32_t)c.rng.rand(ABSMAXHALF_BINARY_BLOCK) - 1;
+        if (np >= 15) { ws->status = CASE_OVERFLOW; ws->reason = 6; return; }
+        pieces[np].p = p; pieces[np].len = as; pieces[np].cnt = 1; np++;
+        p += as; left -= as;
+    }
+    pieces[np].p = p; pieces[np].len = left; pieces[np].cnt = 1; np++;
+    for (int i = np - 1; i >= 0; i--) runs_insert_front(ws, pieces[i]);
+}
+
+// ------------------------------------------------------------------ scheduler: one mux_fuzzers round
+EB_DEV double adjust_priority(double pri, double delta) {   // :1238-1242
+    if (delta == 0.0) return pri;
+    return fmax(2.0, fmin(10.0, pri + delta));
+}
+EB_DEV void mux_fuzzers(CaseCtx& c) {
+    WarpState* ws = c.ws; Rng& g = c.rng;
+    if (active_count(ws) == 0 || active_is_single_empty(ws)) return;
+    realize_virtual(c);
+    if (ws->status != CASE_OK) return;
+    const uint8_t* p = ws->runs[0].p; uint32_t n = ws->runs[0].len;
+    int nr = ws->nrows;
+    // weighted_permutations/1 :1244-1250: key_i = rand(trunc(Score*Pri)), stable sort by key descending
+    for (int i = 0; i < nr; i++) ws->keys[i] = (uint32_t)g.rand((uint64_t)trunc(ws->rows[i].score * (double)ws->rows[i].pri));
+    for (int i = 0; i < nr; i++) {
+        uint32_t k = ws->keys[i]; int j = i - 1;
+        // order[] holds row indices sorted so far; insert i after every entry with key >= k
+        while (j >= 0 && ws->keys[ws->order[j]] < k) { ws->order[j + 1] = ws->order[j]; j--; }
+        ws->order[j + 1] = (uint8_t)i;
+    }
+    int nt = 0;
+    for (int t = 0; t < nr; t++) {
+        bool big = n > ABSMAX_BINARY_BLOCK;   // :1269-1270 -- the node under the cursor is dropped from the list
+        bool changed = false;
+        MutResult r; r.kind = RES_SAME; r.delta = 0; r.rechunk = 0; r.consumed_next = 0;
+        if (!big) {
+            MutRow row = ws->rows[ws->order[t]];
+            mut_apply(c, row, p, n, r);
+            if (r.kind == RES_UNSUPPORTED) ws->status = CASE_UNSUPPORTED;
+            if (ws->status != CASE_OK) return;
+            row.score = adjust_priority(row.score, r.delta);
+            ws->tried[nt++] = row;
+            if (r.kind == RES_SEGS) {
+                uint32_t first = (r.rechunk && ws->tlen >= AVG_BLOCK_SIZE) ? AVG_BLOCK_SIZE : ws->tlen;
+                changed = !(first == n && segs_equal_prefix(ws->tseg, ws->ntseg, p, n));
+            }
+            if (!changed) { ws->n_failed++; continue; }
+            if (ws->n_used < 16) ws->used[ws->n_used] = row.name;
+            ws->n_used++;
+        }
+        // new scheduler list: reversed(tried) ++ untried tail (in permutation order)
+        int tail = nr - (t + 1);
+        for (int j = 0; j < tail; j++) ws->tried[nt + j] = ws->rows[ws->order[t + 1 + j]];
+        for (int j = 0; j < nt / 2; j++) { MutRow x = ws->tried[j]; ws->tried[j] = ws->tried[nt - 1 - j]; ws->tried[nt - 1 - j] = x; }
+        ws->nrows = nt + tail;
+        for (int j = 0; j < ws->nrows; j++) ws->rows[j] = ws->tried[j];
+        if (big) return;
+        // commit: the head block becomes the virtual result
+        pop_head(ws);
+        if (r.consumed_next && ws->nruns > 0) pop_head(ws);
+        ws->vhead = 1; ws->vchunked = r.rechunk; ws->nvseg = ws->ntseg; ws->vlen = ws->tlen;
+        for (int j = 0; j < ws->ntseg; j++) ws->vseg[j] = ws->tseg[j];
+        return;
+    }
+    // every mutator failed: mux_fuzzers(Out) -- the tried list reversed
+    for (int j = 0; j < nt / 2; j++) { MutRow x = ws->tried[j]; ws->tried[j] = ws->tried[nt - 1 - j]; ws->tried[nt - 1 - j] = x; }
+    for (int j = 0; j < nt; j++) ws->rows[j] = ws->tried[j];
+    ws->nrows = nt;
+}
+
+// ------------------------------------------------------------------ generator
+EB_DEV const uint8_t* random_block_dev(CaseCtx& c, uint32_t n) {   // random_block/1: draw i lands at byte n-1-i
+    uint8_t* buf = scratch_alloc(c, n);
+    if (!buf) return nullptr;
+    for (uint32_t i = 0; i < n; i++) { uint32_t b = (uint32_t)c.rng.rand(256); if (lane_id() == 0) buf[n - 1 - i] = (uint8_t)b; }
+    __syncwarp();
+    return buf;
+}
+EB_DEV void generate(CaseCtx& c, const uint8_t* blob, uint32_t blen) {
+    WarpState* ws = c.ws; Rng& g = c.rng; const BatchParams* bp = c.bp;
+    ws->nruns = 0; ws->vhead = 0;
+    if (bp->generator == 0) {   // direct_generator + finish
+        (void)g.rand((uint64_t)bp->rbs_bound);
+        Blk b; b.p = blob; b.len = blen; b.cnt = 1; runs_push_back(ws, b);
+        uint64_t x = g.rand((uint64_t)blen + 1);
+        if (x == blen) {
+            uint64_t bits = (uint64_t)g.rand_range(1, 16);
+            uint32_t nlen = (uint32_t)g.rand(1ull << bits);
+            if (nlen) { const uint8_t* t = random_block_dev(c, nlen); if (t) { Blk tb; tb.p = t; tb.len = nlen; tb.cnt = 1; runs_push_back(ws, tb); } }
+        }
+    } else {                    // random_stream
+        for (;;) {
+            uint32_t n = (uint32_t)g.rand_range(32, (int64_t)bp->rbs_bound);
+            const uint8_t* t = random_block_dev(c, n);
+            if (!t || ws->status != CASE_OK) return;
+            Blk tb; tb.p = t; tb.len = n; tb.cnt = 1; runs_push_back(ws, tb);
+            if (ws->status != CASE_OK) return;
+            uint64_t ip = (uint64_t)g.rand_range(1, 100);
+            if (g.rand(ip) == 0) break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ pattern state machine
+enum { CONT_OD = 0, CONT_ND = 1, CONT_BU = 2, CONT_PAT = 3 };
+
+__host__ EB_DEV bool pat_supported(int id) { return id == P_OD || id == P_ND || id == P_BU || id == P_SK || id == P_CO || id == P_NU; }
+
+EB_DEV void run_case_machine(CaseCtx& c, int pat) {
+    WarpState* ws = c.ws; Rng& g = c.rng;
+    int cont = CONT_OD, next = 0;
+    for (int guard = 0; guard < 100000 && ws->status == CASE_OK; guard++) {
+        // ---- pattern dispatch
+        uint64_t ip = 0;
+        if (pat == P_NU) { split_big(c); emit_all(c); return; }
+        if (pat == P_CO) { if (g.erand(2) == 1) { split_big(c); emit_all(c); return; } pat = P_OD; }
+        if (pat == P_OD || pat == P_ND || pat == P_BU) {
+            cont = pat == P_OD ? CONT_OD : pat == P_ND ? CONT_ND : CONT_BU;
+            // mutate_once/4 :267-278
+            if (active_is_single_empty(ws)) { ws->vhead = 0; ws->nruns = 0; return; }
+            ip = g.rand(INITIAL_IP);
+            if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
+            split_big(c);
+        } else if (pat == P_SK) {
+            // make_complex_pat + mutate_once_skipper :148-161,352-361
+            next = (int)g.rand_elem_idx(P_COUNT);
+            ip = g.rand(INITIAL_IP);
+            if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
+            realize_virtual(c);
+            if (ws->status != CASE_OK) return;
+            uint32_t n0 = ws->runs[0].len;
+            uint32_t len = (uint32_t)g.rand((uint64_t)(n0 / 2));
+            o_push(c, seg_copy(ws->runs[0].p, len));
+            Blk tail; tail.p = ws->runs[0].p + len; tail.len = n0 - len; tail.cnt = 1;
+            pop_head(ws); runs_insert_front(ws, tail);
+            split_big(c);
+            cont = CONT_PAT;
+        } else { ws->status = CASE_UNSUPPORTED; return; }
+        if (ws->status != CASE_OK) return;
+        // ---- mutate_once_loop :283-296
+        for (;;) {
+            uint64_t x = g.rand(ip);
+            if (x == 0 || active_count(ws) == 1) break;
+            emit_head(c);
+            if (ws->status != CASE_OK) return;
+        }
+        mux_fuzzers(c);
+        if (ws->status != CASE_OK) return;
+        // ---- continuation
+        if (cont == CONT_OD) { emit_all(c); return; }
+        if (cont == CONT_ND) {
+            if (g.rand_occurs_fixed(4, 5)) { pat = P_ND; continue; }
+            emit_all(c); return;
+        }
+        if (cont == CONT_BU) {   // pat_burst_cont :332-343
+            for (int nb = 1;; nb++) {
+                bool pr = g.rand_occurs_fixed(4, 5);
+                if (!(pr || nb < 2)) break;
+                mux_fuzzers(c);
+                if (ws->status != CASE_OK) return;
+            }
+            emit_all(c); return;
+        }
+        pat = next;   // CONT_PAT: the continuation pattern runs on the result list
+    }
+}
+
+// ------------------------------------------------------------------ kernel
+struct DecideArgs {
+    const uint8_t* data; const uint64_t* off; Arenas ar;
+    CaseOut* cases; uint64_t* out_len; uint64_t* out_sz16; MetaDev* meta;
+};
+
+// one test case, start to finish, by one warp
+EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideArgs& a, uint64_t k, int32_t pa1, int32_t pa2, int32_t pa3) {
+    const uint8_t* data = a.data; const uint64_t* off = a.off; const Arenas& ar = a.ar;
+    CaseOut* cases = a.cases; uint64_t* out_len = a.out_len; uint64_t* out_sz16 = a.out_sz16; MetaDev* meta = a.meta;
+    {
+        uint64_t I = bp.first_case + k;                 // the reference's 1-based case number
+        uint64_t b = (I - 1) % bp.n_blobs;
+        const uint8_t* blob = data + off[b]; uint32_t blen = (uint32_t)(off[b + 1] - off[b]);
+        CaseCtx c; c.ws = ws; c.bp = &bp; c.ar = ar;
+        // thread seed: three erand(99999) at parent draw index 3*(I-1) (the caller keeps the parent state there)
+        Rng par; par.mode = 0; par.a1 = pa1; par.a2 = pa2; par.a3 = pa3; par.draws = 0; par.key = 0; par.ctr_hi = 0;
+        int64_t ts0 = (int64_t)par.erand(99999), ts1 = (int64_t)par.erand(99999), ts2 = (int64_t)par.erand(99999);
+        c.rng.mode = bp.rng_mode; c.rng.key = bp.philox_key; c.rng.ctr_hi = I;
+        c.rng.seed(ts0, ts1, ts2);
+        // fresh per-case state (CurMuta is not carried between cases, reference src/erlamsa_main.erl:223-235)
+        ws->status = CASE_OK; ws->reason = 0; ws->n_used = 0; ws->n_failed = 0; ws->noseg = 0; ws->olen = 0;
+        ws->st_n[0] = ws->st_n[1] = 0; ws->fo_has = 0; ws->ntseg = 0; ws->tlen = 0; ws->nvseg = 0; ws->vlen = 0; ws->vchunked = 0;
+        for (int i = 0; i < 16; i++) ws->used[i] = -1;
+        ws->nrows = bp.n_rows;
+        for (int i = 0; i < bp.n_rows; i++) { MutRow r; r.score = (double)bp.row_score[i]; r.pri = bp.row_pri[i]; r.name = bp.row_id[i]; r.fn = bp.row_id[i]; r.pad = 0; ws->rows[i] = r; }
+        __syncwarp();
+        generate(c, blob, blen);
+        int pat = -1;
+        if (ws->status == CASE_OK) {
+            // mux_patterns :438-443 + choose_pri (reference src/erlamsa_utils.erl:155-160)
+            int64_t x = (int64_t)c.rng.rand((uint64_t)bp.pat_sum);
+            for (int i = 0; i < bp.n_pats; i++) { if (x == 0 || x < bp.pat_pri[i]) { pat = bp.pat_id[i]; break; } x -= bp.pat_pri[i]; }
+            if (pat < 0) ws->status = CASE_DIED; else run_case_machine(c, pat);
+        }
+        if (ws->status == CASE_OK && ws->olen > bp.max_case_out) { ws->status = CASE_OVERFLOW; ws->reason = 5; }
+        if (ws->status == CASE_UNSUPPORTED || ws->status == CASE_OVERFLOW) { ws->noseg = 0; ws->olen = 0; o_push(c, seg_copy(blob, blen)); }
+        if (ws->status == CASE_DIED) { ws->noseg = 0; ws->olen = 0; }
+        __syncwarp();
+        // publish the edit script
+        unsigned long long sb = 0; int ns = ws->noseg;
+        if (lane_id() == 0 && ns > 0) sb = atomicAdd(ar.segs_used, (unsigned long long)ns);
+        sb = __shfl_sync(0xffffffffu, sb, 0);
+        if (sb + ns > ar.segs_cap) { if (lane_id() == 0) atomicOr(ar.overflow, 2u); ns = 0; ws->olen = 0; ws->status = CASE_OVERFLOW; ws->reason = 7; }
+        for (int i = lane_id(); i < ns; i += 32) ar.segs[sb + i] = ws->oseg[i];
+        if (lane_id() == 0) {
+            CaseOut co; co.seg_begin = sb; co.nseg = (uint32_t)ns; co.status = ws->status; co.out_len = ws->olen; co.pad = 0;
+            cases[k] = co; out_len[k] = ws->olen; out_sz16[k] = align16(ws->olen);
+            if (meta) {
+                MetaDev m; m.pattern = pat; m.generator = bp.generator; m.n_used = ws->n_used; m.n_failed = ws->n_failed;
+                for (int i = 0; i < 16; i++) m.used[i] = ws->used[i];
+                m.draws = c.rng.draws; m.status = (int32_t)ws->status; m.pad = (int32_t)ws->reason; m.thread_seed[0] = ts0; m.thread_seed[1] = ts1; m.thread_seed[2] = ts2;
+                meta[k] = m;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// WARPS warps per CTA, each taking whole cases. With SYNC the CTA re-converges before every case so
+// that its warps walk the (large, branchy) scalar program in step and share instruction-cache
+// lines: profiles/decide_r1b showed 53% of stall samples on instruction fetch with free-running warps.
+template <int WARPS, bool SYNC, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+eb_decide_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ off, BatchParams bp, Arenas ar,
+                 CaseOut* __restrict__ cases, uint64_t* __restrict__ out_len, uint64_t* __restrict__ out_sz16, MetaDev* __restrict__ meta) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    WarpState* ws = reinterpret_cast<WarpState*>(smem_raw) + (threadIdx.x >> 5);
+    DecideArgs a; a.data = data; a.off = off; a.ar = ar; a.cases = cases; a.out_len = out_len; a.out_sz16 = out_sz16; a.meta = meta;
+    uint64_t warp_global = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    uint64_t nwarps = (uint64_t)gridDim.x * WARPS;
+    uint64_t rounds = (bp.n_cases + nwarps - 1) / nwarps;
+    // parent stream position of this warp's first case, and the multipliers that advance it by one
+    // round (3 draws per case, nwarps cases per round): x_{k+s} = x_k * a^s mod p per AS183 component
+    Rng par; par.mode = 0; par.a1 = bp.parent_a1; par.a2 = bp.parent_a2; par.a3 = bp.parent_a3; par.draws = 0; par.key = 0; par.ctr_hi = 0;
+    par.jump(3 * (bp.first_case - 1 + warp_global));
+    uint32_t s1 = modpow_u32<30269>(AS_M1, 3 * nwarps), s2 = modpow_u32<30307>(AS_M2, 3 * nwarps), s3 = modpow_u32<30323>(AS_M3, 3 * nwarps);
+    for (uint64_t r = 0; r < rounds; r++) {
+        if (SYNC) __syncthreads();
+        uint64_t k = r * nwarps + warp_global;
+        if (k < bp.n_cases) decide_one_case(ws, bp, a, k, par.a1, par.a2, par.a3);
+        par.a1 = (int32_t)(((uint32_t)par.a1 * s1) % 30269u); par.a2 = (int32_t)(((uint32_t)par.a2 * s2) % 30307u); par.a3 = (int32_t)(((uint32_t)par.a3 * s3) % 30323u);
+    }
+}
+
+}  // namespace eb

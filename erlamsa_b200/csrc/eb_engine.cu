@@ -1,0 +1,398 @@
+// erlamsa_b200 -- host side of the engine and the C ABI (include/erlamsa_b200.h).
+//
+// Per batch the host restates the PARENT-process part of erlamsa_main:fuzzer/1
+// (reference src/erlamsa_main.erl:124-163: seed, make_mutator, make_generator, make_pattern --
+// a few dozen RNG draws) and hands the result to the device as BatchParams; everything per case
+// runs on the GPU: eb_decide_kernel -> prefix sum -> eb_apply_kernel.
+// There is deliberately NO CPU fallback: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+#include "../../include/erlamsa_b200.h"
+#include "eb_decide.cuh"
+#include "eb_apply.cuh"
+#include "eb_erlsort.hpp"
+
+using namespace eb;
+
+static const char* const kMutCodes[EB200_N_MUTATORS] = {
+    "sgm", "js", "uw", "ui", "ab", "ad", "tr2", "td", "num", "ts1", "tr", "ts2",
+    "bd", "bei", "bed", "bf", "bi", "ber", "br", "sp", "sr", "sd", "snand", "srnd",
+    "ld", "lds", "lr2", "lri", "lr", "ls", "lp", "lis", "lrs", "ft", "fn", "fo",
+    "len", "b64", "uri", "zip", "nil"};
+static const int kMutPri[EB200_N_MUTATORS] = {10, 3, 1, 2, 1, 1, 1, 1, 3, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                                              1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 2, 2, 7, 1, 1, 0};
+static const char* const kPatCodes[EB200_N_PATTERNS] = {"od", "nd", "bu", "sk", "sz", "cs", "ar", "cp", "co", "nu"};
+static const int kPatPri[EB200_N_PATTERNS] = {1, 2, 1, 2, 2, 1, 1, 1, 0, 0};
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct eb200_ctx {
+    int device = 0;
+    int num_sms = 148;
+    std::string last_err;
+    DevBuf cases, out_len, sz16, tile_sum, tile_case, counters, segs, scratch, data, off, out, out_off, meta;
+    cudaEvent_t ev[6];
+    bool funny_loaded = false;
+    int apply_variant = 0;
+    int decide_variant = 0;
+};
+
+// apply-kernel configurations (words per thread, loads in flight per thread, min CTAs/SM); index 0 ships,
+// the others are kept for A/B measurements (env EB200_APPLY_VARIANT)
+struct ApplyVariant {
+    uint32_t tile; const char* name;
+    void (*launch)(unsigned, cudaStream_t, const CaseOut*, const Seg*, const uint64_t*, const uint32_t*, uint64_t, uint8_t*, uint64_t);
+};
+template <int W, int B, int M>
+static void launch_apply(unsigned ctas, cudaStream_t st, const CaseOut* c, const Seg* s, const uint64_t* oo, const uint32_t* tc, uint64_t n, uint8_t* out, uint64_t cap) {
+    eb_apply_kernel<W, B, M><<<ctas, APPLY_THREADS, 0, st>>>(c, s, oo, tc, n, out, cap);
+}
+#define AV(W, B, M) {APPLY_THREADS * W * 16, #W "w" #B "b" #M "m", launch_apply<W, B, M>}
+// measured on C3 (profiles/variants_r1.txt): 16w2b8m 2.20 ms (5969 GB/s) | 32w1b8m 2.35 | 16w1b8m 2.37 | 32w2b6m 2.42 | 16w2b6m 2.45 | 8w2b6m 2.55
+static const ApplyVariant apply_variants[] = {AV(16, 2, 8), AV(16, 1, 8), AV(16, 2, 6), AV(32, 2, 8), AV(8, 2, 8), AV(32, 1, 8)};
+static const int n_apply_variants = (int)(sizeof(apply_variants) / sizeof(apply_variants[0]));
+
+// decide-kernel configurations (warps per CTA, per-case CTA barrier, min CTAs/SM); env EB200_DECIDE_VARIANT
+struct DecideVariant {
+    int warps; int ctas_per_sm; const char* name;
+    cudaError_t (*prepare)();
+    void (*launch)(int, cudaStream_t, const uint8_t*, const uint64_t*, const BatchParams&, const Arenas&, CaseOut*, uint64_t*, uint64_t*, MetaDev*);
+};
+template <int W, bool S, int M>
+static cudaError_t prepare_decide() { return cudaFuncSetAttribute(eb_decide_kernel<W, S, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpState) * W)); }
+template <int W, bool S, int M>
+static void launch_decide(int grid, cudaStream_t st, const uint8_t* d, const uint64_t* o, const BatchParams& bp, const Arenas& ar, CaseOut* c, uint64_t* ol, uint64_t* sz, MetaDev* m) {
+    eb_decide_kernel<W, S, M><<<grid, W * 32, sizeof(WarpState) * W, st>>>(d, o, bp, ar, c, ol, sz, m);
+}
+#define DV(W, S, M) {W, M, #W "w" #S #M "m", prepare_decide<W, S, M>, launch_decide<W, S, M>}
+// measured on C3 (profiles/variants_r1.txt): 32w-sync 2.55 ms | 16w-sync 2.76 | 4w-free 3.55 | 32w-free 3.55
+static const DecideVariant decide_variants[] = {DV(32, true, 1), DV(16, true, 2), DV(4, false, 8), DV(32, false, 1)};
+static const int n_decide_variants = (int)(sizeof(decide_variants) / sizeof(decide_variants[0]));
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_); return EB200_ERR_CUDA; } } while (0)
+
+static int64_t erl_round(double x) { return (int64_t)(x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5)); }
+
+// funny_unicode/0, reference src/erlamsa_mutations.erl:1052-1078: 17 hand-written byte strings, then the UTF-8
+// encodings (encode_point :1036-1049) of a code-point list that a foldl builds back to front.
+static void build_funny(std::vector<FunnyEntry>& out) {
+    auto put = [&](std::initializer_list<int> l) { FunnyEntry e; e.len = (uint32_t)l.size(); e.bytes = 0; int i = 0; for (int b : l) e.bytes |= (uint32_t)(b & 255) << (8 * i++); out.push_back(e); };
+    put({239, 191, 191}); put({240, 144, 128, 128}); put({0xef, 0xbb, 0xbf}); put({0xfe, 0xff}); put({0xff, 0xfe});
+    put({0, 0, 0xff, 0xff}); put({0xff, 0xff, 0, 0}); put({43, 47, 118, 56}); put({43, 47, 118, 57}); put({43, 47, 118, 43});
+    put({43, 47, 118, 47}); put({247, 100, 76}); put({221, 115, 102, 115}); put({14, 254, 255}); put({251, 238, 40});
+    put({251, 238, 40, 255}); put({132, 49, 149, 51});
+    struct R { int a, b; };
+    const R codes[] = {{0x0009, 0x000d}, {0x008D, 0}, {0x00a0, 0}, {0x1680, 0}, {0x180e, 0}, {0x2000, 0x200a}, {0x2028, 0}, {0x2029, 0},
+                       {0x202f, 0}, {0x205f, 0}, {0x3000, 0}, {0x200e, 0x200f}, {0x202a, 0x202e}, {0x200c, 0x200d}, {0x0345, 0}, {0x00b7, 0},
+                       {0x02d0, 0x02d1}, {0xff70, 0}, {0x02b0, 0x02b8}, {0xfdd0, 0}, {0x034f, 0}, {0x115f, 0x1160}, {0x2065, 0x2069},
+                       {0x3164, 0}, {0xffa0, 0}, {0xe0001, 0}, {0xe0020, 0xe007f}, {0x0e40, 0x0e44}, {0x1f4a9, 0}};
+    std::vector<int> pts;
+    for (const R& r : codes) {   // each group is prepended, ranges ascending inside the group
+        std::vector<int> grp; if (r.b == 0) grp.push_back(r.a); else for (int x = r.a; x <= r.b; x++) grp.push_back(x);
+        pts.insert(pts.begin(), grp.begin(), grp.end());
+    }
+    for (int p : pts) {
+        if (p < 0x80) put({p});
+        else if (p < 0x800) put({0xc0 | (0x1f & (p >> 6)), (p & 0x3f) | 0x80});
+        else if (p < 0x10000) put({0xe0 | (0x0f & (p >> 12)), ((p >> 6) & 0x3f) | 0x80, (p & 0x3f) | 0x80});
+        else put({0xf0 | (0x7 & (p >> 18)), ((p >> 12) & 0x3f) | 0x80, ((p >> 6) & 0x3f) | 0x80, (p & 0x3f) | 0x80});
+    }
+}
+
+// choose_pri/2, reference src/erlamsa_utils.erl:155-160
+static int choose_pri(const std::vector<std::pair<int, int>>& sorted, int64_t n) {
+    for (auto& p : sorted) { if (n == 0 || n < p.first) return p.second; n -= p.first; }
+    return -1;
+}
+static std::vector<std::pair<int, int>> sort_by_priority(const std::vector<std::pair<int, int>>& l) {
+    ErlangListSort<std::pair<int, int>> s([](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+    return s(l);
+}
+
+// The parent process' draws: T0..T3 of SURVEY.md appendix A.
+static int compute_batch_params(const eb200_opts* o, uint64_t n_blobs, uint64_t n_cases, BatchParams& bp) {
+    memset(&bp, 0, sizeof(bp));
+    Rng par; par.mode = 0; par.key = 0; par.ctr_hi = 0; par.draws = 0;
+    par.seed(o->seed[0], o->seed[1], o->seed[2]);                       // erlamsa_main.erl:134
+    bp.snand_kind = (int)par.rand_elem_idx(3);                           // mutations/1 :1313
+    (void)par.rand_elem_idx(1);                                          //             :1314
+    int n = 0;
+    for (int i = 0; i < M_COUNT; i++) if (o->muta_pri[i] >= 0) {
+        if (!mut_supported(i)) return EB200_ERR_UNSUPPORTED;
+        bp.row_id[n] = (uint8_t)i; bp.row_pri[n] = o->muta_pri[i]; n++;
+    }
+    bp.n_rows = n;
+    for (int i = n - 1; i >= 0; i--) { uint64_t s = par.rand(10); bp.row_score[i] = (int)(s < 2 ? 2 : s); }   // mutators_mutator :1390-1395
+    std::vector<std::pair<int, int>> gs;                                 // make_generator for paths == [direct]
+    if (o->gen_random_pri >= 0) gs.push_back({o->gen_random_pri, 1});
+    if (o->gen_direct_pri >= 0) gs.push_back({o->gen_direct_pri, 0});
+    if (gs.empty()) return EB200_ERR_ARG;
+    { auto sg = sort_by_priority(gs); int sum = 0; for (auto& g : sg) sum += g.first;
+      int g = choose_pri(sg, (int64_t)par.rand((uint64_t)sum)); if (g < 0) return EB200_ERR_ARG; bp.generator = g; }
+    std::vector<std::pair<int, int>> ps;                                 // make_pattern: foldl prepends -> reversed table
+    for (int i = P_COUNT - 1; i >= 0; i--) if (o->pat_pri[i] >= 0) {
+        if (o->pat_pri[i] > 0 && !pat_supported(i)) return EB200_ERR_UNSUPPORTED;
+        ps.push_back({o->pat_pri[i], i});
+    }
+    if (ps.empty()) return EB200_ERR_ARG;
+    auto sp = sort_by_priority(ps);
+    bp.n_pats = (int)sp.size(); bp.pat_sum = 0;
+    for (int i = 0; i < bp.n_pats; i++) { bp.pat_pri[i] = sp[i].first; bp.pat_id[i] = sp[i].second; bp.pat_sum += sp[i].first; }
+    bp.parent_a1 = par.a1; bp.parent_a2 = par.a2; bp.parent_a3 = par.a3;
+    bp.rng_mode = o->rng_mode;
+    bp.philox_key = ((uint64_t)(uint32_t)o->seed[0] * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(uint32_t)o->seed[1] << 32) ^ (uint64_t)(uint32_t)o->seed[2] * 0xD1B54A32D192ED03ull;
+    double bs = o->blockscale > 0 ? o->blockscale : 1.0;
+    bp.rbs_bound = (int)erl_round(4096.0 * bs); bp.rbs_min = (int)erl_round(256.0 * bs);
+    bp.first_case = o->first_case ? o->first_case : 1;
+    bp.n_blobs = n_blobs; bp.n_cases = n_cases;
+    bp.max_case_out = o->max_case_out ? o->max_case_out : (64ull << 20);
+    if (bp.max_case_out > 0x7fffffffull) bp.max_case_out = 0x7fffffffull;
+    bp.ssrf_port = o->ssrf_port;
+    memcpy(bp.ssrf_host, o->ssrf_host, 64);
+    return EB200_OK;
+}
+
+extern "C" {
+
+void eb200_default_opts(eb200_opts* o) {
+    memset(o, 0, sizeof(*o));
+    o->seed[0] = 1; o->seed[1] = 2; o->seed[2] = 3;
+    o->blockscale = 1.0;
+    for (int i = 0; i < EB200_N_MUTATORS; i++) o->muta_pri[i] = kMutPri[i];
+    for (int i = 0; i < EB200_N_PATTERNS; i++) o->pat_pri[i] = kPatPri[i];
+    o->gen_direct_pri = 500; o->gen_random_pri = 1;
+    strcpy(o->ssrf_host, "localhost"); o->ssrf_port = 51234;
+    o->rng_mode = EB200_RNG_AS183; o->first_case = 1;
+}
+
+int eb200_init(int device, eb200_ctx** out) {
+    if (!out) return EB200_ERR_ARG;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return EB200_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return EB200_ERR_ARG;
+    eb200_ctx* ctx = new eb200_ctx(); ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
+    cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    if (const char* v = getenv("EB200_APPLY_VARIANT")) { int k = atoi(v); if (k >= 0 && k < n_apply_variants) ctx->apply_variant = k; }
+    std::vector<FunnyEntry> f; build_funny(f);
+    int fn = (int)f.size(); f.resize(192);
+    if (cudaMemcpyToSymbol(c_funny, f.data(), sizeof(FunnyEntry) * 192) != cudaSuccess || cudaMemcpyToSymbol(c_funny_n, &fn, sizeof(int)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
+    if (const char* v = getenv("EB200_DECIDE_VARIANT")) { int k = atoi(v); if (k >= 0 && k < n_decide_variants) ctx->decide_variant = k; }
+    if (decide_variants[ctx->decide_variant].prepare() != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
+    *out = ctx; return EB200_OK;
+}
+
+void eb200_shutdown(eb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta}) b->release();
+    for (auto& e : ctx->ev) cudaEventDestroy(e);
+    delete ctx;
+}
+
+// decide + scan for a batch resident on the device. On return *total_out = packed output size.
+static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* opts, const uint8_t* d_data, const uint64_t* d_off,
+                           uint64_t data_bytes, uint64_t* d_out_off, uint64_t* d_out_len, eb200_meta* d_meta, cudaStream_t st, uint64_t* total_out, uint32_t* launches) {
+    uint64_t n = bp.n_cases;
+    CK(ctx->cases.ensure(n * sizeof(CaseOut)));
+    CK(ctx->sz16.ensure(n * 8));
+    uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    CK(ctx->tile_sum.ensure((ntiles + 1) * 8));
+    CK(ctx->counters.ensure(64));
+    uint64_t seg_cap = ctx->segs.cap / sizeof(Seg);
+    if (seg_cap < n * 6 + 1024) { CK(ctx->segs.ensure((n * 6 + 1024) * sizeof(Seg))); seg_cap = ctx->segs.cap / sizeof(Seg); }
+    uint64_t scratch_want = opts->scratch_bytes ? opts->scratch_bytes : std::min<uint64_t>(4 * data_bytes + (64ull << 20), 8ull << 30);
+    if (ctx->scratch.cap < scratch_want) CK(ctx->scratch.ensure(scratch_want));
+    for (int attempt = 0;; attempt++) {
+        CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+        Arenas ar;
+        ar.scratch = (uint8_t*)ctx->scratch.p; ar.scratch_cap = ctx->scratch.cap - 64;
+        ar.scratch_used = (unsigned long long*)ctx->counters.p;
+        ar.segs = (Seg*)ctx->segs.p; ar.segs_cap = ctx->segs.cap / sizeof(Seg);
+        ar.segs_used = (unsigned long long*)ctx->counters.p + 1;
+        ar.overflow = (uint32_t*)((unsigned long long*)ctx->counters.p + 2);
+        const DecideVariant& dv = decide_variants[ctx->decide_variant];
+        uint64_t want_ctas = (n + dv.warps - 1) / dv.warps;
+        int grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * dv.ctas_per_sm);
+        if (grid < 1) grid = 1;
+        CK(cudaEventRecord(ctx->ev[0], st));
+        dv.launch(grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[1], st));
+        (*launches)++;
+        uint32_t ovf = 0;
+        CK(cudaMemcpyAsync(&ovf, ar.overflow, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!ovf) break;
+        if (attempt >= 3) return EB200_ERR_SCRATCH;
+        if (ovf & 1) { size_t nw = ctx->scratch.cap * 2; CK(ctx->scratch.ensure(nw)); }
+        if (ovf & 2) { size_t nw = ctx->segs.cap * 2; CK(ctx->segs.ensure(nw)); }
+    }
+    eb_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t*)ctx->sz16.p, n, (uint64_t*)ctx->tile_sum.p);
+    eb_scan_tile_offsets<<<1, SCAN_THREADS, 0, st>>>((uint64_t*)ctx->tile_sum.p, ntiles, (uint64_t*)ctx->tile_sum.p + ntiles);
+    eb_scan_finish<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t*)ctx->sz16.p, n, (const uint64_t*)ctx->tile_sum.p, (const uint64_t*)ctx->tile_sum.p + ntiles, d_out_off);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[2], st));
+    *launches += 3;
+    CK(cudaMemcpyAsync(total_out, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return EB200_OK;
+}
+
+static int run_apply(eb200_ctx* ctx, uint64_t n, const uint64_t* d_out_off, uint8_t* d_out, uint64_t out_capacity, uint64_t total, cudaStream_t st, uint32_t* launches) {
+    CK(cudaEventRecord(ctx->ev[3], st));
+    if (total > 0) {
+        const ApplyVariant& av = apply_variants[ctx->apply_variant];
+        uint64_t ctas = (total + av.tile - 1) / av.tile;
+        CK(ctx->tile_case.ensure((ctas + 1) * sizeof(uint32_t)));
+        eb_tile_cases<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_out_off, n, (uint32_t*)ctx->tile_case.p, av.tile);
+        av.launch((unsigned)ctas, st, (const CaseOut*)ctx->cases.p, (const Seg*)ctx->segs.p, d_out_off, (const uint32_t*)ctx->tile_case.p, n, d_out, out_capacity);
+        CK(cudaGetLastError());
+        (*launches) += 2;
+    }
+    CK(cudaEventRecord(ctx->ev[4], st));
+    return EB200_OK;
+}
+
+static void fill_stats(eb200_ctx* ctx, eb200_stats* s) {
+    if (!s) return;
+    cudaEventElapsedTime(&s->ms_decide, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&s->ms_scan, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&s->ms_apply, ctx->ev[3], ctx->ev[4]);
+}
+
+int eb200_fuzz_batch_device(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* d_data, const uint64_t* d_off, uint64_t n_blobs, uint64_t data_bytes,
+                            uint64_t n_cases, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_off, uint64_t* d_out_len,
+                            eb200_meta* d_meta, void* stream, eb200_stats* stats) {
+    if (!ctx || !opts || !d_data || !d_off || !d_out || !d_out_off || !d_out_len || n_blobs == 0) return EB200_ERR_ARG;
+    if (((uintptr_t)d_data & 15u) || ((uintptr_t)d_out & 15u)) return EB200_ERR_ARG;
+    static_assert(sizeof(eb200_meta) == sizeof(MetaDev), "meta layout");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_cases == 0) return EB200_OK;
+    BatchParams bp; int rc = compute_batch_params(opts, n_blobs, n_cases, bp);
+    if (rc) return rc;
+    uint32_t launches = 0; uint64_t total = 0;
+    CK(cudaEventRecord(ctx->ev[5], st));
+    rc = run_decide_scan(ctx, bp, opts, d_data, d_off, data_bytes, d_out_off, d_out_len, d_meta, st, &total, &launches);
+    if (rc) return rc;
+    if (total > out_capacity) return EB200_ERR_NOMEM;
+    rc = run_apply(ctx, n_cases, d_out_off, d_out, out_capacity, total, st, &launches);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    if (stats) {
+        fill_stats(ctx, stats); cudaEventElapsedTime(&stats->ms_total, ctx->ev[5], ctx->ev[4]);
+        stats->n_cases = n_cases; stats->kernels_launched = launches; stats->bytes_out = total;
+    }
+    return EB200_OK;
+}
+
+static int fuzz_batch_host(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases,
+                           uint8_t** out_data, uint8_t* user_out, uint64_t user_cap, uint64_t* out_off, uint64_t* out_len, eb200_meta* meta, eb200_stats* stats);
+
+int eb200_fuzz_batch(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases,
+                     uint8_t** out_data, uint64_t* out_off, uint64_t* out_len, eb200_meta* meta, eb200_stats* stats) {
+    if (!out_data) return EB200_ERR_ARG;
+    return fuzz_batch_host(ctx, opts, data, off, n_blobs, n_cases, out_data, nullptr, 0, out_off, out_len, meta, stats);
+}
+int eb200_fuzz_batch_into(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases,
+                          uint8_t* out_buf, uint64_t out_capacity, uint64_t* out_off, uint64_t* out_len, eb200_meta* meta, eb200_stats* stats) {
+    if (!out_buf) return EB200_ERR_ARG;
+    uint8_t* dummy = nullptr;
+    return fuzz_batch_host(ctx, opts, data, off, n_blobs, n_cases, &dummy, out_buf, out_capacity, out_off, out_len, meta, stats);
+}
+
+static int fuzz_batch_host(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases,
+                           uint8_t** out_data, uint8_t* user_out, uint64_t user_cap, uint64_t* out_off, uint64_t* out_len, eb200_meta* meta, eb200_stats* stats) {
+    if (!ctx || !opts || !off || !out_data || !out_off || !out_len || n_blobs == 0) return EB200_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    *out_data = nullptr;
+    if (n_cases == 0) return EB200_OK;
+    uint64_t data_bytes = off[n_blobs];
+    if (data_bytes && !data) return EB200_ERR_ARG;
+    for (uint64_t b = 0; b < n_blobs; b++) if (off[b + 1] < off[b] || off[b + 1] - off[b] > 0xfffffff0ull) return EB200_ERR_ARG;
+    BatchParams bp; int rc = compute_batch_params(opts, n_blobs, n_cases, bp);
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    CK(ctx->data.ensure(data_bytes + 64));
+    CK(ctx->off.ensure((n_blobs + 1) * 8));
+    CK(ctx->out_off.ensure((n_cases + 1) * 8));
+    CK(ctx->out_len.ensure(n_cases * 8));
+    CK(ctx->meta.ensure(n_cases * sizeof(MetaDev)));
+    CK(cudaEventRecord(ctx->ev[5], st));
+    if (data_bytes) CK(cudaMemcpyAsync(ctx->data.p, data, data_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->off.p, off, (n_blobs + 1) * 8, cudaMemcpyHostToDevice, st));
+    uint32_t launches = 0; uint64_t total = 0;
+    rc = run_decide_scan(ctx, bp, opts, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, (uint64_t*)ctx->out_off.p,
+                         (uint64_t*)ctx->out_len.p, (eb200_meta*)ctx->meta.p, st, &total, &launches);
+    if (rc) return rc;
+    CK(ctx->out.ensure(total + 64));
+    rc = run_apply(ctx, n_cases, (const uint64_t*)ctx->out_off.p, (uint8_t*)ctx->out.p, ctx->out.cap, total, st, &launches);
+    if (rc) return rc;
+    uint8_t* host_out = user_out;
+    if (user_out) { if (total > user_cap) return EB200_ERR_NOMEM; }
+    else { host_out = (uint8_t*)malloc(total ? total : 1); if (!host_out) return EB200_ERR_NOMEM; }
+    cudaError_t e = cudaSuccess;
+    if (total) e = cudaMemcpyAsync(host_out, ctx->out.p, total, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_off, ctx->out_off.p, (n_cases + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_len, ctx->out_len.p, n_cases * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && meta) e = cudaMemcpyAsync(meta, ctx->meta.p, n_cases * sizeof(MetaDev), cudaMemcpyDeviceToHost, st);
+    cudaEvent_t evEnd = ctx->ev[4];
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { if (!user_out) free(host_out); ctx->last_err = cudaGetErrorString(e); return EB200_ERR_CUDA; }
+    *out_data = user_out ? nullptr : host_out;
+    if (stats) {
+        fill_stats(ctx, stats); cudaEventElapsedTime(&stats->ms_total, ctx->ev[5], evEnd);
+        stats->n_cases = n_cases; stats->kernels_launched = launches; stats->bytes_out = 0; stats->bytes_in = 0;
+        for (uint64_t k = 0; k < n_cases; k++) { stats->bytes_out += out_len[k]; uint64_t b = (bp.first_case - 1 + k) % n_blobs; stats->bytes_in += off[b + 1] - off[b]; }
+        if (meta) for (uint64_t k = 0; k < n_cases; k++) { if (meta[k].status == EB200_CASE_UNSUPPORTED) stats->n_unsupported++; else if (meta[k].status == EB200_CASE_DIED) stats->n_died++; else if (meta[k].status == EB200_CASE_OVERFLOW) stats->n_overflow++; }
+    }
+    return EB200_OK;
+}
+
+void eb200_free(void* p) { free(p); }
+
+const char* eb200_mutator_code(int i) { return (i >= 0 && i < EB200_N_MUTATORS) ? kMutCodes[i] : nullptr; }
+int eb200_mutator_default_pri(int i) { return (i >= 0 && i < EB200_N_MUTATORS) ? kMutPri[i] : -1; }
+int eb200_mutator_supported(int i) { return (i >= 0 && i < EB200_N_MUTATORS) ? (mut_supported(i) ? 1 : 0) : 0; }
+const char* eb200_pattern_code(int i) { return (i >= 0 && i < EB200_N_PATTERNS) ? kPatCodes[i] : nullptr; }
+int eb200_pattern_default_pri(int i) { return (i >= 0 && i < EB200_N_PATTERNS) ? kPatPri[i] : -1; }
+int eb200_pattern_supported(int i) { return (i >= 0 && i < EB200_N_PATTERNS) ? (pat_supported(i) ? 1 : 0) : 0; }
+
+const char* eb200_strerror(int code) {
+    switch (code) {
+    case EB200_OK: return "ok";
+    case EB200_ERR_CUDA: return "CUDA runtime error";
+    case EB200_ERR_ARG: return "bad argument";
+    case EB200_ERR_UNSUPPORTED: return "selected mutator/pattern has no device implementation";
+    case EB200_ERR_NOMEM: return "out of memory / output arena too small";
+    case EB200_ERR_SCRATCH: return "device scratch arena exhausted";
+    case EB200_ERR_NO_DEVICE: return "no CUDA device (the engine has no CPU fallback)";
+    default: return "unknown error";
+    }
+}
+const char* eb200_last_cuda_error(eb200_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
+const char* eb200_version(void) { return "erlamsa_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+"""Option handling that mirrors the reference's name surface.
+
+* mutator / pattern codes and default priorities: reference src/erlamsa_mutations.erl:1291-1331,
+  src/erlamsa_patterns.erl:395-404 (read back from the native library so there is one table);
+* the `-m` / `-p` grammar "code=pri,code,..." of erlamsa_cmdparse:string_to_actions/3
+  (reference src/erlamsa_cmdparse.erl:233-257): a bare code means priority 1;
+* the option-map keys read by erlamsa_main:fuzzer/1 (reference src/erlamsa_main.erl:127-163).
+"""
+from . import _native as N
+
+
+def mutator_codes():
+    L = N.lib()
+    return [L.eb200_mutator_code(i).decode() for i in range(N.N_MUTATORS)]
+
+
+def pattern_codes():
+    L = N.lib()
+    return [L.eb200_pattern_code(i).decode() for i in range(N.N_PATTERNS)]
+
+
+def default_mutations():
+    """erlamsa_mutations:default/1 -> [{Code, Pri}]"""
+    L = N.lib()
+    return [(L.eb200_mutator_code(i).decode(), L.eb200_mutator_default_pri(i)) for i in range(N.N_MUTATORS)]
+
+
+def default_patterns():
+    """erlamsa_patterns:default/0"""
+    L = N.lib()
+    return [(L.eb200_pattern_code(i).decode(), L.eb200_pattern_default_pri(i)) for i in range(N.N_PATTERNS)]
+
+
+def supported_mutations():
+    L = N.lib()
+    return [c for i, c in enumerate(mutator_codes()) if L.eb200_mutator_supported(i)]
+
+
+def supported_patterns():
+    L = N.lib()
+    return [c for i, c in enumerate(pattern_codes()) if L.eb200_pattern_supported(i)]
+
+
+def string_to_actions(s, what, defaults):
+    """"bd=2,num,sr=3" -> [("bd",2),("num",1),("sr",3)]; "default" keeps the table. Unknown names raise,
+    like the reference's `Unknown <what>` failure (src/erlamsa_cmdparse.erl:244-251)."""
+    if s == "default":
+        return list(defaults)
+    known = dict(defaults)
+    out = []
+    for tok in s.split(","):
+        if not tok:
+            continue
+        name, _, pri = tok.partition("=")
+        if name not in known:
+            raise ValueError("Unknown %s: %s" % (what, name))
+        out.append((name, int(pri) if pri else 1))
+    return out
+
+
+def make_opts(opts=None):
+    """Erlang-style option map (python dict with the reference's keys) -> native eb200_opts."""
+    opts = dict(opts or {})
+    o = N.Opts()
+    N.lib().eb200_default_opts(o)
+    if "seed" in opts:
+        a, b, c = opts["seed"]
+        o.seed[0], o.seed[1], o.seed[2] = int(a), int(b), int(c)
+    else:
+        # the reference falls back to gen_urandom_seed/0 (src/erlamsa_rnd.erl:50-62)
+        import os
+        r = os.urandom(6)
+        o.seed[0], o.seed[1], o.seed[2] = [int.from_bytes(r[i:i + 2], "big") for i in (0, 2, 4)]
+    o.blockscale = float(opts.get("blockscale", 1.0))
+    for key, codes, field, what in (("mutations", mutator_codes(), o.muta_pri, "mutation"),
+                                    ("patterns", pattern_codes(), o.pat_pri, "pattern")):
+        if key in opts:
+            sel = opts[key]
+            if isinstance(sel, str):
+                sel = string_to_actions(sel, what, default_mutations() if key == "mutations" else default_patterns())
+            sel = dict(sel)
+            for name in sel:
+                if name not in codes:
+                    raise ValueError("Unknown %s: %s" % (what, name))
+            for i, c in enumerate(codes):
+                field[i] = int(sel[c]) if c in sel else -1
+    if "generators" in opts:
+        g = dict(opts["generators"])
+        o.gen_direct_pri = int(g.get("direct", -1))
+        o.gen_random_pri = int(g.get("random", -1))
+    o.ssrf_host = str(opts.get("ssrf_host", "localhost")).encode()[:63]
+    o.ssrf_port = int(opts.get("ssrf_port", 51234))
+    o.rng_mode = {"as183": 0, "philox": 1}[opts.get("rng", "as183")]
+    o.first_case = int(opts.get("skip", 0)) + 1
+    if "first_case" in opts:
+        o.first_case = int(opts["first_case"])
+    o.max_case_out = int(opts.get("max_case_out", 0))
+    o.scratch_bytes = int(opts.get("scratch_bytes", 0))
+    return o

@@ -1,0 +1,37 @@
+"""A/B timing of engine build variants on the C3 workload (not a test; run on the GPU box).
+usage: python tests/perf_variants.py [n_variants] [cases]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import erlamsa_b200  # noqa: E402
+
+nvar = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+n_cases = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+size = 65536
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev); g.manual_seed(1)
+data = torch.randint(0, 256, (n_cases * size + 64,), dtype=torch.uint8, device=dev, generator=g)
+off = torch.arange(0, (n_cases + 1) * size, size, dtype=torch.int64, device=dev)
+out_cap = n_cases * size + 64 * n_cases + (64 << 20)
+d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
+d_off = torch.empty(n_cases + 1, dtype=torch.int64, device=dev)
+d_len = torch.empty(n_cases, dtype=torch.int64, device=dev)
+muts = {c: 1 for c in ("bd", "bei", "bed", "bf", "bi", "ber", "br", "num")}
+ndec = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+for v in range(nvar + ndec):
+    os.environ["EB200_APPLY_VARIANT"] = str(v if v < nvar else 0)
+    os.environ["EB200_DECIDE_VARIANT"] = str(0 if v < nvar else v - nvar)
+    eng = erlamsa_b200.Engine(0)
+    res = []
+    for i in range(6):
+        st = eng.fuzz_batch_device({"mutations": muts, "patterns": {"od": 1}, "seed": (1, 2, 3), "first_case": 1 + i * n_cases, "scratch_bytes": 256 << 20},
+                                   data.data_ptr(), off.data_ptr(), n_cases, n_cases * size, n_cases, d_out.data_ptr(), out_cap, d_off.data_ptr(),
+                                   d_len.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        res.append((st.ms_decide, st.ms_scan, st.ms_apply, st.ms_total))
+    res = res[2:]
+    avg = [sum(r[k] for r in res) / len(res) for k in range(4)]
+    gbs = (2 * n_cases * size) / (avg[2] * 1e-3) / 1e9
+    print("variant %d: decide %.3f  scan %.3f  apply %.3f ms (%.0f GB/s)  total %.3f" % (v, avg[0], avg[1], avg[2], gbs, avg[3]), flush=True)
+    eng.close()
