@@ -96,6 +96,9 @@ struct Arenas {
     uint8_t* scratch; uint64_t scratch_cap; unsigned long long* scratch_used;
     Seg* segs; uint64_t segs_cap; unsigned long long* segs_used;
     uint32_t* overflow;   // bit 0 scratch, bit 1 segs
+    // per-warp reusable temporaries (parse tables, stacks, sort keys): warp slot w owns
+    // temp + w * temp_per_warp; reset for every mutator attempt, never referenced by a result
+    uint8_t* temp; uint64_t temp_per_warp;
 };
 
 struct __align__(8) MetaDev {

@@ -102,6 +102,9 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
     realize_virtual(c);
     if (ws->status != CASE_OK) return;
     const uint8_t* p = ws->runs[0].p; uint32_t n = ws->runs[0].len;
+    if (ws->runs[0].cnt > 1) { c.has_next = 1; c.next_p = p + n; c.next_n = n; }
+    else if (ws->nruns > 1) { c.has_next = 1; c.next_p = ws->runs[1].p; c.next_n = ws->runs[1].len; }
+    else { c.has_next = 0; c.next_p = nullptr; c.next_n = 0; }
     int nr = ws->nrows;
     // weighted_permutations/1 :1244-1250: key_i = rand(trunc(Score*Pri)), stable sort by key descending
     for (int i = 0; i < nr; i++) ws->keys[i] = (uint32_t)g.rand((uint64_t)trunc(ws->rows[i].score * (double)ws->rows[i].pri));
@@ -118,6 +121,7 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
         MutResult r; r.kind = RES_SAME; r.delta = 0; r.rechunk = 0; r.consumed_next = 0;
         if (!big) {
             MutRow row = ws->rows[ws->order[t]];
+            temp_reset(c);
             mut_apply(c, row, p, n, r);
             if (r.kind == RES_UNSUPPORTED) ws->status = CASE_UNSUPPORTED;
             if (ws->status != CASE_OK) return;
@@ -126,6 +130,9 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
             if (r.kind == RES_SEGS) {
                 uint32_t first = (r.rechunk && ws->tlen >= AVG_BLOCK_SIZE) ? AVG_BLOCK_SIZE : ws->tlen;
                 changed = !(first == n && segs_equal_prefix(ws->tseg, ws->ntseg, p, n));
+            } else if (r.kind == RES_RUNS) {
+                Seg s0 = seg_copy(ws->rrun[0].p, ws->rrun[0].len);
+                changed = !(ws->rrun[0].len == n && segs_equal_prefix(&s0, 1, p, n));
             }
             if (!changed) { ws->n_failed++; continue; }
             if (ws->n_used < 16) ws->used[ws->n_used] = row.name;
@@ -141,6 +148,10 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
         // commit: the head block becomes the virtual result
         pop_head(ws);
         if (r.consumed_next && ws->nruns > 0) pop_head(ws);
+        if (r.kind == RES_RUNS) {
+            for (int j = ws->rrun_n - 1; j >= 0; j--) runs_insert_front(ws, ws->rrun[j]);
+            return;
+        }
         ws->vhead = 1; ws->vchunked = r.rechunk; ws->nvseg = ws->ntseg; ws->vlen = ws->tlen;
         for (int j = 0; j < ws->ntseg; j++) ws->vseg[j] = ws->tseg[j];
         return;
@@ -263,6 +274,8 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         uint64_t b = (I - 1) % bp.n_blobs;
         const uint8_t* blob = data + off[b]; uint32_t blen = (uint32_t)(off[b + 1] - off[b]);
         CaseCtx c; c.ws = ws; c.bp = &bp; c.ar = ar;
+        c.temp_base = ar.temp ? ar.temp + (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ar.temp_per_warp : nullptr;
+        c.temp_used = 0;
         // thread seed: three erand(99999) at parent draw index 3*(I-1) (the caller keeps the parent state there)
         Rng par; par.mode = 0; par.a1 = pa1; par.a2 = pa2; par.a3 = pa3; par.draws = 0; par.key = 0; par.ctr_hi = 0;
         int64_t ts0 = (int64_t)par.erand(99999), ts1 = (int64_t)par.erand(99999), ts2 = (int64_t)par.erand(99999);

@@ -48,7 +48,7 @@ struct eb200_ctx {
     int device = 0;
     int num_sms = 148;
     std::string last_err;
-    DevBuf cases, out_len, sz16, tile_sum, tile_case, counters, segs, scratch, data, off, out, out_off, meta;
+    DevBuf cases, out_len, sz16, tile_sum, tile_case, counters, segs, scratch, temp, data, off, out, out_off, meta;
     cudaEvent_t ev[6];
     bool funny_loaded = false;
     int apply_variant = 0;
@@ -204,7 +204,7 @@ int eb200_init(int device, eb200_ctx** out) {
 void eb200_shutdown(eb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta}) b->release();
+    for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->temp, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta}) b->release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     delete ctx;
 }
@@ -234,6 +234,18 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
         uint64_t want_ctas = (n + dv.warps - 1) / dv.warps;
         int grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * dv.ctas_per_sm);
         if (grid < 1) grid = 1;
+        ar.temp = nullptr; ar.temp_per_warp = 0;
+        bool needs_temp = false;
+        for (int i = 0; i < bp.n_rows; i++) needs_temp |= mut_needs_temp(bp.row_id[i]);
+        if (needs_temp) {   // parse tables are proportional to the block being mutated: size the per-warp region from the mean blob
+            uint64_t mean = bp.n_blobs ? data_bytes / bp.n_blobs : 0;
+            uint64_t per = std::min<uint64_t>(std::max<uint64_t>(64 * mean, 256u << 10), 16u << 20);
+            per = (per + 255) & ~255ull;
+            uint64_t nw = (uint64_t)grid * dv.warps;
+            while (per > (256u << 10) && per * nw > (24ull << 30)) per >>= 1;
+            CK(ctx->temp.ensure(per * nw + 256));
+            ar.temp = (uint8_t*)ctx->temp.p; ar.temp_per_warp = per;
+        }
         CK(cudaEventRecord(ctx->ev[0], st));
         dv.launch(grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta);
         CK(cudaGetLastError());

@@ -1,0 +1,186 @@
+// erlamsa_b200 -- the fuse mutators ft fn fo on the device (reference src/erlamsa_mutations.erl:386-427
+// over src/erlamsa_fuse.erl:47-135).
+//
+// fuse(A, B) = prefix of A up to i ++ suffix of B from j, where the k bytes before i and before j are
+// equal; k grows level by level (each level stops with probability 1/8) and the pair (i, j) is drawn
+// by index from ORDERED lists, so exact parity needs the reference's list orders, not just its sets:
+//   * a node = (source suffixes, target suffixes) sharing the bytes consumed so far; suffix = start
+//     position, the empty suffix = len;
+//   * char_suffixes/1 (:62-70) files each suffix's tail under its first byte, newest first (so every
+//     level reverses the order inside a class) -- a stable counting sort written back to front;
+//     the quirk fix_empty_list ([[]] -> []) drops the empty tail when it is the first of its class;
+//   * split/2 (:85-100) walks the classes in ascending byte order and PREPENDS the children, so a
+//     level's node list is the emission order reversed.
+// Positions are kept in ping-pong arrays per side in the warp's temp region; the automaton is run
+// warp-uniformly (all lanes compute and store the same values, each lane reads back its own stores).
+#pragma once
+#include "eb_state.cuh"
+
+namespace eb {
+
+struct FNode { uint32_t fo, fc, to, tc; };
+
+struct FuseSide {
+    const uint8_t* s; uint32_t len;
+    uint32_t* cnt;     // [256] per-class element count; all zero between nodes
+    uint32_t* start;   // [256] class start inside the next-level array
+    uint32_t bits[8];  // classes that exist for the node being split (possibly with an empty list)
+    uint32_t size[8];  // scratch: unused
+};
+
+// One node, one side: classify the suffix list src[0,k) by first byte into dst[base ...), classes in ascending
+// byte order, each class newest-first. After the call: bits = existing classes, start[c]/cnt2[c] describe class c.
+// `csize` (256 entries) receives the class sizes (cnt is consumed back to zero by the placement walk).
+EB_DEV uint32_t fuse_classify(FuseSide& sd, const uint32_t* src, uint32_t k, uint32_t* dst, uint32_t base, uint32_t* csize) {
+    for (int i = 0; i < 8; i++) sd.bits[i] = 0;
+    bool special_dropped = false;
+    for (uint32_t q = 0; q < k; q++) {                 // count
+        uint32_t p = src[q];
+        if (p >= sd.len) continue;                      // the [] suffix contributes nothing (:68)
+        uint32_t ch = sd.s[p];
+        sd.bits[ch >> 5] |= 1u << (ch & 31);
+        if (p + 1 == sd.len && sd.cnt[ch] == 0) { special_dropped = true; continue; }   // [[]] -> []
+        sd.cnt[ch] = sd.cnt[ch] + 1;
+    }
+    uint32_t run = base;
+    for (int w = 0; w < 8; w++) {                       // class starts, ascending byte
+        uint32_t m = sd.bits[w];
+        while (m) { uint32_t b = (uint32_t)__ffs(m) - 1; m &= m - 1; uint32_t ch = (uint32_t)w * 32 + b; sd.start[ch] = run; csize[ch] = sd.cnt[ch]; run += sd.cnt[ch]; }
+    }
+    for (uint32_t q = 0; q < k; q++) {                 // place: first arrival lands last in its class
+        uint32_t p = src[q];
+        if (p >= sd.len) continue;
+        if (p + 1 == sd.len && special_dropped) continue;
+        uint32_t ch = sd.s[p];
+        uint32_t c2 = sd.cnt[ch] - 1; sd.cnt[ch] = c2;
+        dst[sd.start[ch] + c2] = p + 1;
+    }
+    return run - base;
+}
+
+// find_jump_points/2 :103-128 + any_position_pair/1 :73-77
+EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb, uint32_t& from, uint32_t& to) {
+    Rng& g = c.rng;
+    uint64_t fcap = (uint64_t)na + 80, tcap = (uint64_t)nb + 80, ncap = (uint64_t)(na < nb ? na : nb) + 80;
+    uint32_t* F[2]; uint32_t* T[2]; FNode* ND[2];
+    for (int i = 0; i < 2; i++) { F[i] = (uint32_t*)temp_alloc(c, fcap * 4); T[i] = (uint32_t*)temp_alloc(c, tcap * 4); ND[i] = (FNode*)temp_alloc(c, ncap * sizeof(FNode)); }
+    uint32_t* tabs = (uint32_t*)temp_alloc(c, 6 * 256 * 4);
+    if (!F[0] || !F[1] || !T[0] || !T[1] || !ND[0] || !ND[1] || !tabs) return false;
+    FuseSide sa, sb; sa.s = a; sa.len = na; sa.cnt = tabs; sa.start = tabs + 256; sb.s = b; sb.len = nb; sb.cnt = tabs + 512; sb.start = tabs + 768;
+    uint32_t* sizeA = tabs + 1024; uint32_t* sizeB = tabs + 1280;
+    for (uint32_t i = lane_id(); i < 256; i += 32) { sa.cnt[i] = 0; sb.cnt[i] = 0; }
+    for (uint32_t i = lane_id(); i < na; i += 32) F[0][i] = i;
+    for (uint32_t i = lane_id(); i < nb; i += 32) T[0][i] = i;
+    __syncwarp();
+    int cur = 0; uint32_t ncur = 1;
+    { FNode r0; r0.fo = 0; r0.fc = na; r0.to = 0; r0.tc = nb; ND[0][0] = r0; }
+    int64_t fuel = 100000;
+    for (;;) {
+        bool stop = fuel < 0;
+        if (!stop) stop = g.rand(8) == 0;
+        uint32_t nnext = 0;
+        if (!stop) {
+            int nx = cur ^ 1; uint32_t fo = 0, to = 0;
+            // nodes are stored in emission order; the reference's list is that order reversed
+            for (uint32_t e = ncur; e-- > 0;) {
+                FNode nd = ND[cur][e];
+                uint32_t fa = fuse_classify(sa, F[cur] + nd.fo, nd.fc, F[nx], fo, sizeA);
+                uint32_t tb = fuse_classify(sb, T[cur] + nd.to, nd.tc, T[nx], to, sizeB);
+                for (int w = 0; w < 8; w++) {
+                    uint32_t m = sa.bits[w];
+                    while (m) {
+                        uint32_t bit = (uint32_t)__ffs(m) - 1; m &= m - 1; uint32_t ch = (uint32_t)w * 32 + bit;
+                        FNode ch_n;
+                        if (sizeA[ch] == 0) {       // {_Char, []} -> [[[]], []]: the two empty suffixes, whatever B holds (:91-93)
+                            if (fo + fa + 1 > fcap || to + tb + 1 > tcap || nnext >= ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
+                            F[nx][fo + fa] = na; T[nx][to + tb] = nb;
+                            ch_n.fo = fo + fa; ch_n.fc = 1; ch_n.to = to + tb; ch_n.tc = 1; fa++; tb++;
+                            ND[nx][nnext++] = ch_n; continue;
+                        }
+                        if (!((sb.bits[w] >> bit) & 1u)) continue;                     // notfound
+                        if (nnext >= ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
+                        ch_n.fo = sa.start[ch]; ch_n.fc = sizeA[ch]; ch_n.to = sb.start[ch]; ch_n.tc = sizeB[ch];
+                        ND[nx][nnext++] = ch_n;
+                    }
+                }
+                fo += fa; to += tb;
+            }
+            if (nnext == 0) stop = true;
+            else { fuel -= (int64_t)nnext; cur = nx; ncur = nnext; continue; }
+        }
+        // any_position_pair(Nodes)
+        uint32_t r = (uint32_t)g.rand_elem_idx(ncur);
+        FNode nd = ND[cur][ncur - 1 - r];
+        int64_t fi = g.rand_elem_idx(nd.fc);
+        from = fi < 0 ? na : F[cur][nd.fo + (uint32_t)fi];
+        int64_t ti = g.rand_elem_idx(nd.tc);
+        to = ti < 0 ? nb : T[cur][nd.to + (uint32_t)ti];
+        return true;
+    }
+}
+
+// fuse/2 :130-135 as an edit script: pushes A[0,i) and B[j,nb) to tseg
+EB_DEV bool fuse_push(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb) {
+    WarpState* ws = c.ws;
+    if (na == 0) { t_push(ws, seg_copy(b, nb)); return true; }
+    if (nb == 0) { t_push(ws, seg_copy(a, na)); return true; }
+    uint32_t from, to;
+    uint64_t mark = c.temp_used;
+    bool ok = fuse_device(c, a, na, b, nb, from, to);
+    c.temp_used = mark;                       // the level tables die here
+    if (!ok) return false;
+    t_push(ws, seg_copy(a, from)); t_push(ws, seg_copy(b + to, nb - to));
+    return true;
+}
+// materialise the candidate script into scratch (the second fuse of fn/fo reads the first one's bytes)
+EB_DEV const uint8_t* tseg_to_scratch(CaseCtx& c, uint32_t& len) {
+    WarpState* ws = c.ws;
+    len = ws->tlen;
+    uint8_t* buf = scratch_alloc(c, len);
+    if (!buf) return nullptr;
+    segs_write(ws->tseg, ws->ntseg, buf);
+    return buf;
+}
+
+EB_DEV void mut_fuse(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutResult& r) {
+    WarpState* ws = c.ws; Rng& g = c.rng;
+    r.rechunk = 0; r.consumed_next = 0; r.kind = RES_SEGS;
+    t_reset(ws);
+    if (id == M_FT) {   // sed_fuse_this :386-390
+        if (!fuse_push(c, p, n, p, n)) { r.kind = RES_SAME; r.delta = 0; return; }
+        r.delta = g.rand_delta(); return;
+    }
+    uint32_t h1 = n / 2;   // erlamsa_utils:halve/1: the first half is floor(n/2)
+    if (id == M_FN) {   // sed_fuse_next :393-402
+        const uint8_t* bp = c.has_next ? c.next_p : p; uint32_t bn = c.has_next ? c.next_n : n;
+        if (!fuse_push(c, p, h1, bp, bn)) { r.kind = RES_SAME; r.delta = 0; return; }
+        uint32_t abl_n; const uint8_t* abl = tseg_to_scratch(c, abl_n);
+        if (!abl) { r.kind = RES_SAME; r.delta = 0; return; }
+        t_reset(ws);
+        if (!fuse_push(c, abl, abl_n, p + h1, n - h1)) { r.kind = RES_SAME; r.delta = 0; return; }
+        r.delta = g.rand_delta(); r.rechunk = 1; r.consumed_next = c.has_next ? 1 : 0;
+        return;
+    }
+    // sed_fuse_old :404-427 -- remember/1 closure: the first call remembers H itself
+    if (!ws->fo_has) { ws->fo_has = 1; ws->fo_p = p; ws->fo_n = n; }
+    const uint8_t* op = ws->fo_p; uint32_t on = ws->fo_n; uint32_t o1 = on / 2;
+    if (!fuse_push(c, p, h1, op, o1)) { r.kind = RES_SAME; r.delta = 0; return; }          // a -> o
+    uint32_t an; const uint8_t* ab = tseg_to_scratch(c, an);
+    if (!ab) { r.kind = RES_SAME; r.delta = 0; return; }
+    t_reset(ws);
+    if (!fuse_push(c, op + o1, on - o1, p + h1, n - h1)) { r.kind = RES_SAME; r.delta = 0; return; }   // o -> a
+    uint32_t bn2; const uint8_t* bb = tseg_to_scratch(c, bn2);
+    if (!bb) { r.kind = RES_SAME; r.delta = 0; return; }
+    uint64_t swap = g.rand(3);
+    r.delta = g.rand_delta();
+    if (swap == 0) { ws->fo_p = p; ws->fo_n = n; }
+    // flush_bvecs(A, flush_bvecs(B, T)): two re-chunked regions -> handed back as block runs
+    ws->rrun_n = 0;
+    { uint32_t k = an / AVG_BLOCK_SIZE; Blk f; f.p = ab; f.len = AVG_BLOCK_SIZE; f.cnt = k; if (k) ws->rrun[ws->rrun_n++] = f;
+      Blk l; l.p = ab + (uint64_t)k * AVG_BLOCK_SIZE; l.len = an - k * AVG_BLOCK_SIZE; l.cnt = 1; ws->rrun[ws->rrun_n++] = l; }
+    { uint32_t k = bn2 / AVG_BLOCK_SIZE; Blk f; f.p = bb; f.len = AVG_BLOCK_SIZE; f.cnt = k; if (k) ws->rrun[ws->rrun_n++] = f;
+      Blk l; l.p = bb + (uint64_t)k * AVG_BLOCK_SIZE; l.len = bn2 - k * AVG_BLOCK_SIZE; l.cnt = 1; ws->rrun[ws->rrun_n++] = l; }
+    r.kind = RES_RUNS;
+}
+
+}  // namespace eb

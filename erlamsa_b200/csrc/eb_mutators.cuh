@@ -12,7 +12,7 @@
 
 namespace eb {
 
-enum { RES_SAME = 0, RES_SEGS = 1, RES_UNSUPPORTED = 2 };
+enum { RES_SAME = 0, RES_SEGS = 1, RES_UNSUPPORTED = 2, RES_RUNS = 3 };
 struct MutResult { int kind; double delta; int rechunk; int consumed_next; };
 
 // funny_unicode/0 table (reference :1052-1078), built on the host at init
@@ -310,9 +310,24 @@ EB_DEV void mut_st_line(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutRes
     r.delta = 1; r.kind = RES_SEGS;
 }
 
+}  // namespace eb
+#include "eb_mut_text.cuh"
+#include "eb_mut_tree.cuh"
+#include "eb_mut_fuse.cuh"
+namespace eb {
+
+// mutators whose working tables live in the per-warp temp arena
+__host__ __device__ inline bool mut_needs_temp(int id) {
+    switch (id) {
+    case M_AB: case M_AD: case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: case M_FT: case M_FN: case M_FO: return true;
+    default: return false;
+    }
+}
+
 // which mutators have a device implementation
 __host__ EB_DEV bool mut_supported(int id) {
     switch (id) {
+    case M_AB: case M_AD: case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: case M_FT: case M_FN: case M_FO:
     case M_UW: case M_UI: case M_NUM:
     case M_BD: case M_BEI: case M_BED: case M_BF: case M_BI: case M_BER: case M_BR:
     case M_SP: case M_SR: case M_SD: case M_SNAND: case M_SRND:
@@ -328,6 +343,9 @@ EB_DEV void mut_apply(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, Mut
     case M_BD: case M_BEI: case M_BED: case M_BF: case M_BI: case M_BER: case M_BR: case M_UW: case M_UI: mut_byte(c, id, p, n, r); return;
     case M_SP: case M_SR: case M_SD: case M_SNAND: case M_SRND: mut_bytes(c, id, p, n, r); return;
     case M_NUM: mut_num(c, p, n, r); return;
+    case M_AB: case M_AD: mut_ascii(c, id, p, n, r); return;
+    case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: mut_tree(c, id, p, n, r); return;
+    case M_FT: case M_FN: case M_FO: mut_fuse(c, id, p, n, r); return;
     case M_LD: case M_LDS: case M_LR2: case M_LRI: case M_LR: case M_LS: case M_LP: mut_line(c, id, p, n, r); return;
     case M_LIS: case M_LRS: mut_st_line(c, id, p, n, r); return;
     case M_NIL: r.kind = RES_SAME; r.delta = -1; r.rechunk = 0; r.consumed_next = 0; return;

@@ -40,6 +40,8 @@ struct WarpState {
     Seg oseg[MAX_OSEG]; int noseg; uint64_t olen;
     // closure state: construct_st_line_muta (lis = 0, lrs = 1), remember/1 of sed_fuse_old
     StSlot st[2][10]; int st_n[2];
+    // RES_RUNS results: the new head is handed back as real block runs (fo: two re-chunked regions)
+    Blk rrun[4]; int rrun_n;
     const uint8_t* fo_p; uint32_t fo_n; int fo_has;
     uint16_t sc[SC_MAX];
     uint32_t status; uint32_t reason;
@@ -51,6 +53,9 @@ struct CaseCtx {
     Rng rng;
     const BatchParams* bp;
     Arenas ar;
+    const uint8_t* next_p; uint32_t next_n; int has_next;   // the block after This (sed_fuse_next reads it)
+    uint8_t* temp_base;      // this warp's reusable temp region
+    uint64_t temp_used;
 };
 
 // ------------------------------------------------------------------ arenas
@@ -65,6 +70,15 @@ EB_DEV uint8_t* scratch_alloc(CaseCtx& c, uint64_t bytes) {
         return nullptr;
     }
     return c.ar.scratch + off;
+}
+
+// temporaries that die with the mutator attempt: bump inside the warp's private region, spilling to
+// the (never freed) scratch arena only when a single attempt needs more than the region holds
+EB_DEV void temp_reset(CaseCtx& c) { c.temp_used = 0; }
+EB_DEV uint8_t* temp_alloc(CaseCtx& c, uint64_t bytes) {
+    uint64_t need = align16(bytes) + 16;
+    if (c.temp_base && c.temp_used + need <= c.ar.temp_per_warp) { uint8_t* p = c.temp_base + c.temp_used; c.temp_used += need; return p; }
+    return scratch_alloc(c, bytes);
 }
 
 // ------------------------------------------------------------------ segment constructors

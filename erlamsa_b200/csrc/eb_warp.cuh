@@ -92,10 +92,14 @@ __device__ __forceinline__ uint32_t bytemask4(uint32_t cmp) {   // 0xFF/0x00 per
 //   newline : t = b ^ 0x0a is zero   <=>  bit 7 of ((t & 0x7f) + 0x7f) | t is clear
 // (no carries cross byte lanes: 0x7f + 0x7f < 0x100); the four bit-7 flags are then gathered with one multiply.
 template <int PRED>
-__device__ __forceinline__ uint32_t pred4(uint32_t w) {
+__device__ __forceinline__ uint32_t pred_flags(uint32_t w) {   // bit 7 of each byte = predicate
     uint32_t t = w ^ (PRED == PRED_DIGIT ? 0x30303030u : 0x0a0a0a0au);
     uint32_t u = ((t & 0x7f7f7f7fu) + (PRED == PRED_DIGIT ? 0x76767676u : 0x7f7f7f7fu)) | t;
-    uint32_t f = (~u & 0x80808080u) >> 7;          // bits 0, 8, 16, 24
+    return ~u & 0x80808080u;
+}
+template <int PRED>
+__device__ __forceinline__ uint32_t pred4(uint32_t w) {
+    uint32_t f = pred_flags<PRED>(w) >> 7;         // bits 0, 8, 16, 24
     return (f * 0x01020408u) >> 24;                // -> bits 0..3
 }
 template <int PRED>
@@ -157,8 +161,27 @@ __device__ __noinline__ uint32_t scan_count(const uint8_t* p, uint32_t n, uint16
 #pragma unroll
         for (int j = 0; j < 8; j++) w[j] = scan_chunk_load(c, it0 + j);
         uint32_t acc = 0;
+        if (it0 * 512u >= c.lead && (it0 + 8) * 512u <= c.span) {
+            // interior superchunk: every byte is valid, so count straight on the bit-7 byte flags
+            // (no validity masks, no packing): ~33 integer ops per 16-byte word instead of ~70
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc += __popc(scan_chunk_reduce<PRED, RUNSTART>(c, it0 + j, w[j], carry));
+            for (int j = 0; j < 8; j++) {
+                uint32_t f0 = pred_flags<PRED>(w[j].x), f1 = pred_flags<PRED>(w[j].y), f2 = pred_flags<PRED>(w[j].z), f3 = pred_flags<PRED>(w[j].w);
+                if (RUNSTART) {
+                    uint32_t top = f3 >> 24;                                  // last byte's flag, moved to bit 7
+                    uint32_t prev = __shfl_up_sync(0xffffffffu, top, 1);
+                    if (lane_id() == 0) prev = carry << 7;
+                    carry = __shfl_sync(0xffffffffu, top, 31) >> 7;
+                    uint32_t s0 = f0 & ~((f0 << 8) | prev), s1 = f1 & ~((f1 << 8) | (f0 >> 24)), s2 = f2 & ~((f2 << 8) | (f1 >> 24)), s3 = f3 & ~((f3 << 8) | (f2 >> 24));
+                    acc += __popc((s0 >> 7) | (s1 >> 6) | (s2 >> 5) | (s3 >> 4));
+                } else {
+                    acc += __popc((f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc += __popc(scan_chunk_reduce<PRED, RUNSTART>(c, it0 + j, w[j], carry));
+        }
         uint32_t s = warp_sum(acc); total += s;
         if (lane_id() == 0) sc[it0 >> 3] = (uint16_t)s;
     }

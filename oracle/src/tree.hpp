@@ -98,7 +98,10 @@ constexpr size_t STUTTER_MEM_CAP = 64u << 20;   // stands in for the 256 MB proc
 
 // repeat_path/3 :974-985, emitted flattened
 inline void repeat_path_emit(const Term& parent, const Term& child, uint64_t n, Bin& out) {
-    if (n < 2 || out.size() > STUTTER_MEM_CAP) { flatten_into(parent, out); return; }
+    // the reference stops nesting when the BEAM process passes 256 MB (non-deterministic); the restatement
+    // refuses such blow-ups instead of guessing where the guard would have fired
+    if (out.size() > STUTTER_MEM_CAP) throw Unsupported("tree stutter blow-up beyond the memory guard");
+    if (n < 2) { flatten_into(parent, out); return; }
     auto op = [&](const std::vector<Term>& l, size_t i, Bin& o) { repeat_path_emit(parent, child, n - 1, o); flatten_tail(l, i + 1, o); };
     edit_sublist_emit(parent.k, &child, op, out);
 }

@@ -47,6 +47,21 @@ def test_single_mutator_od(engine, oracle, code):
     assert n == len(blobs)
 
 
+@pytest.mark.parametrize("code", ["ab", "ad", "tr2", "td", "ts1", "ts2", "tr", "ft", "fn", "fo"])
+def test_structure_mutators_od(engine, oracle, code):
+    """strlex / parse-tree / fuse mutators on quoted, bracketed, line-structured text (plus binary and tiny blobs)"""
+    blobs = corpus.text_corpus(0xE21A0500 + len(code), 200) + corpus.mixed_corpus(0xE21A0600, 40, 400)
+    n = compare(engine, oracle, blobs, {code: 1}, {"od": 1}, seed=(3, 1, 4))
+    assert n >= len(blobs) - 4
+
+
+def test_structure_mutators_multi_round(engine, oracle):
+    """closure state (fo's remembered block, lis/lrs slots) and re-chunked block lists across nd / bu rounds"""
+    muts = {c: 1 for c in ("ab", "ad", "tr2", "td", "ts1", "ts2", "tr", "ft", "fn", "fo", "num", "lis", "bd")}
+    blobs = corpus.text_corpus(0xE21A0700, 300, 900)
+    compare(engine, oracle, blobs, muts, {"nd": 2, "bu": 1, "od": 1}, seed=(2, 7, 1), allow_unsupported=True)
+
+
 @pytest.mark.parametrize("pat", ["od", "nd", "bu", "sk", "co", "nu"])
 def test_patterns_with_mix(engine, oracle, pat):
     import erlamsa_b200
