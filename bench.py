@@ -36,6 +36,21 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the apply kernel from the committed ncu capture of this
+    workload (profiles/apply_<tag>.txt, `ncu --set full`, one launch); None when there is no capture for it."""
+    tag = {"c3": "apply_r1b.txt"}.get(workload)
+    p = os.path.join(ROOT, "profiles", tag) if tag else None
+    if not p or not os.path.exists(p):
+        return None
+    tot = 0.0
+    for ln in open(p):
+        f = ln.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(f[2], 1.0)
+    return tot or None
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -210,7 +225,8 @@ def run_ours(args):
                    "parallelism": "cases sharded by id, no collective"},
         "gb_per_s_mutated": (data_bytes + out_len_sum) * world * args.steps / (ms * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": "eb_apply_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": avg_apply},
+                     "traffic": ncu_traffic(args.workload) if not args.cases else None, "traffic_source": "ncu --set full capture, profiles/apply_r1b.txt",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": avg_apply},
         "kernel_ms": {"decide": sum(decide_ms) / len(decide_ms), "scan": sum(scan_ms) / len(scan_ms), "apply": avg_apply},
         "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
     }
@@ -276,9 +292,12 @@ def run_reference(args):
         muts = {c: 1 for c in muts}
     threads = os.cpu_count() or 1
     blobs = cpu_corpus(kind, 64, size, 0xE21A0003)
-    dt, _ = cpu_run(blobs, muts, pats, 16 * threads, 1, threads)
-    rate = 16 * threads / dt
-    per_step = max(threads, int(rate * 4.0))          # ~4 s of CPU work per step
+    # calibrate in two rounds so that thread start-up does not dominate the estimate, then give every step ~3 s of wall time
+    dt, _ = cpu_run(blobs, muts, pats, 32 * threads, 1, threads)
+    rate = 32 * threads / dt
+    dt, _ = cpu_run(blobs, muts, pats, max(32 * threads, int(rate * 1.0)), 1, threads)
+    rate = max(32 * threads, int(rate * 1.0)) / dt
+    per_step = max(threads, int(rate * 3.0))
     for i in range(args.warmup):
         cpu_run(blobs, muts, pats, max(threads, per_step // 8), 1 + i * per_step, threads)
     t_total = 0.0

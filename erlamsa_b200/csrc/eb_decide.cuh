@@ -135,6 +135,7 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
                 changed = !(ws->rrun[0].len == n && segs_equal_prefix(&s0, 1, p, n));
             }
             if (!changed) { ws->n_failed++; continue; }
+            if (r.kind == RES_SEGS && ws->tlen > c.bp->max_case_out) { ws->status = CASE_OVERFLOW; ws->reason = 5; return; }
             if (ws->n_used < 16) ws->used[ws->n_used] = row.name;
             ws->n_used++;
         }
@@ -195,10 +196,78 @@ EB_DEV void generate(CaseCtx& c, const uint8_t* blob, uint32_t blen) {
     }
 }
 
+// ------------------------------------------------------------------ sizer / checksum wrappers (patterns sz, cs)
+// checksum of output bytes [from, olen) of the (virtual) output edit script
+EB_DEV uint32_t oseg_checksum(CaseCtx& c, uint64_t from, bool crc) {
+    WarpState* ws = c.ws; int l = lane_id();
+    uint64_t pos = 0; uint32_t x = 0; uint32_t acc = 0;
+    for (int k = 0; k < ws->noseg; k++) {
+        Seg s = ws->oseg[k]; uint64_t b = pos, e = pos + s.len; pos = e;
+        if (e <= from) continue;
+        uint32_t o = b < from ? (uint32_t)(from - b) : 0; uint32_t len = s.len - o;
+        if (!crc) {
+            uint32_t y = 0;
+            if (s.kind() == SEG_COPY) { const uint8_t* q = (const uint8_t*)(uintptr_t)s.src + o; for (uint32_t i = l; i < len; i += 32) y ^= q[i]; }
+            else for (uint32_t i = l; i < len; i += 32) y ^= segs_byte(&s, 1, o + i);
+            x ^= y;
+        } else {
+            uint32_t cs;
+            if (s.kind() == SEG_COPY) cs = warp_crc32((const uint8_t*)(uintptr_t)s.src + o, len);
+            else { uint32_t r = 0xffffffffu; for (uint32_t i = 0; i < len; i++) r = crc32_byte(r, segs_byte(&s, 1, o + i)); cs = ~r; }
+            if (len) acc = crc_combine(acc, cs, len);
+        }
+    }
+    if (crc) return acc;
+    for (int o = 16; o; o >>= 1) x ^= __shfl_xor_sync(0xffffffffu, x, o);
+    return x & 0xff;
+}
+// overwrite `nb` output bytes at offset `at` (a placeholder emitted earlier) with `bytes` (little-endian packed)
+EB_DEV void oseg_patch(CaseCtx& c, uint64_t at, uint64_t bytes, uint32_t nb) {
+    WarpState* ws = c.ws; uint64_t pos = 0;
+    for (int k = 0; k < ws->noseg; k++) {
+        Seg& s = ws->oseg[k]; uint64_t b = pos, e = pos + s.len; pos = e;
+        if (at < b || at >= e) continue;
+        if (s.kind() == SEG_INLINE && at == b && s.len == nb) { s.src = bytes; return; }
+        if (s.kind() == SEG_COPY && at + nb <= e) {   // the script was folded into scratch meanwhile: patch the bytes in place
+            uint8_t* q = (uint8_t*)(uintptr_t)s.src + (at - b);
+            if ((uint32_t)lane_id() < nb) q[lane_id()] = (uint8_t)(bytes >> (8 * lane_id()));
+            __syncwarp(); return;
+        }
+        ws->status = CASE_OVERFLOW; ws->reason = 10; return;
+    }
+}
+// unwind innermost first: sz patches its length field with the size of everything emitted since, then emits the
+// bytes that followed the blob; cs appends the checksum of the new blob (rebuild_blob / recalc_csum)
+EB_DEV void unwind_wrappers(CaseCtx& c) {
+    WarpState* ws = c.ws;
+    while (ws->nwrap > 0 && ws->status == CASE_OK) {
+        WarpState::Wrap w = ws->wrap[--ws->nwrap];
+        if (w.kind == 1) {
+            uint64_t newlen = ws->olen - w.mark;
+            oseg_patch(c, w.field_pos, enc_field(newlen, w.bits, w.big != 0), w.bits / 8);
+            o_push(c, seg_copy(w.tail_p, w.tail_n));
+        } else {
+            uint32_t v = oseg_checksum(c, w.mark, w.kind == 3);
+            if (w.kind == 3) o_push(c, seg_inline(enc_field(v, 32, true), 4)); else o_push(c, seg_inline(v, 1));
+        }
+    }
+}
+EB_DEV bool looks_like_zip(const uint8_t* p, uint32_t n) {   // an end-of-central-directory signature anywhere
+    uint32_t hit = 0;
+    for (uint32_t i = lane_id(); i + 4 <= n; i += 32) hit |= (p[i] == 'P' && p[i + 1] == 'K' && p[i + 2] == 5 && p[i + 3] == 6) ? 1u : 0u;
+    return __any_sync(0xffffffffu, hit != 0);
+}
+EB_DEV bool maybe_compressed(const uint8_t* p, uint32_t n) {   // gzip magic or a plausible zlib header
+    if (n < 2) return false;
+    uint32_t a = p[0], b = p[1];
+    if (a == 0x1f && b == 0x8b) return true;
+    return (a & 15) == 8 && (a >> 4) <= 7 && ((a << 8) | b) % 31 == 0;
+}
+
 // ------------------------------------------------------------------ pattern state machine
 enum { CONT_OD = 0, CONT_ND = 1, CONT_BU = 2, CONT_PAT = 3 };
 
-__host__ EB_DEV bool pat_supported(int id) { return id == P_OD || id == P_ND || id == P_BU || id == P_SK || id == P_CO || id == P_NU; }
+__host__ EB_DEV bool pat_supported(int id) { return id >= 0 && id < P_COUNT; }
 
 EB_DEV void run_case_machine(CaseCtx& c, int pat) {
     WarpState* ws = c.ws; Rng& g = c.rng;
@@ -227,6 +296,70 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             o_push(c, seg_copy(ws->runs[0].p, len));
             Blk tail; tail.p = ws->runs[0].p + len; tail.len = n0 - len; tail.cnt = 1;
             pop_head(ws); runs_insert_front(ws, tail);
+            split_big(c);
+            cont = CONT_PAT;
+        } else if (pat == P_SZ || pat == P_CS) {
+            // make_complex_pat + mutate_once_sizer :83-111 / mutate_once_csum :117-144
+            next = (int)g.rand_elem_idx(P_COUNT);
+            ip = g.rand(INITIAL_IP);
+            if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
+            realize_virtual(c);
+            if (ws->status != CASE_OK) return;
+            const uint8_t* p0 = ws->runs[0].p; uint32_t n0 = ws->runs[0].len;
+            temp_reset(c);
+            if (ws->nwrap >= 8) { ws->status = CASE_OVERFLOW; ws->reason = 9; return; }
+            WarpState::Wrap w; w.tail_p = nullptr; w.tail_n = 0; w.bits = 0; w.big = 0; w.field_pos = 0;
+            bool found = false; uint32_t b0 = 0, bl = 0;
+            if (pat == P_SZ) {
+                Sizer e; found = lens_pick(c, p0, n0, e);
+                if (found) {
+                    uint32_t fb = e.size_bits / 8; b0 = e.a + fb; bl = (uint32_t)e.len;
+                    o_push(c, seg_copy(p0, e.a));
+                    w.kind = 1; w.bits = e.size_bits; w.big = e.big; w.field_pos = ws->olen;
+                    o_push(c, seg_inline(0, fb));
+                    w.tail_p = p0 + b0 + bl; w.tail_n = n0 - b0 - bl;
+                }
+            } else {
+                Csum e; found = csum_pick(c, p0, n0, e);
+                if (found) { b0 = e.plen; bl = e.blen; o_push(c, seg_copy(p0, e.plen)); w.kind = e.crc ? 3 : 2; }
+            }
+            if (ws->status != CASE_OK) return;
+            if (found) {
+                w.mark = ws->olen;
+                ws->wrap[ws->nwrap++] = w;
+                Blk blob; blob.p = p0 + b0; blob.len = bl; blob.cnt = 1;
+                pop_head(ws); runs_insert_front(ws, blob);
+            }
+            split_big(c);
+            cont = CONT_PAT;
+        } else if (pat == P_AR) {
+            // mutate_once_archiver :167-214 on data that is not a ZIP archive: all blocks are glued into one
+            next = (int)g.rand_elem_idx(P_COUNT);
+            ip = g.rand(INITIAL_IP);
+            if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
+            realize_virtual(c);
+            if (ws->status != CASE_OK) return;
+            if (active_count(ws) > 1) {
+                uint64_t tot = 0; for (int i = 0; i < ws->nruns; i++) tot += (uint64_t)ws->runs[i].len * ws->runs[i].cnt;
+                if (tot > c.bp->max_case_out) { ws->status = CASE_OVERFLOW; ws->reason = 5; return; }
+                uint8_t* buf = scratch_alloc(c, tot);
+                if (!buf) return;
+                uint8_t* wq = buf;
+                for (int i = 0; i < ws->nruns; i++) { uint64_t l = (uint64_t)ws->runs[i].len * ws->runs[i].cnt; warp_copy(wq, ws->runs[i].p, l); wq += l; }
+                __syncwarp();
+                ws->nruns = 0; Blk all; all.p = buf; all.len = (uint32_t)tot; all.cnt = 1; runs_push_back(ws, all);
+            }
+            if (looks_like_zip(ws->runs[0].p, ws->runs[0].len)) { ws->status = CASE_UNSUPPORTED; return; }
+            split_big(c);
+            cont = CONT_PAT;
+        } else if (pat == P_CP) {
+            // mutate_once_compressed :217-260 on data that is neither gzip nor zlib: plain mutate_once_loop
+            next = (int)g.rand_elem_idx(P_COUNT);
+            ip = g.rand(INITIAL_IP);
+            if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
+            realize_virtual(c);
+            if (ws->status != CASE_OK) return;
+            if (maybe_compressed(ws->runs[0].p, ws->runs[0].len)) { ws->status = CASE_UNSUPPORTED; return; }
             split_big(c);
             cont = CONT_PAT;
         } else { ws->status = CASE_UNSUPPORTED; return; }
@@ -283,7 +416,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         c.rng.seed(ts0, ts1, ts2);
         // fresh per-case state (CurMuta is not carried between cases, reference src/erlamsa_main.erl:223-235)
         ws->status = CASE_OK; ws->reason = 0; ws->n_used = 0; ws->n_failed = 0; ws->noseg = 0; ws->olen = 0;
-        ws->st_n[0] = ws->st_n[1] = 0; ws->fo_has = 0; ws->ntseg = 0; ws->tlen = 0; ws->nvseg = 0; ws->vlen = 0; ws->vchunked = 0;
+        ws->st_n[0] = ws->st_n[1] = 0; ws->fo_has = 0; ws->nwrap = 0; ws->rrun_n = 0; ws->ntseg = 0; ws->tlen = 0; ws->nvseg = 0; ws->vlen = 0; ws->vchunked = 0;
         for (int i = 0; i < 16; i++) ws->used[i] = -1;
         ws->nrows = bp.n_rows;
         for (int i = 0; i < bp.n_rows; i++) { MutRow r; r.score = (double)bp.row_score[i]; r.pri = bp.row_pri[i]; r.name = bp.row_id[i]; r.fn = bp.row_id[i]; r.pad = 0; ws->rows[i] = r; }
@@ -295,6 +428,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
             int64_t x = (int64_t)c.rng.rand((uint64_t)bp.pat_sum);
             for (int i = 0; i < bp.n_pats; i++) { if (x == 0 || x < bp.pat_pri[i]) { pat = bp.pat_id[i]; break; } x -= bp.pat_pri[i]; }
             if (pat < 0) ws->status = CASE_DIED; else run_case_machine(c, pat);
+            if (ws->status == CASE_OK) unwind_wrappers(c);
         }
         if (ws->status == CASE_OK && ws->olen > bp.max_case_out) { ws->status = CASE_OVERFLOW; ws->reason = 5; }
         if (ws->status == CASE_UNSUPPORTED || ws->status == CASE_OVERFLOW) { ws->noseg = 0; ws->olen = 0; o_push(c, seg_copy(blob, blen)); }

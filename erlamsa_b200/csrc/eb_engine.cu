@@ -13,6 +13,7 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include "../../include/erlamsa_b200.h"
 #include "eb_decide.cuh"
 #include "eb_apply.cuh"
@@ -53,6 +54,7 @@ struct eb200_ctx {
     bool funny_loaded = false;
     int apply_variant = 0;
     int decide_variant = 0;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // host-path pipeline (created on first use)
 };
 
 // apply-kernel configurations (words per thread, loads in flight per thread, min CTAs/SM); index 0 ships,
@@ -206,6 +208,7 @@ void eb200_shutdown(eb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->temp, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta}) b->release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
+    if (ctx->s_h2d) { cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h); cudaStreamDestroy(ctx->s_comp); }
     delete ctx;
 }
 
@@ -237,6 +240,7 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
         ar.temp = nullptr; ar.temp_per_warp = 0;
         bool needs_temp = false;
         for (int i = 0; i < bp.n_rows; i++) needs_temp |= mut_needs_temp(bp.row_id[i]);
+        for (int i = 0; i < bp.n_pats; i++) needs_temp |= bp.pat_pri[i] > 0 && (bp.pat_id[i] == P_SK || bp.pat_id[i] == P_SZ || bp.pat_id[i] == P_CS);
         if (needs_temp) {   // parse tables are proportional to the block being mutated: size the per-warp region from the mean blob
             uint64_t mean = bp.n_blobs ? data_bytes / bp.n_blobs : 0;
             uint64_t per = std::min<uint64_t>(std::max<uint64_t>(64 * mean, 256u << 10), 16u << 20);
@@ -327,9 +331,101 @@ int eb200_fuzz_batch(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* data
     if (!out_data) return EB200_ERR_ARG;
     return fuzz_batch_host(ctx, opts, data, off, n_blobs, n_cases, out_data, nullptr, 0, out_off, out_len, meta, stats);
 }
+// Chunked, copy/compute-overlapped variant of the host path: the corpus is uploaded in chunks of cases on a copy
+// stream while the previous chunk is being decided/applied on the compute stream and the one before that is being
+// downloaded on a third stream. Compute for consecutive chunks stays on ONE stream, so the per-batch arenas
+// (cases, segments, scratch) are reused safely; only PCIe traffic overlaps. Needs pinned host buffers to overlap.
+static int fuzz_batch_host_pipelined(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases,
+                                     uint8_t* user_out, uint64_t user_cap, uint64_t* out_off, uint64_t* out_len, eb200_meta* meta, eb200_stats* stats,
+                                     uint64_t chunk) {
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    uint64_t data_bytes = off[n_blobs];
+    uint64_t first = opts->first_case ? opts->first_case : 1;
+    uint64_t b0 = (first - 1) % n_blobs;                 // blob of the first case; the caller checked that the range does not wrap
+    if (!ctx->s_h2d) { CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+                       CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking)); }
+    uint64_t nchunks = (n_cases + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> ev_up(nchunks), ev_done(nchunks);
+    for (uint64_t j = 0; j < nchunks; j++) { CK(cudaEventCreateWithFlags(&ev_up[j], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_done[j], cudaEventDisableTiming)); }
+    CK(ctx->data.ensure(data_bytes + 64));
+    CK(ctx->off.ensure((n_blobs + 1) * 8));
+    CK(ctx->out_off.ensure((n_cases + nchunks + 1) * 8));
+    CK(ctx->out_len.ensure(n_cases * 8));
+    CK(ctx->meta.ensure(n_cases * sizeof(MetaDev)));
+    CK(ctx->out.ensure(data_bytes + data_bytes / 4 + (64ull << 20)));
+    auto t0 = std::chrono::steady_clock::now();
+    CK(cudaMemcpyAsync(ctx->off.p, off, (n_blobs + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+    auto upload = [&](uint64_t j) -> cudaError_t {
+        uint64_t k0 = j * chunk, k1 = std::min(n_cases, k0 + chunk);
+        uint64_t lo = off[b0 + k0], hi = off[b0 + k1];
+        cudaError_t e = cudaSuccess;
+        if (hi > lo) e = cudaMemcpyAsync((uint8_t*)ctx->data.p + lo, data + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_up[j], ctx->s_h2d);
+        return e;
+    };
+    CK(upload(0));
+    uint64_t base = 0; uint32_t launches = 0; int rc = EB200_OK;
+    std::vector<uint64_t> bases(nchunks + 1, 0);
+    for (uint64_t j = 0; j < nchunks && rc == EB200_OK; j++) {
+        if (j + 1 < nchunks) CK(upload(j + 1));                          // next chunk's upload overlaps this chunk's compute
+        uint64_t k0 = j * chunk, k1 = std::min(n_cases, k0 + chunk), nc = k1 - k0;
+        CK(cudaStreamWaitEvent(ctx->s_comp, ev_up[j], 0));
+        eb200_opts o = *opts; o.first_case = first + k0;
+        BatchParams bp; rc = compute_batch_params(&o, n_blobs, nc, bp);
+        if (rc) break;
+        uint64_t* d_off_j = (uint64_t*)ctx->out_off.p + k0 + j;          // nc + 1 entries per chunk
+        uint64_t total = 0;
+        rc = run_decide_scan(ctx, bp, &o, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, d_off_j,
+                             (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches);
+        if (rc) break;
+        if (base + total > user_cap) { rc = EB200_ERR_NOMEM; break; }
+        if (base + total + 64 > ctx->out.cap) {                          // rare: the estimate was too small -- drain and grow
+            CK(cudaStreamSynchronize(ctx->s_d2h)); CK(cudaStreamSynchronize(ctx->s_comp));
+            CK(ctx->out.ensure((base + total) * 2 + 64));
+        }
+        rc = run_apply(ctx, nc, d_off_j, (uint8_t*)ctx->out.p + base, ctx->out.cap - base, total, ctx->s_comp, &launches);
+        if (rc) break;
+        CK(cudaEventRecord(ev_done[j], ctx->s_comp));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ev_done[j], 0));
+        if (total) CK(cudaMemcpyAsync(user_out + base, (uint8_t*)ctx->out.p + base, total, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaMemcpyAsync(out_off + k0, d_off_j, nc * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaMemcpyAsync(out_len + k0, (uint64_t*)ctx->out_len.p + k0, nc * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (meta) CK(cudaMemcpyAsync(meta + k0, (MetaDev*)ctx->meta.p + k0, nc * sizeof(MetaDev), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        bases[j] = base; base += total;
+    }
+    cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_comp);
+    cudaError_t e = cudaStreamSynchronize(ctx->s_d2h);
+    for (uint64_t j = 0; j < nchunks; j++) { cudaEventDestroy(ev_up[j]); cudaEventDestroy(ev_done[j]); }
+    if (rc) return rc;
+    if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return EB200_ERR_CUDA; }
+    for (uint64_t j = 0; j < nchunks; j++) { uint64_t k0 = j * chunk, k1 = std::min(n_cases, k0 + chunk); for (uint64_t k = k0; k < k1; k++) out_off[k] += bases[j]; }
+    out_off[n_cases] = base;
+    if (stats) {
+        stats->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        stats->n_cases = n_cases; stats->kernels_launched = launches;
+        for (uint64_t k = 0; k < n_cases; k++) { stats->bytes_out += out_len[k]; stats->bytes_in += off[b0 + k + 1] - off[b0 + k]; }
+    }
+    return EB200_OK;
+}
+
 int eb200_fuzz_batch_into(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases,
                           uint8_t* out_buf, uint64_t out_capacity, uint64_t* out_off, uint64_t* out_len, eb200_meta* meta, eb200_stats* stats) {
     if (!out_buf) return EB200_ERR_ARG;
+    if (ctx && opts && off && data && out_off && out_len && n_blobs) {
+        // big batches whose cases read a contiguous run of blobs go through the overlapped pipeline
+        uint64_t data_bytes = off[n_blobs];
+        uint64_t first = opts->first_case ? opts->first_case : 1;
+        uint64_t b0 = (first - 1) % n_blobs;
+        bool ok = true;
+        for (uint64_t b = 0; b < n_blobs && ok; b++) ok = off[b + 1] >= off[b] && off[b + 1] - off[b] <= 0xfffffff0ull;
+        if (!ok) return EB200_ERR_ARG;
+        if (b0 + n_cases <= n_blobs && data_bytes >= (256ull << 20) && n_cases >= 4096) {
+            uint64_t avg = std::max<uint64_t>(1, data_bytes / n_blobs);
+            uint64_t chunk = std::max<uint64_t>(1024, (128ull << 20) / avg);
+            if (chunk * 2 <= n_cases) return fuzz_batch_host_pipelined(ctx, opts, data, off, n_blobs, n_cases, out_buf, out_capacity, out_off, out_len, meta, stats, chunk);
+        }
+    }
     uint8_t* dummy = nullptr;
     return fuzz_batch_host(ctx, opts, data, off, n_blobs, n_cases, &dummy, out_buf, out_capacity, out_off, out_len, meta, stats);
 }

@@ -314,12 +314,13 @@ EB_DEV void mut_st_line(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutRes
 #include "eb_mut_text.cuh"
 #include "eb_mut_tree.cuh"
 #include "eb_mut_fuse.cuh"
+#include "eb_field.cuh"
 namespace eb {
 
 // mutators whose working tables live in the per-warp temp arena
 __host__ __device__ inline bool mut_needs_temp(int id) {
     switch (id) {
-    case M_AB: case M_AD: case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: case M_FT: case M_FN: case M_FO: return true;
+    case M_AB: case M_AD: case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: case M_FT: case M_FN: case M_FO: case M_LEN: return true;
     default: return false;
     }
 }
@@ -328,6 +329,7 @@ __host__ __device__ inline bool mut_needs_temp(int id) {
 __host__ EB_DEV bool mut_supported(int id) {
     switch (id) {
     case M_AB: case M_AD: case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: case M_FT: case M_FN: case M_FO:
+    case M_LEN: case M_ZIP:
     case M_UW: case M_UI: case M_NUM:
     case M_BD: case M_BEI: case M_BED: case M_BF: case M_BI: case M_BER: case M_BR:
     case M_SP: case M_SR: case M_SD: case M_SNAND: case M_SRND:
@@ -346,6 +348,11 @@ EB_DEV void mut_apply(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, Mut
     case M_AB: case M_AD: mut_ascii(c, id, p, n, r); return;
     case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: mut_tree(c, id, p, n, r); return;
     case M_FT: case M_FN: case M_FO: mut_fuse(c, id, p, n, r); return;
+    case M_LEN: mut_len(c, p, n, r); return;
+    case M_ZIP: {   // zip_path_traversal :1149-1163 on data that is not a ZIP archive: zip:foldl fails, delta -1, no draws
+        bool z = false; { uint32_t hit = 0; for (uint32_t i = lane_id(); i + 4 <= n; i += 32) hit |= (p[i] == 'P' && p[i + 1] == 'K' && p[i + 2] == 5 && p[i + 3] == 6) ? 1u : 0u; z = __any_sync(0xffffffffu, hit != 0); }
+        r.kind = z ? RES_UNSUPPORTED : RES_SAME; r.delta = -1; r.rechunk = 0; r.consumed_next = 0; return;
+    }
     case M_LD: case M_LDS: case M_LR2: case M_LRI: case M_LR: case M_LS: case M_LP: mut_line(c, id, p, n, r); return;
     case M_LIS: case M_LRS: mut_st_line(c, id, p, n, r); return;
     case M_NIL: r.kind = RES_SAME; r.delta = -1; r.rechunk = 0; r.consumed_next = 0; return;

@@ -42,6 +42,10 @@ struct WarpState {
     StSlot st[2][10]; int st_n[2];
     // RES_RUNS results: the new head is handed back as real block runs (fo: two re-chunked regions)
     Blk rrun[4]; int rrun_n;
+    // pending sizer / checksum wrappers (patterns sz, cs): everything emitted after `mark` is the enclosed
+    // blob; when the case is complete the length field at `field_pos` is patched / the checksum appended
+    struct Wrap { uint32_t kind; uint32_t bits; uint32_t big; uint32_t tail_n; uint64_t field_pos; uint64_t mark; const uint8_t* tail_p; } wrap[8];
+    int nwrap;
     const uint8_t* fo_p; uint32_t fo_n; int fo_has;
     uint16_t sc[SC_MAX];
     uint32_t status; uint32_t reason;

@@ -54,6 +54,7 @@ struct Opts {
     int gen_random_pri = 1;
     std::string ssrf_host = "localhost";   // get_ssrf_ep/0 default, src/erlamsa_mutations.erl:697-702
     int ssrf_port = 51234;
+    uint64_t max_case_out = 64ull << 20;   // not a reference option: the harness' guard against runaway repeats (cf. maxrunningtime)
     Opts() {
         for (int i = 0; i < M_COUNT; i++) muta_pri[i] = MUT_DEFAULT_PRI[i];
         for (int i = 0; i < P_COUNT; i++) pat_pri[i] = PAT_DEFAULT_PRI[i];
@@ -64,6 +65,8 @@ struct Opts {
 struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
 // thrown where the reference's worker process would crash (case yields empty output)
 struct CaseDied : std::runtime_error { using std::runtime_error::runtime_error; };
+// the case grew past the harness' output cap (the reference would run into its maxrunningtime watchdog instead)
+struct CaseOverflow : std::runtime_error { using std::runtime_error::runtime_error; };
 
 // per-case record, compared 1:1 with the engine's eb200_meta
 struct Meta {

@@ -246,6 +246,7 @@ struct Fuzzer {
             for (auto& b : res) out += b;
         } catch (const Unsupported&) { meta.status = 1; out.clear(); }
         catch (const CaseDied&) { meta.status = 2; out.clear(); }
+        catch (const CaseOverflow&) { meta.status = 3; out = input; }
         meta.draws = rng.draws;
         return out;
     }
@@ -264,6 +265,7 @@ struct eo_opts_c {
     int32_t gen_direct_pri, gen_random_pri;
     char ssrf_host[64];
     int32_t ssrf_port;
+    uint64_t max_case_out;
 };
 struct eo_meta_c {
     int32_t pattern, generator, n_used, n_failed;
@@ -280,6 +282,7 @@ static eo::Opts conv(const eo_opts_c* c) {
     for (int i = 0; i < eo::P_COUNT; i++) o.pat_pri[i] = c->pat_pri[i];
     o.gen_direct_pri = c->gen_direct_pri; o.gen_random_pri = c->gen_random_pri;
     o.ssrf_host = std::string(c->ssrf_host, strnlen(c->ssrf_host, 64)); o.ssrf_port = c->ssrf_port;
+    if (c->max_case_out) o.max_case_out = c->max_case_out;
     return o;
 }
 static void conv_meta(const eo::Meta& m, eo_meta_c* c) {

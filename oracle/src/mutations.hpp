@@ -531,6 +531,10 @@ struct Mutations {
         case M_URI: { MutRes r = uri_mutator(ll); node.fn = M_B64; return r; }
         case M_B64: return base64_mutator(ll);
         case M_NIL: { MutRes r; r.ll = ll; r.delta = -1; return r; }
+        case M_ZIP: {   // zip_path_traversal :1149-1163: zip:foldl fails on non-archives -> unchanged, delta -1, no draws
+            if (ll[0].find(std::string("PK\x05\x06", 4)) != Bin::npos) throw Unsupported("zip mutator on ZIP-looking data");
+            MutRes r; r.ll = ll; r.delta = -1; return r;
+        }
         default: throw Unsupported(std::string("mutator not restated in the oracle: ") + MUT_CODES[node.fn]);
         }
     }
@@ -557,6 +561,7 @@ struct Mutations {
             }
             MutNode node = perm[i];
             MutRes res = apply(node, ll);
+            { uint64_t tot = 0; for (auto& b : res.ll) tot += b.size(); if (tot > opts.max_case_out) throw CaseOverflow("case output cap"); }
             node.score = adjust_priority(node.score, res.delta);
             out.push_back(node);
             if (!res.ll.empty() && res.ll[0] == ll[0]) { if (meta) meta->n_failed++; continue; }

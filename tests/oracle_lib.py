@@ -22,7 +22,7 @@ class Opts(C.Structure):
     _fields_ = [("seed", C.c_int64 * 3), ("blockscale", C.c_double),
                 ("muta_pri", C.c_int32 * 41), ("pat_pri", C.c_int32 * 10),
                 ("gen_direct_pri", C.c_int32), ("gen_random_pri", C.c_int32),
-                ("ssrf_host", C.c_char * 64), ("ssrf_port", C.c_int32)]
+                ("ssrf_host", C.c_char * 64), ("ssrf_port", C.c_int32), ("max_case_out", C.c_uint64)]
 
 
 class Meta(C.Structure):
@@ -68,7 +68,7 @@ def lib():
 
 
 def make_opts(seed=(1, 2, 3), mutations=None, patterns=None, blockscale=1.0, generators=None,
-              ssrf_host="localhost", ssrf_port=51234):
+              ssrf_host="localhost", ssrf_port=51234, max_case_out=0):
     """mutations / patterns: None = reference defaults, else dict or list of (code, pri) -- the
     reference's `[{Code, Pri}]` option lists (src/erlamsa_main.erl:129,156)."""
     o = Opts()
@@ -89,6 +89,7 @@ def make_opts(seed=(1, 2, 3), mutations=None, patterns=None, blockscale=1.0, gen
         o.gen_random_pri = g.get("random", -1)
     o.ssrf_host = ssrf_host.encode()
     o.ssrf_port = ssrf_port
+    o.max_case_out = max_case_out
     return o
 
 

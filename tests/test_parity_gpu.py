@@ -10,9 +10,12 @@ pytestmark = pytest.mark.gpu
 SUPPORTED_PATS = {"od": 1, "nd": 2, "bu": 1, "sk": 2, "co": 0, "nu": 0}
 
 
+CAP = 1 << 20   # per-case output cap given to both sides (runaway repeats are flagged, not compared)
+
+
 def compare(engine, oracle, blobs, mutations, patterns, seed=(1, 2, 3), n_cases=None, first_case=1, allow_unsupported=False):
-    o_out, o_meta = oracle.fuzzer(blobs, mutations=mutations, patterns=patterns, seed=seed, n_cases=n_cases, first_case=first_case)
-    g_out, g_meta = engine.fuzz_batch(blobs, {"mutations": mutations, "patterns": patterns, "seed": seed, "first_case": first_case, "max_case_out": 1 << 28},
+    o_out, o_meta = oracle.fuzzer(blobs, mutations=mutations, patterns=patterns, seed=seed, n_cases=n_cases, first_case=first_case, max_case_out=CAP)
+    g_out, g_meta = engine.fuzz_batch(blobs, {"mutations": mutations, "patterns": patterns, "seed": seed, "first_case": first_case, "max_case_out": CAP},
                                       n_cases=n_cases)
     assert len(o_out) == len(g_out)
     bad = []
@@ -24,9 +27,9 @@ def compare(engine, oracle, blobs, mutations, patterns, seed=(1, 2, 3), n_cases=
             continue
         if ma.status != 0:
             continue
-        if mb.status == 3 and len(a) > (4 << 20):
-            # documented capacity limit: a case that blows up past a few MiB (sr/lr repeats compounded by nd)
-            # may exceed the engine's per-case run/piece tables; it is flagged, never silently wrong
+        if ma.status == 3 or (mb.status == 3 and mb.pad in (1, 4, 5, 6)):
+            # documented capacity limits: a case that blows up past the output cap (sr/lr repeats compounded by
+            # nd/bu rounds) or the engine's run/piece tables is flagged on either side, never silently wrong
             n_big += 1
             continue
         n_cmp += 1
@@ -35,7 +38,7 @@ def compare(engine, oracle, blobs, mutations, patterns, seed=(1, 2, 3), n_cases=
             bad.append((k, len(blobs[(first_case - 1 + k) % len(blobs)]), len(a), len(b), ma.draws, mb.draws, ma.pattern, mb.pattern,
                         list(ma.used)[:4], list(mb.used)[:4], mb.status, mb.pad))
     assert not bad, "mismatches (case, in_len, oracle_len, gpu_len, o_draws, g_draws, o_pat, g_pat, o_used, g_used, g_status): %r" % bad[:8]
-    assert n_big * 20 <= len(o_out), "too many capacity overflows: %d" % n_big
+    assert n_big * 8 <= len(o_out), "too many capacity overflows: %d" % n_big
     return n_cmp
 
 
@@ -60,6 +63,60 @@ def test_structure_mutators_multi_round(engine, oracle):
     muts = {c: 1 for c in ("ab", "ad", "tr2", "td", "ts1", "ts2", "tr", "ft", "fn", "fo", "num", "lis", "bd")}
     blobs = corpus.text_corpus(0xE21A0700, 300, 900)
     compare(engine, oracle, blobs, muts, {"nd": 2, "bu": 1, "od": 1}, seed=(2, 7, 1), allow_unsupported=True)
+
+
+def framed_corpus(seed, count):
+    """blobs that really carry length fields / xor8 / crc32 trailers, so the sizer and checksum searches FIND something"""
+    import struct
+    import zlib
+    r = corpus.rng(seed)
+    out = []
+    for i in range(count):
+        body = corpus.random_bytes(r, int(r.integers(4, 600))) if i % 2 else corpus.structured_text(r, int(r.integers(4, 600)))
+        pre = corpus.random_bytes(r, int(r.integers(0, 12)))
+        kind = i % 7
+        if kind == 0:
+            out.append(pre + struct.pack(">H", len(body)) + body)
+        elif kind == 1:
+            out.append(pre + struct.pack("<I", len(body)) + body + b"TAIL")
+        elif kind == 2:
+            out.append(pre + bytes([min(len(body), 255)]) + body[:255])
+        elif kind == 3:
+            x = 0
+            for b in body:
+                x ^= b
+            out.append(pre + body + bytes([x]))
+        elif kind == 4:
+            out.append(pre + body + struct.pack(">I", zlib.crc32(body)))
+        elif kind == 5:
+            out.append(struct.pack(">Q", len(body) + 2) + body + b"xy")
+        else:
+            out.append(pre + body)
+    return out
+
+
+@pytest.mark.parametrize("pat", ["sz", "cs", "ar", "cp"])
+def test_complex_patterns(engine, oracle, pat):
+    muts = {c: 1 for c in ("bd", "bf", "bi", "num", "sd", "ld", "ab", "td", "ft")}
+    blobs = framed_corpus(0xE21A0800, 210) + corpus.mixed_corpus(0xE21A0801, 60, 1200)
+    n = compare(engine, oracle, blobs, muts, {pat: 1}, seed=(6, 6, 6), allow_unsupported=True)
+    assert n > len(blobs) * 0.8
+
+
+def test_len_mutator(engine, oracle):
+    blobs = framed_corpus(0xE21A0900, 210) + corpus.mixed_corpus(0xE21A0901, 60, 3000)
+    n = compare(engine, oracle, blobs, {"len": 1}, {"od": 1, "nd": 1}, seed=(8, 1, 8))
+    assert n >= len(blobs) - 3
+
+
+def test_default_pattern_mix_and_all_device_mutators(engine, oracle):
+    """the reference's default patterns (all ten) over every mutator that has a device implementation"""
+    import erlamsa_b200
+    muts = {c: p for c, p in erlamsa_b200.default_mutations() if c in erlamsa_b200.supported_mutations()}
+    pats = dict(erlamsa_b200.default_patterns())
+    blobs = framed_corpus(0xE21A0A00, 140) + corpus.text_corpus(0xE21A0A01, 200, 900) + corpus.mixed_corpus(0xE21A0A02, 160, 1500)
+    n = compare(engine, oracle, blobs, muts, pats, seed=(1, 2, 3), allow_unsupported=True)
+    assert n > len(blobs) * 0.9
 
 
 @pytest.mark.parametrize("pat", ["od", "nd", "bu", "sk", "co", "nu"])
@@ -90,6 +147,43 @@ def test_case_window_and_corpus_wraparound(engine, oracle):
     blobs = corpus.mixed_corpus(0xE21A0300, 37)
     muts = {c: 1 for c in ("bd", "bf", "num", "sr", "ld")}
     compare(engine, oracle, blobs, muts, {"od": 1, "nd": 1}, n_cases=150, first_case=1000)
+
+
+def test_pipelined_host_path_equals_plain_host_path(engine):
+    """eb200_fuzz_batch_into switches to the chunked copy/compute-overlapped pipeline for big batches; results must
+    be identical to the single-shot host path (same case ids, same bytes)"""
+    import ctypes as C
+    import numpy as np
+    from erlamsa_b200 import _native as N
+    import erlamsa_b200
+    n, size = 8192, 40960
+    r = corpus.rng(0xE21A0B00)
+    data = r.integers(0, 256, size=n * size, dtype=np.uint8)
+    data[::97] = 0x31                                  # sprinkle digits so that num has work
+    off = np.arange(0, (n + 1) * size, size, dtype=np.uint64)
+    opts = erlamsa_b200.make_opts({"mutations": {c: 1 for c in ("bd", "bei", "bf", "bi", "num", "sd")}, "patterns": {"od": 1, "nd": 1},
+                                   "seed": (4, 4, 4), "first_case": 1, "max_case_out": 1 << 22})
+    out = np.zeros(n * size + (8 << 20), dtype=np.uint8)
+    o_off = np.zeros(n + 1, dtype=np.uint64); o_len = np.zeros(n, dtype=np.uint64)
+    st = N.Stats()
+    rc = N.lib().eb200_fuzz_batch_into(engine._ctx, C.byref(opts), data.ctypes.data, off.ctypes.data, n, n, out.ctypes.data, out.size,
+                                       o_off.ctypes.data, o_len.ctypes.data, None, C.byref(st))
+    assert rc == 0
+    # plain path: same call through the malloc()ing entry point (never pipelined)
+    out_p = C.c_void_p(); p_off = np.zeros(n + 1, dtype=np.uint64); p_len = np.zeros(n, dtype=np.uint64)
+    rc = N.lib().eb200_fuzz_batch(engine._ctx, C.byref(opts), data.ctypes.data, C.cast(off.ctypes.data, C.POINTER(C.c_uint64)), n, n, C.byref(out_p),
+                                  C.cast(p_off.ctypes.data, C.POINTER(C.c_uint64)), C.cast(p_len.ctypes.data, C.POINTER(C.c_uint64)), None, None)
+    assert rc == 0
+    try:
+        assert (o_len == p_len).all()
+        plain = np.ctypeslib.as_array(C.cast(out_p, C.POINTER(C.c_uint8)), shape=(int(p_off[n]),))
+        for k in list(range(0, n, 257)) + [n - 1]:
+            a = out[int(o_off[k]):int(o_off[k]) + int(o_len[k])]
+            b = plain[int(p_off[k]):int(p_off[k]) + int(p_len[k])]
+            assert a.tobytes() == b.tobytes(), k
+        assert int(o_off[n]) == int(p_off[n])
+    finally:
+        N.lib().eb200_free(out_p)
 
 
 def test_philox_mode_runs_and_differs(engine):
