@@ -396,7 +396,22 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
 struct DecideArgs {
     const uint8_t* data; const uint64_t* off; Arenas ar;
     CaseOut* cases; uint64_t* out_len; uint64_t* out_sz16; MetaDev* meta;
+    // single-pass (fused) mode
+    int fused; uint8_t* out; uint64_t out_capacity; const uint64_t* slot_off; uint64_t* out_off;
+    uint64_t ovf_base; unsigned long long* ovf_used; uint64_t data_bytes;
 };
+struct FusedArgs { int fused; uint8_t* out; uint64_t out_capacity; const uint64_t* slot_off; uint64_t* out_off; uint64_t ovf_base; unsigned long long* ovf_used; uint64_t data_bytes; };
+
+// slot sizes for the single-pass mode: input length + slack, 16-byte aligned (the common mutations change a
+// case by a few bytes; anything bigger spills to the overflow region)
+__global__ void __launch_bounds__(256) eb_slot_sizes(const uint64_t* __restrict__ off, uint64_t first_case, uint64_t n_blobs, uint64_t n_cases, uint64_t* __restrict__ sz16) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_cases) return;
+    uint64_t b = (first_case - 1 + k) % n_blobs;
+    uint64_t len = off[b + 1] - off[b];
+    uint64_t slack = len / 16; if (slack < 256) slack = 256; if (slack > 65536) slack = 65536;
+    sz16[k] = align16(len + slack);
+}
 
 // one test case, start to finish, by one warp
 EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideArgs& a, uint64_t k, int32_t pa1, int32_t pa2, int32_t pa3) {
@@ -434,15 +449,36 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         if (ws->status == CASE_UNSUPPORTED || ws->status == CASE_OVERFLOW) { ws->noseg = 0; ws->olen = 0; o_push(c, seg_copy(blob, blen)); }
         if (ws->status == CASE_DIED) { ws->noseg = 0; ws->olen = 0; }
         __syncwarp();
-        // publish the edit script
         unsigned long long sb = 0; int ns = ws->noseg;
-        if (lane_id() == 0 && ns > 0) sb = atomicAdd(ar.segs_used, (unsigned long long)ns);
-        sb = __shfl_sync(0xffffffffu, sb, 0);
-        if (sb + ns > ar.segs_cap) { if (lane_id() == 0) atomicOr(ar.overflow, 2u); ns = 0; ws->olen = 0; ws->status = CASE_OVERFLOW; ws->reason = 7; }
-        for (int i = lane_id(); i < ns; i += 32) ar.segs[sb + i] = ws->oseg[i];
+        if (a.fused) {
+            // single-pass mode: the output slot of case k was fixed before the kernel (prefix sum over INPUT sizes +
+            // slack), so the warp that decided the case executes its edit script right away; results that outgrow
+            // the slot go to the overflow region behind the slots
+            uint64_t s0 = a.slot_off[k], cap = a.slot_off[k + 1] - s0;
+            uint64_t dsto = s0;
+            if (ws->olen > cap) {
+                unsigned long long o = 0, need = align16(ws->olen);
+                if (lane_id() == 0) o = atomicAdd(a.ovf_used, need);
+                o = __shfl_sync(0xffffffffu, o, 0);
+                if (a.ovf_base + o + need > a.out_capacity) {   // no room: flag the case, emit the input unchanged (always fits its slot)
+                    if (lane_id() == 0) atomicOr(ar.overflow, 4u);
+                    ws->status = CASE_OVERFLOW; ws->reason = 11; ws->noseg = 0; ws->olen = 0; o_push(c, seg_copy(blob, blen)); ns = ws->noseg;
+                } else dsto = a.ovf_base + o;
+            }
+            segs_write_stream(ws->oseg, ws->noseg, a.out + dsto, data, data + a.data_bytes);
+            if (lane_id() == 0) { a.out_off[k] = dsto; out_len[k] = ws->olen; }
+        } else {
+            // two-pass mode: publish the edit script for the apply kernel
+            if (lane_id() == 0 && ns > 0) sb = atomicAdd(ar.segs_used, (unsigned long long)ns);
+            sb = __shfl_sync(0xffffffffu, sb, 0);
+            if (sb + ns > ar.segs_cap) { if (lane_id() == 0) atomicOr(ar.overflow, 2u); ns = 0; ws->olen = 0; ws->status = CASE_OVERFLOW; ws->reason = 7; }
+            for (int i = lane_id(); i < ns; i += 32) ar.segs[sb + i] = ws->oseg[i];
+        }
         if (lane_id() == 0) {
-            CaseOut co; co.seg_begin = sb; co.nseg = (uint32_t)ns; co.status = ws->status; co.out_len = ws->olen; co.pad = 0;
-            cases[k] = co; out_len[k] = ws->olen; out_sz16[k] = align16(ws->olen);
+            if (!a.fused) {
+                CaseOut co; co.seg_begin = sb; co.nseg = (uint32_t)ns; co.status = ws->status; co.out_len = ws->olen; co.pad = 0;
+                cases[k] = co; out_len[k] = ws->olen; out_sz16[k] = align16(ws->olen);
+            }
             if (meta) {
                 MetaDev m; m.pattern = pat; m.generator = bp.generator; m.n_used = ws->n_used; m.n_failed = ws->n_failed;
                 for (int i = 0; i < 16; i++) m.used[i] = ws->used[i];
@@ -457,13 +493,15 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
 // WARPS warps per CTA, each taking whole cases. With SYNC the CTA re-converges before every case so
 // that its warps walk the (large, branchy) scalar program in step and share instruction-cache
 // lines: profiles/decide_r1b showed 53% of stall samples on instruction fetch with free-running warps.
-template <int WARPS, bool SYNC, int MINB>
+template <int WARPS, int SYNC, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 eb_decide_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ off, BatchParams bp, Arenas ar,
-                 CaseOut* __restrict__ cases, uint64_t* __restrict__ out_len, uint64_t* __restrict__ out_sz16, MetaDev* __restrict__ meta) {
+                 CaseOut* __restrict__ cases, uint64_t* __restrict__ out_len, uint64_t* __restrict__ out_sz16, MetaDev* __restrict__ meta, FusedArgs fa) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WarpState* ws = reinterpret_cast<WarpState*>(smem_raw) + (threadIdx.x >> 5);
     DecideArgs a; a.data = data; a.off = off; a.ar = ar; a.cases = cases; a.out_len = out_len; a.out_sz16 = out_sz16; a.meta = meta;
+    a.fused = fa.fused; a.out = fa.out; a.out_capacity = fa.out_capacity; a.slot_off = fa.slot_off; a.out_off = fa.out_off;
+    a.ovf_base = fa.ovf_base; a.ovf_used = fa.ovf_used; a.data_bytes = fa.data_bytes;
     uint64_t warp_global = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     uint64_t nwarps = (uint64_t)gridDim.x * WARPS;
     uint64_t rounds = (bp.n_cases + nwarps - 1) / nwarps;
@@ -473,7 +511,7 @@ eb_decide_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ 
     par.jump(3 * (bp.first_case - 1 + warp_global));
     uint32_t s1 = modpow_u32<30269>(AS_M1, 3 * nwarps), s2 = modpow_u32<30307>(AS_M2, 3 * nwarps), s3 = modpow_u32<30323>(AS_M3, 3 * nwarps);
     for (uint64_t r = 0; r < rounds; r++) {
-        if (SYNC) __syncthreads();
+        if (SYNC && r % (SYNC ? SYNC : 1) == 0) __syncthreads();
         uint64_t k = r * nwarps + warp_global;
         if (k < bp.n_cases) decide_one_case(ws, bp, a, k, par.a1, par.a2, par.a3);
         par.a1 = (int32_t)(((uint32_t)par.a1 * s1) % 30269u); par.a2 = (int32_t)(((uint32_t)par.a2 * s2) % 30307u); par.a3 = (int32_t)(((uint32_t)par.a3 * s3) % 30323u);

@@ -49,7 +49,8 @@ struct eb200_ctx {
     int device = 0;
     int num_sms = 148;
     std::string last_err;
-    DevBuf cases, out_len, sz16, tile_sum, tile_case, counters, segs, scratch, temp, data, off, out, out_off, meta;
+    DevBuf cases, out_len, sz16, tile_sum, tile_case, slot_off, counters, segs, scratch, temp, data, off, out, out_off, meta;
+    int fused = 1;          // single-pass mode (EB200_MODE=twopass selects decide -> scan -> apply)
     cudaEvent_t ev[6];
     bool funny_loaded = false;
     int apply_variant = 0;
@@ -76,17 +77,17 @@ static const int n_apply_variants = (int)(sizeof(apply_variants) / sizeof(apply_
 struct DecideVariant {
     int warps; int ctas_per_sm; const char* name;
     cudaError_t (*prepare)();
-    void (*launch)(int, cudaStream_t, const uint8_t*, const uint64_t*, const BatchParams&, const Arenas&, CaseOut*, uint64_t*, uint64_t*, MetaDev*);
+    void (*launch)(int, cudaStream_t, const uint8_t*, const uint64_t*, const BatchParams&, const Arenas&, CaseOut*, uint64_t*, uint64_t*, MetaDev*, const FusedArgs&);
 };
-template <int W, bool S, int M>
+template <int W, int S, int M>
 static cudaError_t prepare_decide() { return cudaFuncSetAttribute(eb_decide_kernel<W, S, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpState) * W)); }
-template <int W, bool S, int M>
-static void launch_decide(int grid, cudaStream_t st, const uint8_t* d, const uint64_t* o, const BatchParams& bp, const Arenas& ar, CaseOut* c, uint64_t* ol, uint64_t* sz, MetaDev* m) {
-    eb_decide_kernel<W, S, M><<<grid, W * 32, sizeof(WarpState) * W, st>>>(d, o, bp, ar, c, ol, sz, m);
+template <int W, int S, int M>
+static void launch_decide(int grid, cudaStream_t st, const uint8_t* d, const uint64_t* o, const BatchParams& bp, const Arenas& ar, CaseOut* c, uint64_t* ol, uint64_t* sz, MetaDev* m, const FusedArgs& fa) {
+    eb_decide_kernel<W, S, M><<<grid, W * 32, sizeof(WarpState) * W, st>>>(d, o, bp, ar, c, ol, sz, m, fa);
 }
 #define DV(W, S, M) {W, M, #W "w" #S #M "m", prepare_decide<W, S, M>, launch_decide<W, S, M>}
 // measured on C3 (profiles/variants_r1.txt): 32w-sync 2.55 ms | 16w-sync 2.76 | 4w-free 3.55 | 32w-free 3.55
-static const DecideVariant decide_variants[] = {DV(32, true, 1), DV(16, true, 2), DV(4, false, 8), DV(32, false, 1)};
+static const DecideVariant decide_variants[] = {DV(32, 1, 1), DV(32, 2, 1), DV(32, 4, 1), DV(32, 8, 1), DV(16, 4, 2), DV(4, 0, 8)};
 static const int n_decide_variants = (int)(sizeof(decide_variants) / sizeof(decide_variants[0]));
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_); return EB200_ERR_CUDA; } } while (0)
@@ -198,6 +199,7 @@ int eb200_init(int device, eb200_ctx** out) {
     std::vector<FunnyEntry> f; build_funny(f);
     int fn = (int)f.size(); f.resize(192);
     if (cudaMemcpyToSymbol(c_funny, f.data(), sizeof(FunnyEntry) * 192) != cudaSuccess || cudaMemcpyToSymbol(c_funny_n, &fn, sizeof(int)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
+    if (const char* v = getenv("EB200_MODE")) ctx->fused = strcmp(v, "twopass") != 0;
     if (const char* v = getenv("EB200_DECIDE_VARIANT")) { int k = atoi(v); if (k >= 0 && k < n_decide_variants) ctx->decide_variant = k; }
     if (decide_variants[ctx->decide_variant].prepare() != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
     *out = ctx; return EB200_OK;
@@ -206,7 +208,7 @@ int eb200_init(int device, eb200_ctx** out) {
 void eb200_shutdown(eb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->temp, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta}) b->release();
+    for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->slot_off, &ctx->temp, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta}) b->release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_h2d) { cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h); cudaStreamDestroy(ctx->s_comp); }
     delete ctx;
@@ -251,7 +253,8 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
             ar.temp = (uint8_t*)ctx->temp.p; ar.temp_per_warp = per;
         }
         CK(cudaEventRecord(ctx->ev[0], st));
-        dv.launch(grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta);
+        FusedArgs fa; memset(&fa, 0, sizeof(fa));
+        dv.launch(grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], st));
         (*launches)++;
@@ -274,6 +277,87 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
     return EB200_OK;
 }
 
+// Single-pass mode: slot offsets from INPUT sizes (+ slack) first, then one kernel decides and writes every case.
+// own_out: the output arena is ctx->out (host paths) and may be grown; otherwise the caller's arena is used as is.
+static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* opts, const uint8_t* d_data, const uint64_t* d_off, uint64_t data_bytes,
+                     bool own_out, uint8_t* d_out, uint64_t out_capacity, uint64_t out_base, uint64_t* d_out_off, uint64_t* d_out_len, eb200_meta* d_meta,
+                     cudaStream_t st, uint64_t* total_out, uint32_t* launches) {
+    uint64_t n = bp.n_cases;
+    CK(ctx->sz16.ensure(n * 8));
+    uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    CK(ctx->tile_sum.ensure((ntiles + 1) * 8));
+    CK(ctx->slot_off.ensure((n + 1) * 8));
+    CK(ctx->counters.ensure(64));
+    CK(ctx->cases.ensure(sizeof(CaseOut)));
+    uint64_t scratch_want = opts->scratch_bytes ? opts->scratch_bytes : std::min<uint64_t>(4 * data_bytes + (64ull << 20), 8ull << 30);
+    if (ctx->scratch.cap < scratch_want) CK(ctx->scratch.ensure(scratch_want));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    eb_slot_sizes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, bp.first_case, bp.n_blobs, n, (uint64_t*)ctx->sz16.p);
+    eb_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t*)ctx->sz16.p, n, (uint64_t*)ctx->tile_sum.p);
+    eb_scan_tile_offsets<<<1, SCAN_THREADS, 0, st>>>((uint64_t*)ctx->tile_sum.p, ntiles, (uint64_t*)ctx->tile_sum.p + ntiles);
+    eb_scan_finish<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t*)ctx->sz16.p, n, (const uint64_t*)ctx->tile_sum.p, (const uint64_t*)ctx->tile_sum.p + ntiles, (uint64_t*)ctx->slot_off.p);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[2], st));
+    *launches += 4;
+    uint64_t slots = 0;
+    CK(cudaMemcpyAsync(&slots, (uint64_t*)ctx->slot_off.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (own_out) {
+        uint64_t want = out_base + slots + std::max<uint64_t>(64ull << 20, slots / 8) + 64;
+        if (ctx->out.cap < want) {
+            if (out_base) return EB200_ERR_NOMEM;       // pipelined chunks cannot move the arena under in-flight downloads; the caller sized it
+            CK(ctx->out.ensure(want));
+        }
+        d_out = (uint8_t*)ctx->out.p + out_base; out_capacity = ctx->out.cap - out_base - 64;
+    }
+    if (slots > out_capacity) return EB200_ERR_NOMEM;
+    unsigned long long used[2] = {0, 0};
+    for (int attempt = 0;; attempt++) {
+        CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+        Arenas ar;
+        ar.scratch = (uint8_t*)ctx->scratch.p; ar.scratch_cap = ctx->scratch.cap - 64;
+        ar.scratch_used = (unsigned long long*)ctx->counters.p;
+        ar.segs = (Seg*)ctx->segs.p; ar.segs_cap = 0; ar.segs_used = (unsigned long long*)ctx->counters.p + 1;
+        ar.overflow = (uint32_t*)((unsigned long long*)ctx->counters.p + 2);
+        const DecideVariant& dv = decide_variants[ctx->decide_variant];
+        uint64_t want_ctas = (n + dv.warps - 1) / dv.warps;
+        int grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * dv.ctas_per_sm);
+        if (grid < 1) grid = 1;
+        ar.temp = nullptr; ar.temp_per_warp = 0;
+        bool needs_temp = false;
+        for (int i = 0; i < bp.n_rows; i++) needs_temp |= mut_needs_temp(bp.row_id[i]);
+        for (int i = 0; i < bp.n_pats; i++) needs_temp |= bp.pat_pri[i] > 0 && (bp.pat_id[i] == P_SK || bp.pat_id[i] == P_SZ || bp.pat_id[i] == P_CS);
+        if (needs_temp) {
+            uint64_t mean = bp.n_blobs ? data_bytes / bp.n_blobs : 0;
+            uint64_t per = std::min<uint64_t>(std::max<uint64_t>(64 * mean, 256u << 10), 16u << 20);
+            per = (per + 255) & ~255ull;
+            uint64_t nw = (uint64_t)grid * dv.warps;
+            while (per > (256u << 10) && per * nw > (24ull << 30)) per >>= 1;
+            CK(ctx->temp.ensure(per * nw + 256));
+            ar.temp = (uint8_t*)ctx->temp.p; ar.temp_per_warp = per;
+        }
+        FusedArgs fa; fa.fused = 1; fa.out = d_out; fa.out_capacity = out_capacity; fa.slot_off = (const uint64_t*)ctx->slot_off.p; fa.out_off = d_out_off;
+        fa.ovf_base = slots; fa.ovf_used = (unsigned long long*)ctx->counters.p + 3; fa.data_bytes = data_bytes;
+        CK(cudaEventRecord(ctx->ev[0], st));
+        dv.launch(grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[3], st));
+        (*launches)++;
+        CK(cudaMemcpyAsync(used, (unsigned long long*)ctx->counters.p + 2, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint32_t ovf = (uint32_t)used[0];
+        if (!(ovf & 1) && !((ovf & 4) && own_out && !out_base)) break;
+        if (attempt >= 3) { if (ovf & 1) return EB200_ERR_SCRATCH; break; }
+        if (ovf & 1) { size_t nw = ctx->scratch.cap * 2; CK(ctx->scratch.ensure(nw)); }
+        if ((ovf & 4) && own_out && !out_base) { CK(ctx->out.ensure(ctx->out.cap * 2)); d_out = (uint8_t*)ctx->out.p; out_capacity = ctx->out.cap - 64; }
+    }
+    uint64_t ovf_used = std::min<uint64_t>(used[1], out_capacity - slots);
+    *total_out = slots + ovf_used;
+    CK(cudaMemcpyAsync(d_out_off + n, total_out, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return EB200_OK;
+}
+
 static int run_apply(eb200_ctx* ctx, uint64_t n, const uint64_t* d_out_off, uint8_t* d_out, uint64_t out_capacity, uint64_t total, cudaStream_t st, uint32_t* launches) {
     CK(cudaEventRecord(ctx->ev[3], st));
     if (total > 0) {
@@ -291,6 +375,12 @@ static int run_apply(eb200_ctx* ctx, uint64_t n, const uint64_t* d_out_off, uint
 
 static void fill_stats(eb200_ctx* ctx, eb200_stats* s) {
     if (!s) return;
+    if (ctx->fused) {   // single pass: the "decide" kernel also moved the bytes; there is no apply kernel
+        cudaEventElapsedTime(&s->ms_decide, ctx->ev[0], ctx->ev[3]);
+        cudaEventElapsedTime(&s->ms_scan, ctx->ev[1], ctx->ev[2]);
+        s->ms_apply = 0.f;
+        return;
+    }
     cudaEventElapsedTime(&s->ms_decide, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&s->ms_scan, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&s->ms_apply, ctx->ev[3], ctx->ev[4]);
@@ -310,11 +400,17 @@ int eb200_fuzz_batch_device(eb200_ctx* ctx, const eb200_opts* opts, const uint8_
     if (rc) return rc;
     uint32_t launches = 0; uint64_t total = 0;
     CK(cudaEventRecord(ctx->ev[5], st));
-    rc = run_decide_scan(ctx, bp, opts, d_data, d_off, data_bytes, d_out_off, d_out_len, d_meta, st, &total, &launches);
-    if (rc) return rc;
-    if (total > out_capacity) return EB200_ERR_NOMEM;
-    rc = run_apply(ctx, n_cases, d_out_off, d_out, out_capacity, total, st, &launches);
-    if (rc) return rc;
+    if (ctx->fused) {
+        rc = run_fused(ctx, bp, opts, d_data, d_off, data_bytes, false, d_out, out_capacity, 0, d_out_off, d_out_len, d_meta, st, &total, &launches);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev[4], st));
+    } else {
+        rc = run_decide_scan(ctx, bp, opts, d_data, d_off, data_bytes, d_out_off, d_out_len, d_meta, st, &total, &launches);
+        if (rc) return rc;
+        if (total > out_capacity) return EB200_ERR_NOMEM;
+        rc = run_apply(ctx, n_cases, d_out_off, d_out, out_capacity, total, st, &launches);
+        if (rc) return rc;
+    }
     CK(cudaStreamSynchronize(st));
     if (stats) {
         fill_stats(ctx, stats); cudaEventElapsedTime(&stats->ms_total, ctx->ev[5], ctx->ev[4]);
@@ -353,7 +449,7 @@ static int fuzz_batch_host_pipelined(eb200_ctx* ctx, const eb200_opts* opts, con
     CK(ctx->out_off.ensure((n_cases + nchunks + 1) * 8));
     CK(ctx->out_len.ensure(n_cases * 8));
     CK(ctx->meta.ensure(n_cases * sizeof(MetaDev)));
-    CK(ctx->out.ensure(data_bytes + data_bytes / 4 + (64ull << 20)));
+    CK(ctx->out.ensure(data_bytes + data_bytes / 4 + (64ull << 20) * (nchunks + 2)));
     auto t0 = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(ctx->off.p, off, (n_blobs + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
     auto upload = [&](uint64_t j) -> cudaError_t {
@@ -376,16 +472,23 @@ static int fuzz_batch_host_pipelined(eb200_ctx* ctx, const eb200_opts* opts, con
         if (rc) break;
         uint64_t* d_off_j = (uint64_t*)ctx->out_off.p + k0 + j;          // nc + 1 entries per chunk
         uint64_t total = 0;
-        rc = run_decide_scan(ctx, bp, &o, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, d_off_j,
-                             (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches);
-        if (rc) break;
-        if (base + total > user_cap) { rc = EB200_ERR_NOMEM; break; }
-        if (base + total + 64 > ctx->out.cap) {                          // rare: the estimate was too small -- drain and grow
-            CK(cudaStreamSynchronize(ctx->s_d2h)); CK(cudaStreamSynchronize(ctx->s_comp));
-            CK(ctx->out.ensure((base + total) * 2 + 64));
+        if (ctx->fused) {
+            rc = run_fused(ctx, bp, &o, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, true, nullptr, 0, base, d_off_j,
+                           (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches);
+            if (rc) break;
+            if (base + total > user_cap) { rc = EB200_ERR_NOMEM; break; }
+        } else {
+            rc = run_decide_scan(ctx, bp, &o, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, d_off_j,
+                                 (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches);
+            if (rc) break;
+            if (base + total > user_cap) { rc = EB200_ERR_NOMEM; break; }
+            if (base + total + 64 > ctx->out.cap) {                          // rare: the estimate was too small -- drain and grow
+                CK(cudaStreamSynchronize(ctx->s_d2h)); CK(cudaStreamSynchronize(ctx->s_comp));
+                CK(ctx->out.ensure((base + total) * 2 + 64));
+            }
+            rc = run_apply(ctx, nc, d_off_j, (uint8_t*)ctx->out.p + base, ctx->out.cap - base, total, ctx->s_comp, &launches);
+            if (rc) break;
         }
-        rc = run_apply(ctx, nc, d_off_j, (uint8_t*)ctx->out.p + base, ctx->out.cap - base, total, ctx->s_comp, &launches);
-        if (rc) break;
         CK(cudaEventRecord(ev_done[j], ctx->s_comp));
         CK(cudaStreamWaitEvent(ctx->s_d2h, ev_done[j], 0));
         if (total) CK(cudaMemcpyAsync(user_out + base, (uint8_t*)ctx->out.p + base, total, cudaMemcpyDeviceToHost, ctx->s_d2h));
@@ -452,12 +555,19 @@ static int fuzz_batch_host(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t
     if (data_bytes) CK(cudaMemcpyAsync(ctx->data.p, data, data_bytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->off.p, off, (n_blobs + 1) * 8, cudaMemcpyHostToDevice, st));
     uint32_t launches = 0; uint64_t total = 0;
-    rc = run_decide_scan(ctx, bp, opts, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, (uint64_t*)ctx->out_off.p,
-                         (uint64_t*)ctx->out_len.p, (eb200_meta*)ctx->meta.p, st, &total, &launches);
-    if (rc) return rc;
-    CK(ctx->out.ensure(total + 64));
-    rc = run_apply(ctx, n_cases, (const uint64_t*)ctx->out_off.p, (uint8_t*)ctx->out.p, ctx->out.cap, total, st, &launches);
-    if (rc) return rc;
+    if (ctx->fused) {
+        rc = run_fused(ctx, bp, opts, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, true, nullptr, 0, 0, (uint64_t*)ctx->out_off.p,
+                       (uint64_t*)ctx->out_len.p, (eb200_meta*)ctx->meta.p, st, &total, &launches);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev[4], st));
+    } else {
+        rc = run_decide_scan(ctx, bp, opts, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, (uint64_t*)ctx->out_off.p,
+                             (uint64_t*)ctx->out_len.p, (eb200_meta*)ctx->meta.p, st, &total, &launches);
+        if (rc) return rc;
+        CK(ctx->out.ensure(total + 64));
+        rc = run_apply(ctx, n_cases, (const uint64_t*)ctx->out_off.p, (uint8_t*)ctx->out.p, ctx->out.cap, total, st, &launches);
+        if (rc) return rc;
+    }
     uint8_t* host_out = user_out;
     if (user_out) { if (total > user_cap) return EB200_ERR_NOMEM; }
     else { host_out = (uint8_t*)malloc(total ? total : 1); if (!host_out) return EB200_ERR_NOMEM; }

@@ -173,6 +173,27 @@ EB_DEV void segs_write(const Seg* s, int n, uint8_t* dst) {
     __syncwarp();
 }
 
+// single-pass mode: execute a script into its output slot with streaming copies; sources inside the (read-only)
+// corpus [ro_lo, ro_hi) take the non-coherent load path, scratch written by this kernel takes plain loads
+EB_DEV void segs_write_stream(const Seg* s, int n, uint8_t* dst, const uint8_t* ro_lo, const uint8_t* ro_hi) {
+    int l = lane_id();
+    for (int k = 0; k < n; k++) {
+        uint32_t sl = s[k].len;
+        switch (s[k].kind()) {
+        case SEG_COPY: {
+            const uint8_t* src = (const uint8_t*)(uintptr_t)s[k].src;
+            if (src >= ro_lo && src + sl <= ro_hi) warp_copy_stream<true>(dst, src, sl); else warp_copy_stream<false>(dst, src, sl);
+            break;
+        }
+        case SEG_INLINE: if ((uint32_t)l < sl) dst[l] = (uint8_t)(s[k].src >> (8 * l)); break;
+        case SEG_REPEAT: { const uint8_t* src = (const uint8_t*)(uintptr_t)s[k].src; uint32_t u = s[k].arg(); for (uint32_t i = l; i < sl; i += 32) dst[i] = src[i % u]; break; }
+        default: warp_fill(dst, (uint8_t)s[k].arg(), sl);
+        }
+        dst += sl;
+    }
+    __syncwarp();
+}
+
 // append to the output edit script; when the script is full it is folded into one scratch buffer
 EB_DEV void o_push(CaseCtx& c, Seg s) {
     WarpState* ws = c.ws;

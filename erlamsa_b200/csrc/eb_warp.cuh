@@ -37,6 +37,24 @@ __device__ __forceinline__ void stg16_stream(void* p, uint4 v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// the same with an L2 evict-first policy: the single-pass kernel streams 13 GB through L2 next to its warps' stacks,
+// which should be what stays resident
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <bool NC>
+__device__ __forceinline__ uint4 ldg16_ef(const void* p, uint64_t pol) {
+    uint4 r;
+    if (NC) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void stg16_ef(void* p, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 // 16 bytes starting at an arbitrary address: two aligned 16-byte loads + a 128-bit funnel shift.
 // `need` = how many of the 16 bytes the caller will use; the second aligned word is touched only
 // if it holds needed bytes, so no aligned word lying wholly outside [s, s+need) is ever read.
@@ -70,6 +88,69 @@ __device__ __noinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint64_
         uint4 v = load16_unaligned<false>(src + (i << 4), 16);
         *reinterpret_cast<uint4*>(dst + (i << 4)) = v;
     }
+    uint64_t done = nvec << 4;
+    uint64_t tail = n - done;
+    if ((uint64_t)l < tail) dst[done + l] = src[done + l];
+}
+// Streaming variant for the single-pass mode: four independent 16-byte loads in flight per lane, no-allocate
+// stores; NC selects the read-only path (only legal when the source is not written by this kernel, i.e. the corpus).
+template <bool NC>
+__device__ __noinline__ void warp_copy_stream(uint8_t* dst, const uint8_t* src, uint64_t n) {
+    int l = lane_id();
+    if (n == 0) return;
+    uint64_t head = (16 - ((uintptr_t)dst & 15u)) & 15u;
+    if (head > n) head = n;
+    if ((uint64_t)l < head) dst[l] = src[l];
+    dst += head; src += head; n -= head;
+    uint64_t nvec = n >> 4;
+    uint64_t i = l;
+    // 4 KiB tiles, eight aligned 16-byte loads in flight per lane. A misaligned source is realigned in registers:
+    // each lane takes the following aligned word from its neighbour by shuffle (lane 31 from lane 0's next word,
+    // and one extra load for the last), so every source byte crosses the memory pipe once.
+    {
+        const uint32_t off = (uint32_t)((uintptr_t)src & 15u);
+        const uint8_t* base = src - off;
+        const uint32_t sh = (off & 7u) * 8u;
+        const int nl = (l + 1) & 31;
+        const uint64_t pol = l2_evict_first_policy();
+        for (; i - l + 256 <= nvec; i += 256) {          // warp-uniform trip count: the body shuffles
+            uint4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = ldg16_ef<NC>(base + ((i + 32 * j) << 4), pol);
+            if (off == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) stg16_ef(dst + ((i + 32 * j) << 4), v[j], pol);
+                continue;
+            }
+            uint4 ex = make_uint4(0, 0, 0, 0);
+            if (l == 31) ex = ldg16_ef<NC>(base + ((i + 225) << 4), pol);
+            uint4 r = make_uint4(__shfl_sync(0xffffffffu, v[0].x, nl), __shfl_sync(0xffffffffu, v[0].y, nl),
+                                 __shfl_sync(0xffffffffu, v[0].z, nl), __shfl_sync(0xffffffffu, v[0].w, nl));
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint4 rn = ex;                                   // rotation of the following tile row
+                if (j < 7) rn = make_uint4(__shfl_sync(0xffffffffu, v[j + 1].x, nl), __shfl_sync(0xffffffffu, v[j + 1].y, nl),
+                                           __shfl_sync(0xffffffffu, v[j + 1].z, nl), __shfl_sync(0xffffffffu, v[j + 1].w, nl));
+                uint4 hi = (l == 31) ? rn : r;
+                uint64_t x0 = ((uint64_t)v[j].y << 32) | v[j].x, x1 = ((uint64_t)v[j].w << 32) | v[j].z;
+                uint64_t x2 = ((uint64_t)hi.y << 32) | hi.x, x3 = ((uint64_t)hi.w << 32) | hi.z;
+                if (off & 8) { x0 = x1; x1 = x2; x2 = x3; }
+                uint64_t o0 = sh ? (x0 >> sh) | (x1 << (64 - sh)) : x0;
+                uint64_t o1 = sh ? (x1 >> sh) | (x2 << (64 - sh)) : x1;
+                stg16_ef(dst + ((i + 32 * j) << 4), make_uint4((uint32_t)o0, (uint32_t)(o0 >> 32), (uint32_t)o1, (uint32_t)(o1 >> 32)), pol);
+                r = rn;
+            }
+        }
+    }
+    for (; i + 96 < nvec; i += 128) {
+        uint4 v0 = load16_unaligned<NC>(src + (i << 4), 16);
+        uint4 v1 = load16_unaligned<NC>(src + ((i + 32) << 4), 16);
+        uint4 v2 = load16_unaligned<NC>(src + ((i + 64) << 4), 16);
+        uint4 v3 = load16_unaligned<NC>(src + ((i + 96) << 4), 16);
+        stg16_stream(dst + (i << 4), v0); stg16_stream(dst + ((i + 32) << 4), v1);
+        stg16_stream(dst + ((i + 64) << 4), v2); stg16_stream(dst + ((i + 96) << 4), v3);
+    }
+    for (; i < nvec; i += 32) stg16_stream(dst + (i << 4), load16_unaligned<NC>(src + (i << 4), 16));
     uint64_t done = nvec << 4;
     uint64_t tail = n - done;
     if ((uint64_t)l < tail) dst[done + l] = src[done + l];

@@ -14,7 +14,7 @@ dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(1)
 data = torch.randint(0, 256, (n_cases * size + 64,), dtype=torch.uint8, device=dev, generator=g)
 off = torch.arange(0, (n_cases + 1) * size, size, dtype=torch.int64, device=dev)
-out_cap = n_cases * size + 64 * n_cases + (64 << 20)
+out_cap = n_cases * size + n_cases * size // 12 + 512 * n_cases + (256 << 20)
 d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
 d_off = torch.empty(n_cases + 1, dtype=torch.int64, device=dev)
 d_len = torch.empty(n_cases, dtype=torch.int64, device=dev)
@@ -32,6 +32,6 @@ for v in range(nvar + ndec):
         res.append((st.ms_decide, st.ms_scan, st.ms_apply, st.ms_total))
     res = res[2:]
     avg = [sum(r[k] for r in res) / len(res) for k in range(4)]
-    gbs = (2 * n_cases * size) / (avg[2] * 1e-3) / 1e9
+    gbs = (2 * n_cases * size) / ((avg[2] or avg[0]) * 1e-3) / 1e9
     print("variant %d: decide %.3f  scan %.3f  apply %.3f ms (%.0f GB/s)  total %.3f" % (v, avg[0], avg[1], avg[2], gbs, avg[3]), flush=True)
     eng.close()
