@@ -414,7 +414,27 @@ __global__ void __launch_bounds__(256) eb_slot_sizes(const uint64_t* __restrict_
 }
 
 // one test case, start to finish, by one warp
-EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideArgs& a, uint64_t k, int32_t pa1, int32_t pa2, int32_t pa3) {
+// split-phase CTA barrier on a shared-memory mbarrier (one arrival per warp): a warp arrives when its case is
+// DECIDED and waits only before it starts deciding the next one, so its copy runs inside the barrier's slack
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if (lane_id() == 0) {
+        uint64_t st;
+        asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+        (void)st;
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, addr = (uint32_t)__cvta_generic_to_shared(bar);
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+
+EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideArgs& a, uint64_t k, int32_t pa1, int32_t pa2, int32_t pa3, uint64_t* mbar) {
     const uint8_t* data = a.data; const uint64_t* off = a.off; const Arenas& ar = a.ar;
     CaseOut* cases = a.cases; uint64_t* out_len = a.out_len; uint64_t* out_sz16 = a.out_sz16; MetaDev* meta = a.meta;
     {
@@ -449,6 +469,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         if (ws->status == CASE_UNSUPPORTED || ws->status == CASE_OVERFLOW) { ws->noseg = 0; ws->olen = 0; o_push(c, seg_copy(blob, blen)); }
         if (ws->status == CASE_DIED) { ws->noseg = 0; ws->olen = 0; }
         __syncwarp();
+        if (mbar) mbar_arrive_warp(mbar);
         unsigned long long sb = 0; int ns = ws->noseg;
         if (a.fused) {
             // single-pass mode: the output slot of case k was fixed before the kernel (prefix sum over INPUT sizes +
@@ -490,9 +511,11 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
     }
 }
 
-// WARPS warps per CTA, each taking whole cases. With SYNC the CTA re-converges before every case so
+// WARPS warps per CTA, each taking whole cases. With SYNC 1 the CTA re-converges before every case so
 // that its warps walk the (large, branchy) scalar program in step and share instruction-cache
 // lines: profiles/decide_r1b showed 53% of stall samples on instruction fetch with free-running warps.
+// Measured on C3 in single-pass mode (profiles/variants_r1.txt): barrier per case 4.3 ms, every 2nd case 5.2,
+// every 4th 5.9, split-phase (SYNC -1) 4.7, an extra barrier before the copy 4.6, free-running 6.3-6.4.
 template <int WARPS, int SYNC, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 eb_decide_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ off, BatchParams bp, Arenas ar,
@@ -510,10 +533,16 @@ eb_decide_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ 
     Rng par; par.mode = 0; par.a1 = bp.parent_a1; par.a2 = bp.parent_a2; par.a3 = bp.parent_a3; par.draws = 0; par.key = 0; par.ctr_hi = 0;
     par.jump(3 * (bp.first_case - 1 + warp_global));
     uint32_t s1 = modpow_u32<30269>(AS_M1, 3 * nwarps), s2 = modpow_u32<30307>(AS_M2, 3 * nwarps), s3 = modpow_u32<30323>(AS_M3, 3 * nwarps);
+    // SYNC -1: split-phase barrier (arrive after deciding, wait before the next decision)
+    __shared__ uint64_t mbar_store;
+    uint64_t* mbar = SYNC < 0 ? &mbar_store : nullptr;
+    if (SYNC < 0) { if (threadIdx.x == 0) mbar_init(mbar, WARPS); __syncthreads(); }
     for (uint64_t r = 0; r < rounds; r++) {
-        if (SYNC && r % (SYNC ? SYNC : 1) == 0) __syncthreads();
+        if (SYNC > 0) __syncthreads();
         uint64_t k = r * nwarps + warp_global;
-        if (k < bp.n_cases) decide_one_case(ws, bp, a, k, par.a1, par.a2, par.a3);
+        if (k < bp.n_cases) decide_one_case(ws, bp, a, k, par.a1, par.a2, par.a3, mbar);
+        else if (SYNC < 0) mbar_arrive_warp(mbar);
+        if (SYNC < 0) mbar_wait(mbar, (uint32_t)(r & 1));
         par.a1 = (int32_t)(((uint32_t)par.a1 * s1) % 30269u); par.a2 = (int32_t)(((uint32_t)par.a2 * s2) % 30307u); par.a3 = (int32_t)(((uint32_t)par.a3 * s3) % 30323u);
     }
 }

@@ -87,7 +87,7 @@ static void launch_decide(int grid, cudaStream_t st, const uint8_t* d, const uin
 }
 #define DV(W, S, M) {W, M, #W "w" #S #M "m", prepare_decide<W, S, M>, launch_decide<W, S, M>}
 // measured on C3 (profiles/variants_r1.txt): 32w-sync 2.55 ms | 16w-sync 2.76 | 4w-free 3.55 | 32w-free 3.55
-static const DecideVariant decide_variants[] = {DV(32, 1, 1), DV(32, 2, 1), DV(32, 4, 1), DV(32, 8, 1), DV(16, 4, 2), DV(4, 0, 8)};
+static const DecideVariant decide_variants[] = {DV(32, 1, 1), DV(32, -1, 1), DV(16, 1, 2), DV(4, 0, 8)};
 static const int n_decide_variants = (int)(sizeof(decide_variants) / sizeof(decide_variants[0]));
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_); return EB200_ERR_CUDA; } } while (0)
