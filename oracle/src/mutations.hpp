@@ -5,6 +5,9 @@
 // and the weighted scheduler (mux_fuzzers :1258-1280).
 #pragma once
 #include <zlib.h>
+#include <cstring>
+#include <functional>
+#include <memory>
 #include "common.hpp"
 #include "erl_lists.hpp"
 #include "strlex.hpp"
@@ -504,6 +507,13 @@ struct Mutations {
         return o;
     }
     MutRes base64_mutator(const Blocks& ll);   // defined after the scheduler (it runs a nested one)
+    // sgml.hpp / json.hpp (they run nested schedulers on inner text)
+    int depth = 0;
+    std::string ssrf_uri() const;
+    void inner_muta(const std::vector<int>& ids, std::unique_ptr<Mutations>& m, Opts& o2, std::vector<MutNode>& nodes);
+    static Bin inner_round(Mutations& m, const std::vector<MutNode>& nodes, const Bin& b);
+    MutRes sgml_mutate(const Blocks& ll);
+    MutRes json_mutate(const Blocks& ll);
 
     // ------------------------------------------------------------ scheduler :1234-1280, 1385-1395
     std::vector<MutNode> make_mutator_nodes() {   // make_mutator/2 + mutators_mutator/1
@@ -528,6 +538,8 @@ struct Mutations {
         case M_AB: case M_AD: return ascii_muta(node.fn, ll);
         case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: return tree_muta(node.fn, ll);
         case M_LEN: return length_predict(ll);
+        case M_SGM: return sgml_mutate(ll);
+        case M_JS: return json_mutate(ll);
         case M_URI: { MutRes r = uri_mutator(ll); node.fn = M_B64; return r; }
         case M_B64: return base64_mutator(ll);
         case M_NIL: { MutRes r; r.ll = ll; r.delta = -1; return r; }
@@ -598,3 +610,6 @@ inline MutRes Mutations::base64_mutator(const Blocks& ll) {
 }
 
 }  // namespace eo
+
+#include "sgml.hpp"
+#include "json.hpp"

@@ -240,3 +240,74 @@ def test_fuzzer_is_a_pure_function_of_seed_and_input():
 def test_empty_and_tiny_inputs():
     outs, meta = O.fuzzer([b"", b"a", b"\n", b"0"], mutations={"bd": 1, "num": 1, "ld": 1, "sr": 1}, seed=(3, 2, 1), n_cases=200)
     assert all(m.status == 0 for m in meta)
+
+
+# ---- sgm / js (src/erlamsa_sgml.erl, src/erlamsa_json.erl): the reference has no tests for them; the expectations
+# below are derived by hand from the cited clauses and pin the restatement against regressions.
+def _outs(code, data, n=300):
+    res = {}
+    for s in range(n):
+        out, d, rc = O.run_mutator(code, data, (s + 1, s * 7 + 3, s * 13 + 5))
+        res.setdefault((out if rc == 0 else None, d if rc == 0 else None, rc), 0)
+        res[(out if rc == 0 else None, d if rc == 0 else None, rc)] += 1
+    return res
+
+
+def test_sgml_refuses_non_markup():
+    # tz(nil, <<>>) :83 -> throw(incorrect_sgml): unchanged, delta -1; binarish data never reaches the tokenizer (:185-186)
+    for data in (b"hello", b"no tags here at all", b"\x00\x01<a>x</a>", b"<a", b"<a b='1"):
+        assert set(_outs("sgm", data, 40)) == {(data, -1.0, 0)}
+
+
+def test_sgml_unterminated_comment_as_first_tag_kills_the_case():
+    # tz({'!--',_}, <<>>) has no clause (:99-100): function_clause is an error, not the throw sgml_mutate/2 catches (:754)
+    assert set(_outs("sgm", b"<!-- x", 20)) == {(None, None, 2)}
+    # ... but after the first tag it sits inside the catch-all try of :74-79 and degrades to text
+    outs = _outs("sgm", b"<a><!-- x", 200)
+    assert all(rc == 0 for (_, _, rc) in outs) and (b"<a><!-- x", -1.0, 0) in outs
+
+
+def test_sgml_refold_normalises_and_drops_leading_text():
+    # bytes before the first '<' are skipped by tz(nil,_) :82; attributes refold as " name=value" (:290-301), sc as " />" (:313)
+    outs = _outs("sgm", b"pre<a b='1'  c >t<br/></a>post", 400)
+    changed = [o for (o, d, rc) in outs if rc == 0 and o != b"pre<a b='1'  c >t<br/></a>post"]
+    assert changed and all(not o.startswith(b"pre") for o in changed)
+    assert any(o == b"<a b='1' c>t<br /></a>post" for o in changed)          # a no-op mutation still re-serialises
+
+
+def test_sgml_breaktag_reverses_children():
+    # sgml_breaktag :590-601: Internals ++ [{open,..} | Tree] is prepended to a list that is reversed afterwards
+    outs = _outs("sgm", b"<p>1<b>2</p>3</b>", 400)
+    assert any(o == b"<p>2<b>13</b>" for (o, d, rc) in outs)
+    # closed-earlier recovery (:225-234, :210-213) keeps the document text identical when nothing is mutated
+    assert any(o == b"<p>1<b>2</p>3</b>" and d == -1.0 for (o, d, rc) in outs)
+
+
+def test_sgml_xmlns_injection_uses_ssrf_endpoint():
+    outs = _outs("sgm", b"<a>x</a>", 300)
+    want = b'<a xmlns="http://localhost:51234/" xmlns:xsi="http://localhost:51234/" xsi:schemaLocation="http://localhost:51234/">x</a>'
+    assert any(o == want and d == 1.0 for (o, d, rc) in outs)
+
+
+def test_json_tokenizer_tolerance():
+    # a second top-level value is refused (ws/3 with an empty context, :103); EOF inside a structure drops it (:89)
+    assert set(_outs("js", b"1 2", 40)) == {(b"1 2", -1.0, 0)}
+    assert set(_outs("js", b'{"a" 1}', 40)) == {(b'{"a" 1}', -1.0, 0)}
+    assert set(_outs("js", b'{"a":1', 40)) == {(b"", -1.0, 0)}
+    # anything without separators is one "number" token (:188-195); dup of the lone token refolds as a bracketed list (:277-279)
+    outs = _outs("js", b"hello", 400)
+    assert (b"hello", -1.0, 0) in outs and any(o == b"[hello,hello]" and d == 1.0 for (o, d, rc) in outs)
+    # unterminated string -> junkstring with the quote appended (:185-186), folded with both quotes again (:263-264)
+    assert any(o == b'"abc""' for (o, d, rc) in _outs("js", b'"abc', 50))
+
+
+def test_json_structure_and_value_mutations():
+    doc = b'{"a":[1,true,null],"b":"str"}'
+    outs = _outs("js", doc, 600)
+    got = {o for (o, d, rc) in outs if rc == 0}
+    assert b'{"a":[1,false,null],"b":"str"}' in got                         # basic_type_mutation(Boolean)
+    assert b'{"a":[1,true,"%n%s"],"b":"str"}' in got                        # mutate_null/2 :640-643
+    assert any(o.startswith(b'{"@class"') or o.startswith(b'{"$type"') or o.startswith(b'{"__type"') for o in got)   # :615-618
+    assert all(rc in (0, 2) for (_, _, rc) in outs)                         # swap/insert may hit the badmatch of :576-577
+    pumped = {o for (o, d, rc) in _outs("js", b"[1,2,3]", 400) if rc == 0 and d == -2.0 and o.startswith(b"[")}
+    assert b"[1,2,[1,2,[1,2,[1,2,3]]]]" in pumped                           # json_pump, PumpCnt = 2 (:560): the 2nd round re-inserts the pumped tree
