@@ -443,7 +443,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         const uint8_t* blob = data + off[b]; uint32_t blen = (uint32_t)(off[b + 1] - off[b]);
         CaseCtx c; c.ws = ws; c.bp = &bp; c.ar = ar;
         c.temp_base = ar.temp ? ar.temp + (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ar.temp_per_warp : nullptr;
-        c.temp_used = 0;
+        c.temp_used = 0; c.temp_floor = 0; c.snand_kind = bp.snand_kind;
         // thread seed: three erand(99999) at parent draw index 3*(I-1) (the caller keeps the parent state there)
         Rng par; par.mode = 0; par.a1 = pa1; par.a2 = pa2; par.a3 = pa3; par.draws = 0; par.key = 0; par.ctr_hi = 0;
         int64_t ts0 = (int64_t)par.erand(99999), ts1 = (int64_t)par.erand(99999), ts2 = (int64_t)par.erand(99999);

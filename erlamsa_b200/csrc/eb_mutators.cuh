@@ -98,7 +98,7 @@ EB_DEV void mut_bytes(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutResul
             t_push(ws, seg_copy(V, l));
         }
     } else {   // randmask :279-307 -- one occurs draw per byte (drawn one byte ahead), plus a mask draw when it hit
-        int kind = (id == M_SNAND) ? c.bp->snand_kind : 3;
+        int kind = (id == M_SNAND) ? c.snand_kind : 3;
         uint8_t* buf = scratch_alloc(c, l);
         if (!buf) { r.kind = RES_SAME; r.delta = 0; return; }
         uint64_t prob = g.erand(100);
@@ -315,12 +315,14 @@ EB_DEV void mut_st_line(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutRes
 #include "eb_mut_tree.cuh"
 #include "eb_mut_fuse.cuh"
 #include "eb_field.cuh"
+#include "eb_mut_nested.cuh"
 namespace eb {
 
 // mutators whose working tables live in the per-warp temp arena
 __host__ __device__ inline bool mut_needs_temp(int id) {
     switch (id) {
-    case M_AB: case M_AD: case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: case M_FT: case M_FN: case M_FO: case M_LEN: return true;
+    case M_AB: case M_AD: case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: case M_FT: case M_FN: case M_FO: case M_LEN:
+    case M_URI: case M_B64: case M_SGM: case M_JS: return true;
     default: return false;
     }
 }
@@ -329,7 +331,7 @@ __host__ __device__ inline bool mut_needs_temp(int id) {
 __host__ EB_DEV bool mut_supported(int id) {
     switch (id) {
     case M_AB: case M_AD: case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: case M_FT: case M_FN: case M_FO:
-    case M_LEN: case M_ZIP:
+    case M_LEN: case M_ZIP: case M_URI: case M_B64: case M_SGM: case M_JS:   // sgm / js: refusal and single-token paths; the rest flags the case
     case M_UW: case M_UI: case M_NUM:
     case M_BD: case M_BEI: case M_BED: case M_BF: case M_BI: case M_BER: case M_BR:
     case M_SP: case M_SR: case M_SD: case M_SNAND: case M_SRND:
@@ -339,25 +341,43 @@ __host__ EB_DEV bool mut_supported(int id) {
     }
 }
 
-EB_DEV void mut_apply(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) {
+// the mutators that never run a nested scheduler; false when `row` is not one of them
+__device__ __forceinline__ bool mut_apply_base(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) {
     int id = row.fn;
     switch (id) {
-    case M_BD: case M_BEI: case M_BED: case M_BF: case M_BI: case M_BER: case M_BR: case M_UW: case M_UI: mut_byte(c, id, p, n, r); return;
-    case M_SP: case M_SR: case M_SD: case M_SNAND: case M_SRND: mut_bytes(c, id, p, n, r); return;
-    case M_NUM: mut_num(c, p, n, r); return;
-    case M_AB: case M_AD: mut_ascii(c, id, p, n, r); return;
-    case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: mut_tree(c, id, p, n, r); return;
-    case M_FT: case M_FN: case M_FO: mut_fuse(c, id, p, n, r); return;
-    case M_LEN: mut_len(c, p, n, r); return;
+    case M_BD: case M_BEI: case M_BED: case M_BF: case M_BI: case M_BER: case M_BR: case M_UW: case M_UI: mut_byte(c, id, p, n, r); return true;
+    case M_SP: case M_SR: case M_SD: case M_SNAND: case M_SRND: mut_bytes(c, id, p, n, r); return true;
+    case M_NUM: mut_num(c, p, n, r); return true;
+    case M_AB: case M_AD: mut_ascii(c, id, p, n, r); return true;
+    case M_TR2: case M_TD: case M_TS1: case M_TS2: case M_TR: mut_tree(c, id, p, n, r); return true;
+    case M_FT: case M_FN: case M_FO: mut_fuse(c, id, p, n, r); return true;
+    case M_LEN: mut_len(c, p, n, r); return true;
+    case M_URI: mut_uri(c, row, p, n, r); return true;
+    case M_SGM: mut_sgm(c, p, n, r); return true;
     case M_ZIP: {   // zip_path_traversal :1149-1163 on data that is not a ZIP archive: zip:foldl fails, delta -1, no draws
         bool z = false; { uint32_t hit = 0; for (uint32_t i = lane_id(); i + 4 <= n; i += 32) hit |= (p[i] == 'P' && p[i + 1] == 'K' && p[i + 2] == 5 && p[i + 3] == 6) ? 1u : 0u; z = __any_sync(0xffffffffu, hit != 0); }
-        r.kind = z ? RES_UNSUPPORTED : RES_SAME; r.delta = -1; r.rechunk = 0; r.consumed_next = 0; return;
+        r.kind = z ? RES_UNSUPPORTED : RES_SAME; r.delta = -1; r.rechunk = 0; r.consumed_next = 0; return true;
     }
-    case M_LD: case M_LDS: case M_LR2: case M_LRI: case M_LR: case M_LS: case M_LP: mut_line(c, id, p, n, r); return;
-    case M_LIS: case M_LRS: mut_st_line(c, id, p, n, r); return;
-    case M_NIL: r.kind = RES_SAME; r.delta = -1; r.rechunk = 0; r.consumed_next = 0; return;
-    default: r.kind = RES_UNSUPPORTED; r.delta = 0; r.rechunk = 0; r.consumed_next = 0; return;
+    case M_LD: case M_LDS: case M_LR2: case M_LRI: case M_LR: case M_LS: case M_LP: mut_line(c, id, p, n, r); return true;
+    case M_LIS: case M_LRS: mut_st_line(c, id, p, n, r); return true;
+    case M_NIL: r.kind = RES_SAME; r.delta = -1; r.rechunk = 0; r.consumed_next = 0; return true;
+    default: return false;
     }
+}
+// dispatch for a round of the case's own scheduler
+EB_DEV void mut_apply(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) {
+    if (mut_apply_base(c, row, p, n, r)) return;
+    if (row.fn == M_B64) { mut_b64<true>(c, p, n, r); return; }
+    if (row.fn == M_JS) { mut_js<true>(c, p, n, r); return; }
+    r.kind = RES_UNSUPPORTED; r.delta = 0; r.rechunk = 0; r.consumed_next = 0;
+}
+// dispatch inside a nested round (eb_mut_nested.cuh): one level of nesting is executed on the device; a nested
+// round that would itself open one (b64 inside decoded base64, inner-text js) flags the case instead
+EB_DEV void mut_apply_inner(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) {
+    if (mut_apply_base(c, row, p, n, r)) return;
+    if (row.fn == M_JS) { mut_js<false>(c, p, n, r); return; }
+    if (row.fn == M_B64) { mut_b64<false>(c, p, n, r); return; }
+    r.kind = RES_UNSUPPORTED; r.delta = 0; r.rechunk = 0; r.consumed_next = 0;
 }
 
 }  // namespace eb

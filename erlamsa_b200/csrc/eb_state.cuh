@@ -60,6 +60,8 @@ struct CaseCtx {
     const uint8_t* next_p; uint32_t next_n; int has_next;   // the block after This (sed_fuse_next reads it)
     uint8_t* temp_base;      // this warp's reusable temp region
     uint64_t temp_used;
+    uint64_t temp_floor;     // temp_reset() rewinds to here: a mutator that runs a nested scheduler parks its own tables below
+    int snand_kind;          // mask function bound to `snand` when the current table was built (mutations/1 :1313)
 };
 
 // ------------------------------------------------------------------ arenas
@@ -78,7 +80,7 @@ EB_DEV uint8_t* scratch_alloc(CaseCtx& c, uint64_t bytes) {
 
 // temporaries that die with the mutator attempt: bump inside the warp's private region, spilling to
 // the (never freed) scratch arena only when a single attempt needs more than the region holds
-EB_DEV void temp_reset(CaseCtx& c) { c.temp_used = 0; }
+EB_DEV void temp_reset(CaseCtx& c) { c.temp_used = c.temp_floor; }
 EB_DEV uint8_t* temp_alloc(CaseCtx& c, uint64_t bytes) {
     uint64_t need = align16(bytes) + 16;
     if (c.temp_base && c.temp_used + need <= c.ar.temp_per_warp) { uint8_t* p = c.temp_base + c.temp_used; c.temp_used += need; return p; }

@@ -83,3 +83,45 @@ def uniform_corpus(seed, count, size, kind="bin"):
     r = rng(seed)
     f = {"bin": random_bytes, "num": numeric_text, "lines": text_lines}[kind]
     return [f(r, size) for _ in range(count)]
+
+
+def web_corpus(seed, count):
+    """blobs for uri / b64 / js / sgm: URLs inside text, base64 runs fenced by binary bytes (so that a whole
+    strlex text chunk decodes), JSON scalars, and small markup / JSON documents"""
+    import base64
+    r = rng(seed)
+    words = [b"alpha", b"beta", b"gamma", b"delta", b"x", b"42", b"lorem", b"ipsum"]
+    urls = [b"http://example.com/a/b?q=1", b"file://etc/passwd", b"https://host.tld//x///y/z", b"ftp://h", b"a://", b"s3://bucket/key/with/parts",
+            b"file://////", b"://leading", b"gopher://a.b/c"]
+    scalars = [b"12345", b"-17", b" 0", b"+5", b"true", b"false", b"null", b'"a string value"', b'"unterminated', b"hello", b"1e9", b"007", b'""',
+               b"123456789012345678901234567890", b"  null  ", b"3.14"]
+    docs = [b"<a>x</a>", b"<p>1<b>2</p>3</b>", b'<r a="1" b=\'2\' c>t<br/><!-- c --></r>', b"<?xml v?><a/>", b"<!-- x", b"<a", b"text < 3 and > 2",
+            b'{"a":[1,true,null],"b":"str"}', b"[1,2,3]", b'{"k" 1}', b"[1,2", b"{}", b"[]", b'{"a":{"b":[{"c":"d"}]}}']
+    out = []
+    for i in range(count):
+        k = i % 5
+        if k == 0:      # text with URLs
+            parts = []
+            for _ in range(int(r.integers(1, 12))):
+                parts.append(urls[int(r.integers(0, len(urls)))] if r.random() < 0.4 else words[int(r.integers(0, len(words)))])
+                parts.append([b" ", b"\n", b"\x00", b"\xfe", b"\"", b"'"][int(r.integers(0, 6))])
+            out.append(b"".join(parts))
+        elif k == 1:    # base64 runs fenced by non-text bytes
+            parts = []
+            for _ in range(int(r.integers(1, 6))):
+                raw = random_bytes(r, int(r.integers(0, 40))) if r.random() < 0.5 else text_lines(r, int(r.integers(1, 60)))
+                enc = base64.b64encode(raw)
+                if r.random() < 0.2:
+                    enc = enc[:len(enc) // 2] + b"\n" + enc[len(enc) // 2:]      # white space inside is skipped by the decoder
+                if r.random() < 0.15:
+                    enc = enc[:-1]                                               # broken quantum
+                parts.append(enc)
+                parts.append(bytes([int(r.integers(0x80, 0x100))]) * int(r.integers(1, 3)))
+            out.append(b"".join(parts))
+        elif k == 2:
+            out.append(scalars[int(r.integers(0, len(scalars)))])
+        elif k == 3:
+            out.append(docs[int(r.integers(0, len(docs)))])
+        else:
+            out.append(structured_text(r, int(r.integers(1, 400))))
+    return out

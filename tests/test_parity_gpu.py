@@ -65,6 +65,39 @@ def test_structure_mutators_multi_round(engine, oracle):
     compare(engine, oracle, blobs, muts, {"nd": 2, "bu": 1, "od": 1}, seed=(2, 7, 1), allow_unsupported=True)
 
 
+def test_uri_mutator(engine, oracle):
+    """every text chunk holding "://" is rewritten; the mutator then rebinds itself to b64 for the following rounds"""
+    blobs = corpus.web_corpus(0xE21A0900, 300)
+    n = compare(engine, oracle, blobs, {"uri": 1}, {"od": 1}, seed=(5, 5, 5))
+    assert n >= len(blobs) - 10          # "scheme://" with nothing but slashes behind it kills the case on both sides (badmatch :745,:751)
+    compare(engine, oracle, blobs, {"uri": 1, "bd": 1}, {"nd": 1, "bu": 1}, seed=(5, 6, 5), allow_unsupported=True)
+
+
+def test_b64_mutator_nested_round(engine, oracle):
+    """decodable chunks get one nested scheduler round over the whole default table; only a second level of nesting
+    (or an sgm/js document inside the decoded bytes) may flag a case"""
+    blobs = corpus.web_corpus(0xE21A0901, 300)
+    n = compare(engine, oracle, blobs, {"b64": 1}, {"od": 1}, seed=(6, 5, 5), allow_unsupported=True)
+    assert n >= len(blobs) * 0.85
+
+
+def test_sgm_js_refusals_and_scalar_documents(engine, oracle):
+    blobs = corpus.web_corpus(0xE21A0902, 300) + corpus.mixed_corpus(0xE21A0903, 60, 300)
+    n = compare(engine, oracle, blobs, {"sgm": 10, "js": 3, "nil": 0}, {"od": 1}, seed=(7, 5, 5), allow_unsupported=True)
+    assert n >= len(blobs) * 0.7
+    n = compare(engine, oracle, blobs, {"js": 1}, {"od": 1}, seed=(8, 5, 5), allow_unsupported=True)
+    assert n >= len(blobs) * 0.8
+
+
+def test_true_default_mutator_mix(engine, oracle):
+    """all 41 mutators at the reference's default priorities (src/erlamsa_mutations.erl:1291-1331) and the default patterns"""
+    import erlamsa_b200.options as eo
+    muts = dict(eo.default_mutations())
+    blobs = corpus.mixed_corpus(0xE21A0904, 200, 2000) + corpus.web_corpus(0xE21A0905, 100)
+    n = compare(engine, oracle, blobs, muts, {"od": 1, "nd": 2, "bu": 1, "sk": 2, "sz": 2, "cs": 1, "ar": 1, "cp": 1}, seed=(9, 5, 5), allow_unsupported=True)
+    assert n >= len(blobs) * 0.6
+
+
 def framed_corpus(seed, count):
     """blobs that really carry length fields / xor8 / crc32 trailers, so the sizer and checksum searches FIND something"""
     import struct
