@@ -31,8 +31,8 @@ WORKLOADS = {
            "C3: 100000 x 65536 B uniform-random seeds; bd,bei,bed,bf,bi,ber,br,num; pattern od"),
     "c3num": (100000, 65536, "num", ["bd", "bei", "bed", "bf", "bi", "ber", "br", "num"], {"od": 1},
               "C3(ii): 100000 x 65536 B numeric text; bd,bei,bed,bf,bi,ber,br,num; pattern od"),
-    "c2": (10000, 4096, "bin", None, {"od": 1, "nd": 2, "bu": 1},
-           "C2: 10000 x 4096 B uniform-random seeds; device-supported part of the default mutator mix; od,nd,bu"),
+    "c2": (10000, 4096, "bin", None, {"od": 1, "nd": 2, "bu": 1, "sk": 2, "sz": 2, "cs": 1, "ar": 1, "cp": 1, "co": 0, "nu": 0},
+           "C2: 10000 x 4096 B uniform-random seeds; all 41 mutators at the reference's default priorities; default patterns"),
 }
 
 
@@ -147,6 +147,10 @@ def run_ours(args):
     d_out_off = torch.empty(n_cases + 1, dtype=torch.int64, device=dev)
     d_out_len = torch.empty(n_cases, dtype=torch.int64, device=dev)
     base_opts = {"mutations": muts, "patterns": pats, "seed": (1, 2, 3), "rng": args.rng, "scratch_bytes": 512 << 20}
+    if args.workload == "c2":   # repeat mutators compounded by nd/bu rounds: cap a case at 1 MiB (flagged, not dropped) and give the literals room
+        base_opts.update({"scratch_bytes": 8 << 30, "max_case_out": 1 << 20})
+        out_cap += 4 << 30
+        d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
     def step(i):
@@ -167,10 +171,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     ev0.record(stream)
     apply_ms, decide_ms, scan_ms, launches, bytes_out = [], [], [], 0, 0
+    flagged = {"unsupported": 0, "died": 0, "overflow": 0}
     for i in range(args.steps):
         st = step(args.warmup + i)
         apply_ms.append(st.ms_apply); decide_ms.append(st.ms_decide); scan_ms.append(st.ms_scan)
         launches += st.kernels_launched; bytes_out += st.bytes_out
+        flagged["unsupported"] += st.n_unsupported; flagged["died"] += st.n_died; flagged["overflow"] += st.n_overflow
     ev1.record(stream)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
@@ -236,6 +242,9 @@ def run_ours(args):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": dom_ms},
         "kernel_ms": {"decide": sum(decide_ms) / len(decide_ms), "scan": sum(scan_ms) / len(scan_ms), "apply": avg_apply},
         "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+        # rank 0's cases the engine did not mutate: paths without a device implementation (output = input, reported per
+        # case in eb200_meta.status), worker crashes the reference has too, per-case output cap
+        "flagged_cases": dict(flagged, of=n_cases * args.steps),
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args, size, kind, muts, pats, threads=1, budget_s=12.0)
