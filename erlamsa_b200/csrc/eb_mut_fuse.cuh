@@ -29,31 +29,64 @@ struct FuseSide {
 };
 
 // One node, one side: classify the suffix list src[0,k) by first byte into dst[base ...), classes in ascending
-// byte order, each class newest-first. After the call: bits = existing classes, start[c]/cnt2[c] describe class c.
-// `csize` (256 entries) receives the class sizes (cnt is consumed back to zero by the placement walk).
+// byte order, each class newest-first. After the call: bits = existing classes, start[c]/csize[c] describe class c
+// (cnt is consumed back to zero by the placement pass). Thirty-two suffixes per step: lanes holding the same byte
+// find each other with match.any, the lowest of them owns the class counter for that step.
 EB_DEV uint32_t fuse_classify(FuseSide& sd, const uint32_t* src, uint32_t k, uint32_t* dst, uint32_t base, uint32_t* csize) {
+    const int l = lane_id(); const uint32_t lt = (1u << l) - 1u;
     for (int i = 0; i < 8; i++) sd.bits[i] = 0;
+    // the suffix holding only the block's last byte is dropped when it is the FIRST of its class ([[]] -> [], :68-70)
+    uint32_t sq = 0xffffffffu, sch = 0;
+    for (uint32_t q0 = 0; q0 < k; q0 += 32) {
+        uint32_t q = q0 + l; uint32_t p = q < k ? src[q] : 0xffffffffu;
+        uint32_t hit = __ballot_sync(0xffffffffu, q < k && p + 1 == sd.len);
+        if (hit) { sq = q0 + (uint32_t)__ffs(hit) - 1; sch = sd.s[sd.len - 1]; break; }
+    }
     bool special_dropped = false;
-    for (uint32_t q = 0; q < k; q++) {                 // count
-        uint32_t p = src[q];
-        if (p >= sd.len) continue;                      // the [] suffix contributes nothing (:68)
-        uint32_t ch = sd.s[p];
-        sd.bits[ch >> 5] |= 1u << (ch & 31);
-        if (p + 1 == sd.len && sd.cnt[ch] == 0) { special_dropped = true; continue; }   // [[]] -> []
-        sd.cnt[ch] = sd.cnt[ch] + 1;
+    if (sq != 0xffffffffu) {
+        uint32_t before = 0;
+        for (uint32_t q0 = 0; q0 < sq; q0 += 32) {
+            uint32_t q = q0 + l; uint32_t p = q < sq ? src[q] : 0xffffffffu;
+            before |= __ballot_sync(0xffffffffu, q < sq && p < sd.len && sd.s[p] == sch);
+            if (before) break;
+        }
+        special_dropped = before == 0;
+    }
+    for (uint32_t q0 = 0; q0 < k; q0 += 32) {                          // count
+        uint32_t q = q0 + l; uint32_t p = q < k ? src[q] : 0xffffffffu;
+        bool live = q < k && p < sd.len;                                // the [] suffix contributes nothing (:68)
+        uint32_t ch = live ? sd.s[p] : 0x100u + (uint32_t)l;
+        for (int w = 0; w < 8; w++) sd.bits[w] |= __reduce_or_sync(0xffffffffu, (live && (int)(ch >> 5) == w) ? 1u << (ch & 31) : 0u);
+        bool counted = live && !(special_dropped && q == sq);
+        uint32_t key = counted ? ch : 0x100u + (uint32_t)l;
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (counted && (peers & lt) == 0) sd.cnt[ch] = sd.cnt[ch] + (uint32_t)__popc(peers);
+        __syncwarp();
     }
     uint32_t run = base;
-    for (int w = 0; w < 8; w++) {                       // class starts, ascending byte
+    for (int w = 0; w < 8; w++) {                                       // class starts, ascending byte
         uint32_t m = sd.bits[w];
-        while (m) { uint32_t b = (uint32_t)__ffs(m) - 1; m &= m - 1; uint32_t ch = (uint32_t)w * 32 + b; sd.start[ch] = run; csize[ch] = sd.cnt[ch]; run += sd.cnt[ch]; }
+        while (m) {
+            uint32_t b = (uint32_t)__ffs(m) - 1; m &= m - 1; uint32_t ch = (uint32_t)w * 32 + b;
+            uint32_t cc = sd.cnt[ch];
+            if (l == 0) { sd.start[ch] = run; csize[ch] = cc; }
+            run += cc;
+        }
     }
-    for (uint32_t q = 0; q < k; q++) {                 // place: first arrival lands last in its class
-        uint32_t p = src[q];
-        if (p >= sd.len) continue;
-        if (p + 1 == sd.len && special_dropped) continue;
-        uint32_t ch = sd.s[p];
-        uint32_t c2 = sd.cnt[ch] - 1; sd.cnt[ch] = c2;
-        dst[sd.start[ch] + c2] = p + 1;
+    __syncwarp();
+    for (uint32_t q0 = 0; q0 < k; q0 += 32) {                          // place: first arrival lands last in its class
+        uint32_t q = q0 + l; uint32_t p = q < k ? src[q] : 0xffffffffu;
+        bool placed = q < k && p < sd.len && !(special_dropped && q == sq);
+        uint32_t ch = placed ? sd.s[p] : 0;
+        uint32_t key = placed ? ch : 0x100u + (uint32_t)l;
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        uint32_t left = placed ? sd.cnt[ch] : 0;
+        __syncwarp();
+        if (placed) {
+            dst[sd.start[ch] + left - 1 - (uint32_t)__popc(peers & lt)] = p + 1;
+            if ((peers & lt) == 0) sd.cnt[ch] = left - (uint32_t)__popc(peers);
+        }
+        __syncwarp();
     }
     return run - base;
 }
@@ -80,10 +113,56 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
         if (!stop) stop = g.rand(8) == 0;
         uint32_t nnext = 0;
         if (!stop) {
-            int nx = cur ^ 1; uint32_t fo = 0, to = 0;
+            const int nx = cur ^ 1; uint32_t fo = 0, to = 0;
             // nodes are stored in emission order; the reference's list is that order reversed
-            for (uint32_t e = ncur; e-- > 0;) {
-                FNode nd = ND[cur][e];
+            uint32_t e = ncur;
+            const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
+            while (e > 0) {
+                // (1) a run of nodes with at most one suffix on each side (what random data degenerates to after two
+                //     levels): one node per lane, same classification rules written out for the one-element lists
+                bool valid = (uint32_t)l < e;
+                FNode nd; nd.fo = nd.to = 0; nd.fc = nd.tc = 2;
+                if (valid) nd = ND[cur][e - 1 - (uint32_t)l];
+                uint32_t sm = __ballot_sync(0xffffffffu, valid && nd.fc <= 1 && nd.tc <= 1);
+                uint32_t runlen = sm == 0xffffffffu ? 32u : (uint32_t)__ffs(~sm) - 1u;
+                if (runlen > 0) {
+                    bool act = (uint32_t)l < runlen;
+                    uint32_t fa = 0, tb = 0, fval = 0, tval = 0, tsize = 0; bool quirk = false, child = false;
+                    if (act) {
+                        bool ha = nd.fc == 1; uint32_t pa = ha ? F[cur][nd.fo] : na; ha = ha && pa < na;
+                        bool hb = nd.tc == 1; uint32_t pb = hb ? T[cur][nd.to] : nb; hb = hb && pb < nb;
+                        uint32_t cha = ha ? a[pa] : 0x100u, chb = hb ? b[pb] : 0x200u;
+                        bool a_drop = ha && pa + 1 == na, b_drop = hb && pb + 1 == nb;
+                        if (ha && !a_drop) { fval = pa + 1; fa = 1; }
+                        if (hb && !b_drop) { tval = pb + 1; tb = 1; }
+                        if (a_drop) quirk = true;                                  // {_Char, []} -> [[[]], []] (:91-93)
+                        else if (ha && cha == chb) { child = true; tsize = tb; }
+                    }
+                    uint32_t fadd = fa + (quirk ? 1u : 0u), tadd = tb + (quirk ? 1u : 0u), cadd = (quirk || child) ? 1u : 0u;
+                    uint32_t fpre = fadd, tpre = tadd;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, fpre, o), y = __shfl_up_sync(0xffffffffu, tpre, o); if (l >= o) { fpre += x; tpre += y; } }
+                    uint32_t ftot = __shfl_sync(0xffffffffu, fpre, 31), ttot = __shfl_sync(0xffffffffu, tpre, 31);
+                    uint32_t cm = __ballot_sync(0xffffffffu, cadd != 0);
+                    uint32_t ctot = (uint32_t)__popc(cm);
+                    if ((uint64_t)fo + ftot > fcap || (uint64_t)to + ttot > tcap || (uint64_t)nnext + ctot > ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
+                    uint32_t f0 = fo + fpre - fadd, t0 = to + tpre - tadd;
+                    if (fa) F[nx][f0] = fval;
+                    if (tb) T[nx][t0] = tval;
+                    if (quirk) { F[nx][f0 + fa] = na; T[nx][t0 + tb] = nb; }
+                    if (cadd) {
+                        FNode ch_n;
+                        if (quirk) { ch_n.fo = f0 + fa; ch_n.fc = 1; ch_n.to = t0 + tb; ch_n.tc = 1; }
+                        else { ch_n.fo = f0; ch_n.fc = 1; ch_n.to = t0; ch_n.tc = tsize; }
+                        ND[nx][nnext + (uint32_t)__popc(cm & ltm)] = ch_n;
+                    }
+                    fo += ftot; to += ttot; nnext += ctot; e -= runlen;
+                    __syncwarp();
+                    continue;
+                }
+                // (2) a node with longer lists: warp-parallel classification, children walked class by class
+                e--;
+                nd = ND[cur][e];
                 uint32_t fa = fuse_classify(sa, F[cur] + nd.fo, nd.fc, F[nx], fo, sizeA);
                 uint32_t tb = fuse_classify(sb, T[cur] + nd.to, nd.tc, T[nx], to, sizeB);
                 for (int w = 0; w < 8; w++) {
@@ -93,17 +172,20 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
                         FNode ch_n;
                         if (sizeA[ch] == 0) {       // {_Char, []} -> [[[]], []]: the two empty suffixes, whatever B holds (:91-93)
                             if (fo + fa + 1 > fcap || to + tb + 1 > tcap || nnext >= ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
-                            F[nx][fo + fa] = na; T[nx][to + tb] = nb;
+                            if (l == 0) { F[nx][fo + fa] = na; T[nx][to + tb] = nb; }
                             ch_n.fo = fo + fa; ch_n.fc = 1; ch_n.to = to + tb; ch_n.tc = 1; fa++; tb++;
-                            ND[nx][nnext++] = ch_n; continue;
+                            if (l == 0) ND[nx][nnext] = ch_n;
+                            nnext++; continue;
                         }
                         if (!((sb.bits[w] >> bit) & 1u)) continue;                     // notfound
                         if (nnext >= ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
                         ch_n.fo = sa.start[ch]; ch_n.fc = sizeA[ch]; ch_n.to = sb.start[ch]; ch_n.tc = sizeB[ch];
-                        ND[nx][nnext++] = ch_n;
+                        if (l == 0) ND[nx][nnext] = ch_n;
+                        nnext++;
                     }
                 }
                 fo += fa; to += tb;
+                __syncwarp();
             }
             if (nnext == 0) stop = true;
             else { fuel -= (int64_t)nnext; cur = nx; ncur = nnext; continue; }

@@ -23,9 +23,11 @@ if len(sys.argv) > 2:
     print("%-3s %6d cases %8.1f ms host wall  status %s" % (pat, n, dt * 1e3, dict(c)), flush=True)
 else:
     n = sys.argv[1] if len(sys.argv) > 1 else "2000"
-    for pat in ("od", "nd", "bu", "sk", "sz", "cs", "ar", "cp"):
+    specs = [("od", "len"), ("od", "ft"), ("od", "fo"), ("od", "fn"), ("sz", "bd"), ("cs", "bd"), ("nd", "bd,sr,num,sp,ab,td"), ("nd", None), ("sk", None)]
+    for pat, muts in specs:
         try:
-            r = subprocess.run([sys.executable, __file__, pat, n], capture_output=True, text=True, timeout=60)
-            print((r.stdout.strip() or r.stderr.strip()[-300:]), flush=True)
+            r = subprocess.run([sys.executable, __file__, pat, n] + ([muts] if muts else []), capture_output=True, text=True, timeout=45)
+            print((muts or "default").ljust(20), (r.stdout.strip() or r.stderr.strip()[-300:]), flush=True)
         except subprocess.TimeoutExpired:
-            print("%-3s TIMEOUT (60 s)" % pat, flush=True)
+            print("%-3s %s TIMEOUT (45 s) -- stopping" % (pat, muts), flush=True)
+            break
