@@ -193,7 +193,8 @@ def run_ours(args):
         hb = torch.empty(e2e_cases * size + 64, dtype=torch.uint8, pin_memory=True)
         hb[: e2e_cases * size].copy_(data[: e2e_cases * size])
         hoff = (C.c_uint64 * (e2e_cases + 1))(*[i * size for i in range(e2e_cases + 1)])
-        hout = torch.empty(e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + (128 << 20), dtype=torch.uint8, pin_memory=True)
+        hout = torch.empty(e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + ((3 << 30) if args.workload == "c2" else (128 << 20)),
+                           dtype=torch.uint8, pin_memory=True)
         ho_off = (C.c_uint64 * (e2e_cases + 1))(); ho_len = (C.c_uint64 * e2e_cases)()
         st2 = N.Stats()
         o = erlamsa_b200.make_opts(base_opts)

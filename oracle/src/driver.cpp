@@ -394,6 +394,24 @@ int eo_lex_unlex(const uint8_t* in, uint64_t len, const uint8_t** out, uint64_t*
     eo::Chunks cs = eo::lex(eo::Bin((const char*)in, len)); g_unit = eo::unlex(cs);
     *out = (const uint8_t*)g_unit.data(); *out_len = g_unit.size(); if (n_chunks) *n_chunks = (int32_t)cs.size(); return 0;
 }
+// sgml: the stack-discipline builder against the clause-by-clause one (returns 0 when they agree or both refuse)
+int eo_sgml_selfcheck(const uint8_t* in, uint64_t len) {
+    using namespace eo::sgml;
+    eo::Bin s((const char*)in, len);
+    std::vector<Token> tk;
+    try { tk = tokenize(s); } catch (const TokError&) { return 0; }
+    BuildRes a = build_ast2(tk, 0, List(), {}, 0, 0);
+    BuildOut b = build_ast_iter(tk);
+    if (a.k != BuildRes::OK) return 1;
+    eo::Bin fa, fb; fold_ast(a.list, fa); fold_ast(b.list, fb);
+    if (fa != fb) return 2;
+    if (a.n != b.n || a.nt != b.nt) return 3;
+    return equal(a.list, b.list) ? 0 : 4;
+}
+int eo_tree_selfcheck(const uint8_t* in, uint64_t len) {
+    eo::TreeParser a{in, (size_t)len}, b{in, (size_t)len};
+    return a.parse() == b.parse_ref() ? 0 : 1;
+}
 int eo_funny_unicode_count(void) { return (int)eo::Mutations::funny_unicode().size(); }
 const char* eo_mutator_code(int i) { return (i >= 0 && i < eo::M_COUNT) ? eo::MUT_CODES[i] : nullptr; }
 const char* eo_pattern_code(int i) { return (i >= 0 && i < eo::P_COUNT) ? eo::PAT_CODES[i] : nullptr; }

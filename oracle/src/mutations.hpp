@@ -6,6 +6,8 @@
 #pragma once
 #include <zlib.h>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include "common.hpp"
@@ -317,8 +319,11 @@ struct Mutations {
         MutRes r; r.ll = ll; const Bin& h = ll[0];
         if (binarish(h)) { r.delta = -1; return r; }
         TreeParser tp{(const uint8_t*)h.data(), h.size()};
+        const bool trace = getenv("EO_TRACE") != nullptr;
         std::vector<Term> lst = tp.parse();
+        if (trace) fprintf(stderr, "[eo]   tree: parsed, clock %ld\n", (long)clock());
         std::vector<const Term*> subs = sublists_erl(lst);
+        if (trace) fprintf(stderr, "[eo]   tree: %zu sublists, clock %ld\n", subs.size(), (long)clock());
         Bin out;
         if (id == M_TR2 || id == M_TD) {
             const Term* sub = subs.empty() ? nullptr : subs[rng.rand_elem_idx(subs.size())];
@@ -349,6 +354,7 @@ struct Mutations {
             child = cs[rng.rand_elem_idx(cs.size())]; parent = cand; break;
         }
         uint64_t reps = rng.rand_log_u64(10);
+        if (trace) fprintf(stderr, "[eo]   tree: stutter reps %llu, clock %ld\n", (unsigned long long)reps, (long)clock());
         if (!parent) { r.delta = -1; return r; }
         auto op = [&](const std::vector<Term>& l, size_t i, Bin& o) { repeat_path_emit(*parent, *child, reps, o); flatten_tail(l, i + 1, o); };
         edit_sublist_emit(lst, child, op, out);
@@ -524,6 +530,7 @@ struct Mutations {
         return sel;
     }
     MutRes apply(MutNode& node, const Blocks& ll) {
+        if (getenv("EO_TRACE")) fprintf(stderr, "[eo] %*sapply %s on %zu bytes (%zu blocks) draws=%llu\n", depth * 2, "", MUT_CODES[node.fn], ll[0].size(), ll.size(), (unsigned long long)rng.draws);
         switch (node.fn) {
         case M_BD: case M_BEI: case M_BED: case M_BF: case M_BI: case M_BER: case M_BR: return byte_muta(node.fn, ll);
         case M_UW: return utf8_widen(ll);

@@ -51,7 +51,9 @@ inline std::string to_lower_latin1(const std::string& s) {   // string:to_lower/
 }
 
 // tz/2 from state {tag,""} at S[i..] until a {text,Str,Token} result: returns the token and the index of Str
-inline Token scan_tag(const Bin& S, size_t i, size_t& next) {
+struct LastPos { size_t gt, cend, qend, sq, dq; };   // last occurrence of '>', "-->", "?>", "'", '"': a scan past it cannot terminate
+inline LastPos last_positions(const Bin& S) { LastPos l; l.gt = S.rfind('>'); l.cend = S.rfind("-->"); l.qend = S.rfind("?>"); l.sq = S.rfind('\''); l.dq = S.rfind('"'); return l; }
+inline Token scan_tag(const Bin& S, size_t i, size_t& next, const LastPos& last) {
     const size_t n = S.size();
     auto ws = [&](size_t p) { while (p < n && is_ws((uint8_t)S[p])) p++; return p; };
     auto starts = [&](size_t p, const char* lit) { size_t l = strlen(lit); return p + l <= n && S.compare(p, l, lit) == 0; };
@@ -71,17 +73,17 @@ inline Token scan_tag(const Bin& S, size_t i, size_t& next) {
             if (i < n) { tag.push_back(S[i]); i++; continue; }                                                 // :92 (?ok is always true)
             throw TokError{true};                                                                              // :93
         case BANG:                                                                                             // :95-97
-            if (starts(i, ">")) { next = i + 1; Token t; t.k = Token::BANG; t.a = dt; return t; }
-            if (i < n) { dt.push_back(S[i]); i++; continue; }
-            throw TokError{true};
+            { size_t q = (last.gt == Bin::npos || i > last.gt) ? Bin::npos : S.find('>', i);   // the first '>' ends it
+              if (q == Bin::npos) throw TokError{true};
+              next = q + 1; Token t; t.k = Token::BANG; t.a = S.substr(i, q - i); return t; }
         case COMMENT:                                                                                          // :99-100 (no clause for <<>>: function_clause)
-            if (starts(i, "-->")) { next = i + 3; Token t; t.k = Token::COMMENT; t.a = dt; return t; }
-            if (i < n) { dt.push_back(S[i]); i++; continue; }
-            throw TokError{false};
+            { size_t q = (last.cend == Bin::npos || i > last.cend) ? Bin::npos : S.find("-->", i);
+              if (q == Bin::npos) throw TokError{false};
+              next = q + 3; Token t; t.k = Token::COMMENT; t.a = S.substr(i, q - i); return t; }
         case QUE:                                                                                              // :102-104
-            if (starts(i, "?>")) { next = i + 2; Token t; t.k = Token::QUE; t.a = dt; return t; }
-            if (i < n) { dt.push_back(S[i]); i++; continue; }
-            throw TokError{true};
+            { size_t q = (last.qend == Bin::npos || i > last.qend) ? Bin::npos : S.find("?>", i);
+              if (q == Bin::npos) throw TokError{true};
+              next = q + 2; Token t; t.k = Token::QUE; t.a = S.substr(i, q - i); return t; }
         case ETAG:                                                                                             // :106-108
             if (starts(i, "/>")) { next = i + 2; Token t; t.k = Token::SC; t.a = tag; t.params = attrs; return t; }
             if (starts(i, ">")) { next = i + 1; Token t; t.k = Token::OPEN; t.a = tag; t.params = attrs; return t; }
@@ -109,13 +111,13 @@ inline Token scan_tag(const Bin& S, size_t i, size_t& next) {
             if (starts(i, "\"")) { st = DQVAL; i++; continue; }
             st = UQVAL; continue;
         case SQVAL:                                                                                            // :130-132
-            if (starts(i, "'")) { attrs.push_back({a, v, "'"}); a.clear(); st = ATTR; i = ws(i + 1); continue; }
-            if (i < n) { v.push_back(S[i]); i++; continue; }
-            throw TokError{true};
+            { size_t q = (last.sq == Bin::npos || i > last.sq) ? Bin::npos : S.find('\'', i);
+              if (q == Bin::npos) throw TokError{true};
+              attrs.push_back({a, S.substr(i, q - i), "'"}); a.clear(); st = ATTR; i = ws(q + 1); continue; }
         case DQVAL:                                                                                            // :134-136
-            if (starts(i, "\"")) { attrs.push_back({a, v, "\""}); a.clear(); st = ATTR; i = ws(i + 1); continue; }
-            if (i < n) { v.push_back(S[i]); i++; continue; }
-            throw TokError{true};
+            { size_t q = (last.dq == Bin::npos || i > last.dq) ? Bin::npos : S.find('"', i);
+              if (q == Bin::npos) throw TokError{true};
+              attrs.push_back({a, S.substr(i, q - i), "\""}); a.clear(); st = ATTR; i = ws(q + 1); continue; }
         case UQVAL:                                                                                            // :139-142
             if ((i < n && is_ev((uint8_t)S[i])) || starts(i, "/>")) { attrs.push_back({a, v, ""}); a.clear(); st = ATTR; i = ws(i); continue; }
             if (i < n) { v.push_back(S[i]); i++; continue; }
@@ -134,7 +136,8 @@ inline std::vector<Token> tokenize(const Bin& S) {
     if (lt == Bin::npos) throw TokError{true};                         // tz(nil, <<>>) :83
     std::vector<Token> out;
     size_t p = 0;
-    Token cur = scan_tag(S, ws(lt + 1), p);                            // outside any try: failures propagate
+    const LastPos last = last_positions(S);
+    Token cur = scan_tag(S, ws(lt + 1), p, last);                      // outside any try: failures propagate
     for (;;) {
         std::string prefix;
         for (;;) {
@@ -143,7 +146,7 @@ inline std::vector<Token> tokenize(const Bin& S) {
             std::string txt = S.substr(p, q - p);
             size_t e = ws(q + 1), nx = 0;
             try {
-                Token t2 = scan_tag(S, e, nx);
+                Token t2 = scan_tag(S, e, nx, last);
                 out.push_back(cur); Token tx; tx.k = Token::TEXT; tx.a = prefix + txt; out.push_back(tx);
                 cur = t2; p = nx; break;
             } catch (const TokError&) {
@@ -216,6 +219,53 @@ inline BuildRes build_ast2(const std::vector<Token>& tk, size_t i, List acc, std
         }
         }
     }
+}
+
+// The same builder without recursion (documents with tens of thousands of unclosed tags made the recursive form
+// quadratic). What build_ast2/4 computes is a stack discipline over the token stream, in document order:
+//   * a close tag that matches the innermost open tag closes it (:222-224);
+//   * one that matches a tag further out closes THAT tag and turns every open tag in between into a plain
+//     {open,_,_} element followed by what would have been its children (:225-234 with :210-220);
+//   * one that matches nothing is a {close,_} element (:230-231, :235-237);
+//   * at the end of input every tag still open becomes a plain {open,_,_} element (:204-209, :262-264).
+// N counts elements, NT paired tags. build_ast2() above is kept as the executable statement of the reference's
+// clauses; eo_sgml_selfcheck() (driver.cpp) compares the two.
+struct BuildOut { List list; long n = 0, nt = 0; };
+inline BuildOut build_ast_iter(const std::vector<Token>& tk) {
+    struct Frame { const Token* open; std::string lower; List kids; long n = 0, nt = 0; };
+    std::vector<Frame> st; st.emplace_back(); st.back().open = nullptr;
+    auto flatten_top = [&]() {   // the innermost open tag stays unpaired
+        Frame f = std::move(st.back()); st.pop_back(); Frame& p = st.back();
+        p.kids.push_back(mk(Node::OPEN, f.open->a, "", f.open->params));
+        p.kids.insert(p.kids.end(), f.kids.begin(), f.kids.end());
+        p.n += f.n + 1; p.nt += f.nt;
+    };
+    for (const Token& t : tk) {
+        switch (t.k) {
+        case Token::OPEN: { Frame f; f.open = &t; f.lower = to_lower_latin1(t.a); st.push_back(std::move(f)); break; }
+        case Token::CLOSE: {
+            size_t j = st.size();
+            for (size_t q = st.size(); q-- > 1;) if (st[q].lower == t.lower) { j = q; break; }
+            if (j == st.size()) { st.back().kids.push_back(mk(Node::CLOSE, t.a)); st.back().n++; break; }
+            while (st.size() - 1 > j) flatten_top();
+            Frame f = std::move(st.back()); st.pop_back(); Frame& p = st.back();
+            p.kids.push_back(mk(Node::TAG, f.open->a, t.a, f.open->params, f.kids));
+            p.n += f.n + 1; p.nt += f.nt + 1;
+            break;
+        }
+        case Token::TEXT: if (!t.a.empty()) { st.back().kids.push_back(mk(Node::TEXT, t.a)); st.back().n++; } break;
+        case Token::BANG: st.back().kids.push_back(mk(Node::BANG, t.a)); st.back().n++; break;
+        case Token::COMMENT: st.back().kids.push_back(mk(Node::COMMENT, t.a)); st.back().n++; break;
+        case Token::QUE: st.back().kids.push_back(mk(Node::QUE, t.a)); st.back().n++; break;
+        case Token::SC: st.back().kids.push_back(mk(Node::SC, t.a, "", t.params)); st.back().n++; break;
+        case Token::EOFTEXT:
+            while (st.size() > 1) flatten_top();
+            if (!t.a.empty()) { st.back().kids.push_back(mk(Node::TEXT, t.a)); st.back().n++; }
+            break;
+        }
+    }
+    while (st.size() > 1) flatten_top();
+    BuildOut o; o.list = std::move(st.back().kids); o.n = st.back().n; o.nt = st.back().nt; return o;
 }
 
 // ---------------------------------------------------------------- folder :290-331
@@ -323,8 +373,7 @@ inline MutRes Mutations::sgml_mutate(const Blocks& ll) {
     std::vector<Token> tokens;
     try { tokens = tokenize(h); }
     catch (const TokError& e) { if (e.is_throw) return r; throw CaseDied("sgml tokenizer: function_clause"); }
-    BuildRes br = build_ast2(tokens, 0, List(), {}, 0, 0);
-    if (br.k != BuildRes::OK) throw CaseDied("sgml parse: try_clause");
+    BuildOut br = build_ast_iter(tokens);
     const List& ast = br.list; const long N = br.n, NT = br.nt;
     List res = ast; double d = 1;
     uint64_t which = rng.rand(12);                                                   // :698

@@ -47,8 +47,37 @@ struct TreeParser {
         }
         return false;
     }
-    // partial_parse/1
+    // partial_parse/1 :887-905 over grow/3. Written out without recursion: grow fails only by running out of data, and
+    // then every enclosing grow fails too, so the opens that stay literal bytes are exactly the ones still on the
+    // bracket stack at the end of the block; everything else closes. (The recursive form above splices the partial
+    // lists level by level, which is quadratic on blocks with thousands of unclosed brackets.)
     std::vector<Term> parse() {
+        std::vector<uint8_t> literal(n, 0);
+        { std::vector<size_t> st;
+          for (size_t pos = 0; pos < n; pos++) {
+              uint8_t h = d[pos];
+              if (!st.empty() && h == (uint8_t)usual_delims(d[st.back()])) { st.pop_back(); continue; }
+              if (usual_delims(h) >= 0) st.push_back(pos);
+          }
+          for (size_t p : st) literal[p] = 1; }
+        struct Frame { Term node; uint8_t close; };
+        std::vector<Frame> st; std::vector<Term> out;
+        for (size_t pos = 0; pos < n; pos++) {
+            uint8_t h = d[pos];
+            if (!st.empty() && h == st.back().close) {
+                st.back().node.k.push_back(tbyte(h));
+                Term done = std::move(st.back().node); st.pop_back();
+                (st.empty() ? out : st.back().node.k).push_back(std::move(done));
+                continue;
+            }
+            int nc = usual_delims(h);
+            if (nc >= 0 && !literal[pos]) { Frame f; f.node.is_list = true; f.node.k.push_back(tbyte(h)); f.close = (uint8_t)nc; st.push_back(std::move(f)); continue; }
+            (st.empty() ? out : st.back().node.k).push_back(tbyte(h));
+        }
+        return out;
+    }
+    // the clause-by-clause form, kept for the self check (eo_tree_selfcheck)
+    std::vector<Term> parse_ref() {
         std::vector<Term> out; size_t pos = 0;
         while (pos < n) {
             uint8_t h = d[pos]; int nc = usual_delims(h);

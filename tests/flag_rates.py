@@ -20,7 +20,7 @@ sets = {
     "web (urls/base64/json/markup)": corpus.web_corpus(5, 2000),
 }
 for name, blobs in sets.items():
-    outs, meta = eng.fuzz_batch(blobs, {"mutations": muts, "patterns": pats, "seed": (1, 2, 3), "max_case_out": 1 << 20}, n_cases=len(blobs))
+    outs, meta = eng.fuzz_batch(blobs, {"mutations": muts, "patterns": pats, "seed": (1, 2, 3), "max_case_out": 1 << 20, "scratch_bytes": 6 << 30}, n_cases=len(blobs))
     c = collections.Counter(m.status for m in meta)
     print("%-32s ok %5.1f%%  flagged-unsupported %5.1f%%  died %4.1f%%  over-cap %4.1f%%" % (
         name, 100.0 * c[0] / len(blobs), 100.0 * c[1] / len(blobs), 100.0 * c[2] / len(blobs), 100.0 * c[3] / len(blobs)), flush=True)

@@ -311,3 +311,33 @@ def test_json_structure_and_value_mutations():
     assert all(rc in (0, 2) for (_, _, rc) in outs)                         # swap/insert may hit the badmatch of :576-577
     pumped = {o for (o, d, rc) in _outs("js", b"[1,2,3]", 400) if rc == 0 and d == -2.0 and o.startswith(b"[")}
     assert b"[1,2,[1,2,[1,2,[1,2,3]]]]" in pumped                           # json_pump, PumpCnt = 2 (:560): the 2nd round re-inserts the pumped tree
+
+
+def test_linear_time_builders_match_the_clause_by_clause_forms():
+    """the sgml stack-discipline AST builder and the two-pass bracket parser are re-derivations (needed for blocks with
+    thousands of unclosed tags / brackets); they must agree with the literal restatements of the reference's clauses"""
+    L = O.lib()
+    L.eo_sgml_selfcheck.argtypes = [C.c_char_p, C.c_uint64]
+    L.eo_tree_selfcheck.argtypes = [C.c_char_p, C.c_uint64]
+    r = random.Random(5)
+    tags = [b"a", b"B", b"p", b"div"]
+    for _ in range(6000):
+        out = b""
+        for _ in range(r.randint(1, 40)):
+            k = r.randint(0, 9)
+            t = r.choice(tags)
+            if k < 3:
+                out += b"<" + t + (b" x='1'" if r.random() < 0.3 else b"") + b">"
+            elif k < 6:
+                out += b"</" + t + b">"
+            elif k == 6:
+                out += b"<" + t + b"/>"
+            elif k == 7:
+                out += b"<!-- c -->" if r.random() < 0.5 else b"<?q?>"
+            else:
+                out += r.choice([b"text", b" ", b"x<y", b"1 < 2 > 3", b"<"])
+        assert L.eo_sgml_selfcheck(out, len(out)) == 0, out
+    al = b"()[]<>{}\"'ab \n"
+    for _ in range(8000):
+        d = bytes(r.choice(al) for _ in range(r.randint(0, 40)))
+        assert L.eo_tree_selfcheck(d, len(d)) == 0, d
