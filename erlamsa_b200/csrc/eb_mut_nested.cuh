@@ -1,7 +1,7 @@
 // erlamsa_b200 -- mutators that walk the string lexer's chunks and/or run a NESTED scheduler round:
 //   uri  (reference src/erlamsa_mutations.erl:734-784)  SSRF / path-traversal rewrite of every text chunk holding "://"
 //   b64  (reference :657-690)                            base64-decodable text chunks get one full scheduler round
-//   sgm  (reference src/erlamsa_sgml.erl:739-757)        refusal paths exact; a document that tokenizes flags the case
+//   sgm  (reference src/erlamsa_sgml.erl)                eb_mut_sgml.cuh (all twelve mutations; inner text only at top level)
 //   js   (reference src/erlamsa_json.erl:722-731)        tokenizer exact; a lone scalar token is mutated on the device,
 //                                                        a document with containers flags the case
 // A flagged case (CASE_UNSUPPORTED) is reported to the caller and its output is the unchanged input: nothing is
@@ -21,11 +21,12 @@ EB_DEV void mut_apply_inner(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t 
 
 // ------------------------------------------------------------------ small helpers
 // cooperative output builder over a preallocated buffer (literals by lane 0, ranges by the warp)
-struct Bld { uint8_t* p; uint32_t n; uint32_t cap; };
+struct Bld { uint8_t* p; uint32_t n; uint32_t cap; uint32_t ovf; };   // ovf: the running length left 31 bits (sizing passes)
 EB_DEV void bld_put(Bld& b, uint32_t ch) { if (b.n < b.cap && lane_id() == 0) b.p[b.n] = (uint8_t)ch; b.n++; }
 EB_DEV void bld_puts(Bld& b, const char* s) { while (*s) { bld_put(b, (uint8_t)*s); s++; } }
 EB_DEV void bld_copy(Bld& b, const uint8_t* src, uint32_t len) {
-    for (uint32_t i = lane_id(); i < len; i += 32) if (b.n + i < b.cap) b.p[b.n + i] = src[i];
+    if (b.n < b.cap) for (uint32_t i = lane_id(); i < len; i += 32) if (b.n + i < b.cap) b.p[b.n + i] = src[i];
+    if ((uint64_t)b.n + len > 0x7fffffffull) { b.ovf = 1; return; }
     b.n += len;
 }
 EB_DEV void bld_int(Bld& b, int v) {
@@ -227,7 +228,7 @@ EB_DEV void mut_uri(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutRe
         uint32_t cap = len + 256;
         uint8_t* buf = scratch_alloc(c, cap);
         if (!buf) { r.delta = 0; return; }
-        Bld b; b.p = buf; b.n = 0; b.cap = cap;
+        Bld b; b.p = buf; b.n = 0; b.cap = cap; b.ovf = 0;
         bool file = accn >= 4 && acc[accn - 4] == 'f' && acc[accn - 3] == 'i' && acc[accn - 2] == 'l' && acc[accn - 1] == 'e';   // change_scheme/1 :734-736
         // string:tokens(T, "/"): the domain is the first non-empty piece, the query the rest joined by single slashes
         uint32_t d0 = 0; while (d0 < tn && T[d0] == '/') d0++;
@@ -375,67 +376,9 @@ EB_DEV void mut_b64(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     r.kind = RES_SEGS;
 }
 
-// ------------------------------------------------------------------ sgm: refusal paths of sgml_mutate/2
-// tz/2 (reference src/erlamsa_sgml.erl:82-148) from state {tag,""} until the tag is complete.
-// 0: a token came out, 1: throw(incorrect_sgml), 2: function_clause (unterminated comment, :99-100)
-EB_DEV int sgml_scan_tag(const uint8_t* S, uint32_t n, uint32_t i) {
-    enum { TAGN, BANG, COMMENT, QUE, ETAG, ENDTAG, ENDTAG_GT, ATTR, EATT, VAL, SQVAL, DQVAL, UQVAL };
-    int st = TAGN; bool tag_empty = true, a_empty = true;
-    auto isws = [](uint32_t ch) { return ch == ' ' || ch == '\r' || ch == '\n' || ch == '\t'; };
-    auto isev = [&](uint32_t ch) { return isws(ch) || ch == '>' || ch == '='; };
-    auto ws = [&](uint32_t q) { while (q < n && isws(S[q])) q++; return q; };
-    auto st2 = [&](uint32_t q, uint32_t c0, uint32_t c1) { return q + 2 <= n && S[q] == c0 && S[q + 1] == c1; };
-    for (;;) {
-        switch (st) {
-        case TAGN:
-            if (tag_empty && i < n) {
-                if (i + 3 <= n && S[i] == '!' && S[i + 1] == '-' && S[i + 2] == '-') { st = COMMENT; i += 3; continue; }
-                if (S[i] == '!') { st = BANG; i = ws(i + 1); continue; }
-                if (S[i] == '?') { st = QUE; i = ws(i + 1); continue; }
-                if (S[i] == '/') { st = ENDTAG; i = ws(i + 1); continue; }
-            }
-            if (st2(i, '/', '>')) return 0;
-            if (i < n && isev(S[i])) { st = ATTR; a_empty = true; i = ws(i); continue; }
-            if (i < n) { tag_empty = false; i++; continue; }
-            return 1;
-        case BANG: if (i < n && S[i] == '>') return 0; if (i < n) { i++; continue; } return 1;
-        case COMMENT: { uint32_t q = i; for (;;) { q = find_byte(S, q, n, '-'); if (q >= n) return 2; if (q + 3 <= n && S[q + 1] == '-' && S[q + 2] == '>') return 0; q++; } }
-        case QUE: { uint32_t q = i; for (;;) { q = find_byte(S, q, n, '?'); if (q >= n) return 1; if (q + 2 <= n && S[q + 1] == '>') return 0; q++; } }
-        case ETAG: if (st2(i, '/', '>')) return 0; if (i < n && S[i] == '>') return 0; return 1;
-        case ENDTAG: if (i < n && isev(S[i])) { st = ENDTAG_GT; i = ws(i); continue; } if (i < n) { i++; continue; } return 1;
-        case ENDTAG_GT: return (i < n && S[i] == '>') ? 0 : 1;
-        case ATTR:
-            if (a_empty && ((i < n && isev(S[i])) || st2(i, '/', '>'))) { st = ETAG; continue; }
-            if ((i < n && isev(S[i])) || st2(i, '/', '>')) { st = EATT; i = ws(i); continue; }
-            if (i < n) { a_empty = false; i++; continue; }
-            return 1;
-        case EATT:
-            if (i < n && S[i] == '=') { st = VAL; i = ws(i + 1); continue; }
-            a_empty = true; st = ATTR; i = ws(i); continue;
-        case VAL:
-            if (i < n && S[i] == '\'') { st = SQVAL; i++; continue; }
-            if (i < n && S[i] == '"') { st = DQVAL; i++; continue; }
-            st = UQVAL; continue;
-        case SQVAL: { uint32_t q = find_byte(S, i, n, '\''); if (q >= n) return 1; a_empty = true; st = ATTR; i = ws(q + 1); continue; }
-        case DQVAL: { uint32_t q = find_byte(S, i, n, '"'); if (q >= n) return 1; a_empty = true; st = ATTR; i = ws(q + 1); continue; }
-        default:   // UQVAL
-            if ((i < n && isev(S[i])) || st2(i, '/', '>')) { a_empty = true; st = ATTR; i = ws(i); continue; }
-            if (i < n) { i++; continue; }
-            return 1;
-        }
-    }
-}
-EB_DEV void mut_sgm(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
-    r.rechunk = 0; r.consumed_next = 0; r.kind = RES_SAME; r.delta = -1;
-    if (mem_binarish(p, n)) return;                                      // parse/2 :185-186
-    uint32_t lt = find_byte(p, 0, n, '<');
-    if (lt >= n) return;                                                 // tz(nil, <<>>) :83
-    uint32_t e = lt + 1; while (e < n && (p[e] == ' ' || p[e] == '\r' || p[e] == '\n' || p[e] == '\t')) e++;
-    int k = sgml_scan_tag(p, n, e);
-    if (k == 1) return;                                                  // throw(incorrect_sgml) -> {_, Ll, Meta, -1} :754-756
-    if (k == 2) { c.ws->status = CASE_DIED; return; }                    // an error, not the throw sgml_mutate/2 catches
-    r.kind = RES_UNSUPPORTED;                                            // a document: AST mutations are not on the device yet
-}
+}  // namespace eb
+#include "eb_mut_sgml.cuh"
+namespace eb {
 
 // ------------------------------------------------------------------ js
 // tokenize/1 (reference src/erlamsa_json.erl:82-204) with the context list as a stack of one-byte kinds.
@@ -574,7 +517,7 @@ EB_DEV void mut_js(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
             const char* f = c_js_payload[g.rand_elem_idx(6)];
             uint8_t* buf = scratch_alloc(c, 1024);
             if (!buf) { r.delta = 0; return; }
-            Bld b; b.p = buf; b.n = 0; b.cap = 1024;
+            Bld b; b.p = buf; b.n = 0; b.cap = 1024; b.ovf = 0;
             for (int q = 0; f[q]; q++) {
                 if (f[q] == '~' && f[q + 1] == 's') { bld_puts(b, "://"); bld_hostport(b, c.bp); bld_put(b, '/'); q++; }
                 else bld_put(b, (uint8_t)f[q]);

@@ -353,7 +353,6 @@ __device__ __forceinline__ bool mut_apply_base(CaseCtx& c, MutRow& row, const ui
     case M_FT: case M_FN: case M_FO: mut_fuse(c, id, p, n, r); return true;
     case M_LEN: mut_len(c, p, n, r); return true;
     case M_URI: mut_uri(c, row, p, n, r); return true;
-    case M_SGM: mut_sgm(c, p, n, r); return true;
     case M_ZIP: {   // zip_path_traversal :1149-1163 on data that is not a ZIP archive: zip:foldl fails, delta -1, no draws
         bool z = false; { uint32_t hit = 0; for (uint32_t i = lane_id(); i + 4 <= n; i += 32) hit |= (p[i] == 'P' && p[i + 1] == 'K' && p[i + 2] == 5 && p[i + 3] == 6) ? 1u : 0u; z = __any_sync(0xffffffffu, hit != 0); }
         r.kind = z ? RES_UNSUPPORTED : RES_SAME; r.delta = -1; r.rechunk = 0; r.consumed_next = 0; return true;
@@ -369,6 +368,7 @@ EB_DEV void mut_apply(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, Mut
     if (mut_apply_base(c, row, p, n, r)) return;
     if (row.fn == M_B64) { mut_b64<true>(c, p, n, r); return; }
     if (row.fn == M_JS) { mut_js<true>(c, p, n, r); return; }
+    if (row.fn == M_SGM) { mut_sgm<true>(c, p, n, r); return; }
     r.kind = RES_UNSUPPORTED; r.delta = 0; r.rechunk = 0; r.consumed_next = 0;
 }
 // dispatch inside a nested round (eb_mut_nested.cuh): one level of nesting is executed on the device; a nested
@@ -377,6 +377,7 @@ EB_DEV void mut_apply_inner(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t 
     if (mut_apply_base(c, row, p, n, r)) return;
     if (row.fn == M_JS) { mut_js<false>(c, p, n, r); return; }
     if (row.fn == M_B64) { mut_b64<false>(c, p, n, r); return; }
+    if (row.fn == M_SGM) { mut_sgm<false>(c, p, n, r); return; }
     r.kind = RES_UNSUPPORTED; r.delta = 0; r.rechunk = 0; r.consumed_next = 0;
 }
 
