@@ -31,6 +31,8 @@ WORKLOADS = {
            "C3: 100000 x 65536 B uniform-random seeds; bd,bei,bed,bf,bi,ber,br,num; pattern od"),
     "c3num": (100000, 65536, "num", ["bd", "bei", "bed", "bf", "bi", "ber", "br", "num"], {"od": 1},
               "C3(ii): 100000 x 65536 B numeric text; bd,bei,bed,bf,bi,ber,br,num; pattern od"),
+    "c4": (12500, 262144, "markup", ["ab", "ad", "tr2", "td", "ts1", "ts2", "tr", "sgm", "js"], {"od": 1},
+           "C4 (one GPU's quarter): 12500 x 262144 B documents, half SGML half JSON, tiled from 64 distinct ones; ab,ad,tr2,td,ts1,ts2,tr,sgm,js; pattern od"),
     "c2": (10000, 4096, "bin", None, {"od": 1, "nd": 2, "bu": 1, "sk": 2, "sz": 2, "cs": 1, "ar": 1, "cp": 1, "co": 0, "nu": 0},
            "C2: 10000 x 4096 B uniform-random seeds; all 41 mutators at the reference's default priorities; default patterns"),
 }
@@ -111,9 +113,11 @@ def make_corpus_device(torch, kind, n, size, dev, seed):
         import corpus
         import numpy as np
         r = corpus.rng(seed)
-        base = np.frombuffer(b"".join(corpus.numeric_text(r, size) for _ in range(256)), dtype=np.uint8)
+        distinct = 64 if kind == "markup" else 256
+        docs = corpus.uniform_corpus(seed, distinct, size, "markup") if kind == "markup" else [corpus.numeric_text(r, size) for _ in range(distinct)]
+        base = np.frombuffer(b"".join(docs), dtype=np.uint8)
         t = torch.from_numpy(base.copy()).to(dev)
-        reps = (n + 255) // 256
+        reps = (n + distinct - 1) // distinct
         data = torch.cat([t.repeat(reps)[: n * size], torch.zeros(64, dtype=torch.uint8, device=dev)])
     off = torch.arange(0, (n + 1) * size, size, dtype=torch.int64, device=dev)
     return data, off
@@ -147,9 +151,13 @@ def run_ours(args):
     d_out_off = torch.empty(n_cases + 1, dtype=torch.int64, device=dev)
     d_out_len = torch.empty(n_cases, dtype=torch.int64, device=dev)
     base_opts = {"mutations": muts, "patterns": pats, "seed": (1, 2, 3), "rng": args.rng, "scratch_bytes": 512 << 20}
-    if args.workload == "c2":   # repeat mutators compounded by nd/bu rounds: cap a case at 1 MiB (flagged, not dropped) and give the literals room
-        base_opts.update({"scratch_bytes": 8 << 30, "max_case_out": 1 << 20})
+    if args.workload == "c2":   # repeat mutators compounded by nd/bu rounds: cap a case at 128 KiB = 32 x its seed (flagged, not dropped)
+        base_opts.update({"scratch_bytes": 8 << 30, "max_case_out": 128 << 10})
         out_cap += 4 << 30
+        d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
+    if args.workload == "c4":   # re-serialised documents and their literals live in scratch; pump / repeat may double a document
+        base_opts.update({"scratch_bytes": 16 << 30, "max_case_out": 4 << 20})
+        out_cap += 8 << 30
         d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 

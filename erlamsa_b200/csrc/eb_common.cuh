@@ -99,6 +99,7 @@ struct Arenas {
     // per-warp reusable temporaries (parse tables, stacks, sort keys): warp slot w owns
     // temp + w * temp_per_warp; reset for every mutator attempt, never referenced by a result
     uint8_t* temp; uint64_t temp_per_warp;
+    unsigned long long* flagged;   // [3]: cases that ended unsupported / died / over a cap
 };
 
 struct __align__(8) MetaDev {

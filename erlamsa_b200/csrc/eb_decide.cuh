@@ -495,6 +495,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
             if (sb + ns > ar.segs_cap) { if (lane_id() == 0) atomicOr(ar.overflow, 2u); ns = 0; ws->olen = 0; ws->status = CASE_OVERFLOW; ws->reason = 7; }
             for (int i = lane_id(); i < ns; i += 32) ar.segs[sb + i] = ws->oseg[i];
         }
+        if (lane_id() == 0 && ws->status != CASE_OK && ar.flagged) atomicAdd(&ar.flagged[ws->status - 1], 1ull);
         if (lane_id() == 0) {
             if (!a.fused) {
                 CaseOut co; co.seg_begin = sb; co.nseg = (uint32_t)ns; co.status = ws->status; co.out_len = ws->olen; co.pad = 0;

@@ -51,6 +51,7 @@ struct eb200_ctx {
     std::string last_err;
     DevBuf cases, out_len, sz16, tile_sum, tile_case, slot_off, counters, segs, scratch, temp, data, off, out, out_off, meta;
     int fused = 1;          // single-pass mode (EB200_MODE=twopass selects decide -> scan -> apply)
+    unsigned long long flag_counts[3] = {0, 0, 0};   // unsupported / died / overflow of the last batch (device counters)
     cudaEvent_t ev[6];
     bool funny_loaded = false;
     int apply_variant = 0;
@@ -235,6 +236,7 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
         ar.segs = (Seg*)ctx->segs.p; ar.segs_cap = ctx->segs.cap / sizeof(Seg);
         ar.segs_used = (unsigned long long*)ctx->counters.p + 1;
         ar.overflow = (uint32_t*)((unsigned long long*)ctx->counters.p + 2);
+        ar.flagged = (unsigned long long*)ctx->counters.p + 4;
         const DecideVariant& dv = decide_variants[ctx->decide_variant];
         uint64_t want_ctas = (n + dv.warps - 1) / dv.warps;
         int grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * dv.ctas_per_sm);
@@ -248,7 +250,7 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
             uint64_t per = std::min<uint64_t>(std::max<uint64_t>(64 * mean, 256u << 10), 16u << 20);
             per = (per + 255) & ~255ull;
             uint64_t nw = (uint64_t)grid * dv.warps;
-            while (per > (256u << 10) && per * nw > (24ull << 30)) per >>= 1;
+            while (per > (256u << 10) && per * nw > (48ull << 30)) per >>= 1;
             CK(ctx->temp.ensure(per * nw + 256));
             ar.temp = (uint8_t*)ctx->temp.p; ar.temp_per_warp = per;
         }
@@ -260,6 +262,7 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
         (*launches)++;
         uint32_t ovf = 0;
         CK(cudaMemcpyAsync(&ovf, ar.overflow, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->flag_counts, ar.flagged, 24, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (!ovf) break;
         if (attempt >= 3) return EB200_ERR_SCRATCH;
@@ -319,6 +322,7 @@ static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* op
         ar.scratch_used = (unsigned long long*)ctx->counters.p;
         ar.segs = (Seg*)ctx->segs.p; ar.segs_cap = 0; ar.segs_used = (unsigned long long*)ctx->counters.p + 1;
         ar.overflow = (uint32_t*)((unsigned long long*)ctx->counters.p + 2);
+        ar.flagged = (unsigned long long*)ctx->counters.p + 4;
         const DecideVariant& dv = decide_variants[ctx->decide_variant];
         uint64_t want_ctas = (n + dv.warps - 1) / dv.warps;
         int grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * dv.ctas_per_sm);
@@ -332,7 +336,7 @@ static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* op
             uint64_t per = std::min<uint64_t>(std::max<uint64_t>(64 * mean, 256u << 10), 16u << 20);
             per = (per + 255) & ~255ull;
             uint64_t nw = (uint64_t)grid * dv.warps;
-            while (per > (256u << 10) && per * nw > (24ull << 30)) per >>= 1;
+            while (per > (256u << 10) && per * nw > (48ull << 30)) per >>= 1;
             CK(ctx->temp.ensure(per * nw + 256));
             ar.temp = (uint8_t*)ctx->temp.p; ar.temp_per_warp = per;
         }
@@ -344,6 +348,7 @@ static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* op
         CK(cudaEventRecord(ctx->ev[3], st));
         (*launches)++;
         CK(cudaMemcpyAsync(used, (unsigned long long*)ctx->counters.p + 2, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->flag_counts, (unsigned long long*)ctx->counters.p + 4, 24, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         uint32_t ovf = (uint32_t)used[0];
         if (!(ovf & 1) && !((ovf & 4) && own_out && !out_base)) break;
@@ -375,6 +380,7 @@ static int run_apply(eb200_ctx* ctx, uint64_t n, const uint64_t* d_out_off, uint
 
 static void fill_stats(eb200_ctx* ctx, eb200_stats* s) {
     if (!s) return;
+    s->n_unsupported = ctx->flag_counts[0]; s->n_died = ctx->flag_counts[1]; s->n_overflow = ctx->flag_counts[2];
     if (ctx->fused) {   // single pass: the "decide" kernel also moved the bytes; there is no apply kernel
         cudaEventElapsedTime(&s->ms_decide, ctx->ev[0], ctx->ev[3]);
         cudaEventElapsedTime(&s->ms_scan, ctx->ev[1], ctx->ev[2]);

@@ -382,12 +382,20 @@ namespace eb {
 
 // ------------------------------------------------------------------ js
 // tokenize/1 (reference src/erlamsa_json.erl:82-204) with the context list as a stack of one-byte kinds.
-struct JsScan { int status; int ntop; int kind; uint32_t a, b; };      // status 0 ok, 1 throw(incorrect_json), 2 too deep for the device stack
+struct JsScan { int status; int ntop; int kind; uint32_t a, b; uint32_t natoms; int irregular; };   // status 0 ok, 1 throw(incorrect_json), 2 device table full
+// the document as a flat sequence of atoms in source order: what fold_ast/1 re-serialises, white space gone
+enum { JA_NUM = 0, JA_STR, JA_TRUE, JA_FALSE, JA_NULL, JA_JUNK, JA_OARR, JA_CARR, JA_OOBJ, JA_COBJ, JA_COMMA, JA_COLON };
+struct JAtom { uint32_t kind, a, b, match; };
 enum { JV_NUMBER = 0, JV_STRING, JV_TRUE, JV_FALSE, JV_NULL, JV_JUNK, JV_CONTAINER };
 enum { JC_ARRAY = 0, JC_ELEMENTS, JC_OBJECT, JC_MEMBERS, JC_PAIR, JC_PAIR_DELIM, JC_VALUE, JC_ARRAY_END, JC_OBJECT_END, JC_PAIR_START, JC_PAIR_END };
-EB_DEV JsScan js_tokenize(const uint8_t* S, uint32_t n, uint8_t* stk, uint32_t cap) {
-    JsScan o; o.status = 0; o.ntop = 0; o.kind = 0; o.a = o.b = 0;
+EB_DEV JsScan js_tokenize(const uint8_t* S, uint32_t n, uint8_t* stk, uint32_t cap, JAtom* atoms, uint32_t acap) {
+    JsScan o; o.status = 0; o.ntop = 0; o.kind = 0; o.a = o.b = 0; o.natoms = 0; o.irregular = 0;
     uint32_t sp = 0, i = 0;
+    auto ATOM = [&](uint32_t kind, uint32_t a, uint32_t b) {
+        if (!atoms) return;
+        if (o.natoms < acap) { JAtom t; t.kind = kind; t.a = a; t.b = b; t.match = 0; atoms[o.natoms] = t; } else o.status = 2;
+        o.natoms++;
+    };
     auto PUSH = [&](uint32_t k) { if (sp < cap) stk[sp] = (uint8_t)k; else o.status = 2; sp++; };   // every lane stores the same byte
     auto TOP = [&](uint32_t back) -> uint32_t { uint32_t v = stk[sp - 1 - back]; return v; };
     auto notsep = [](uint32_t ch) { return ch != ' ' && ch != '\n' && ch != '\r' && ch != '\t' && ch != ',' && ch != ']' && ch != '}' && ch != ':'; };
@@ -415,45 +423,48 @@ EB_DEV JsScan js_tokenize(const uint8_t* S, uint32_t n, uint8_t* stk, uint32_t c
         switch (topk) {
         case JC_ARRAY:
             sp--; PUSH(JC_ARRAY_END);
-            if (S[i] == ']') { i++; sp--; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
+            if (S[i] == ']') { ATOM(JA_CARR, i, i + 1); i++; sp--; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
             PUSH(JC_ELEMENTS); PUSH(JC_VALUE); continue;
         case JC_ELEMENTS:
-            if (S[i] == ']' && sp >= 2 && TOP(1) == JC_ARRAY_END) { i++; sp -= 2; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
-            if (S[i] == ',') { i++; PUSH(JC_VALUE); continue; }
+            if (S[i] == ']' && sp >= 2 && TOP(1) == JC_ARRAY_END) { ATOM(JA_CARR, i, i + 1); i++; sp -= 2; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
+            if (S[i] == ',') { ATOM(JA_COMMA, i, i + 1); i++; PUSH(JC_VALUE); continue; }
             o.status = 1; return o;
         case JC_OBJECT:
             sp--; PUSH(JC_OBJECT_END);
-            if (S[i] == '}') { i++; sp--; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
+            if (S[i] == '}') { ATOM(JA_COBJ, i, i + 1); i++; sp--; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
             PUSH(JC_MEMBERS); PUSH(JC_PAIR); continue;
         case JC_MEMBERS:
-            if (S[i] == '}' && sp >= 2 && TOP(1) == JC_OBJECT_END) { i++; sp -= 2; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
-            if (S[i] == ',') { i++; PUSH(JC_PAIR); continue; }
+            if (S[i] == '}' && sp >= 2 && TOP(1) == JC_OBJECT_END) { ATOM(JA_COBJ, i, i + 1); i++; sp -= 2; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
+            if (S[i] == ',') { ATOM(JA_COMMA, i, i + 1); i++; PUSH(JC_PAIR); continue; }
             o.status = 1; return o;
         case JC_PAIR:
             sp--;
-            if (S[i] == ':' && sp >= 1 && TOP(0) == JC_PAIR_DELIM) { i++; sp--; PUSH(JC_PAIR_END); PUSH(JC_VALUE); continue; }
+            if (S[i] == ':' && sp >= 1 && TOP(0) == JC_PAIR_DELIM) { o.irregular = 1; i++; sp--; PUSH(JC_PAIR_END); PUSH(JC_VALUE); continue; }
             PUSH(JC_PAIR_DELIM); PUSH(JC_VALUE); continue;
         case JC_PAIR_DELIM:
-            if (S[i] == ':') { i++; sp--; PUSH(JC_PAIR_END); PUSH(JC_VALUE); continue; }
+            if (S[i] == ':') { ATOM(JA_COLON, i, i + 1); i++; sp--; PUSH(JC_PAIR_END); PUSH(JC_VALUE); continue; }
+            o.irregular = 1;                                             // a key followed by another value: pairs as keys, not laid out on the device
             PUSH(JC_PAIR_DELIM); PUSH(JC_VALUE); continue;
         case JC_VALUE: sp--; want_value = true; break;
         default: o.status = 2; return o;                                 // case_clause in ws/3: cannot be reached from the states above
         }
         if (!want_value) continue;
         uint32_t ch = S[i];
-        if (ch == '[') { i++; PUSH(JC_ARRAY); continue; }
-        if (ch == '{') { i++; PUSH(JC_OBJECT); continue; }
-        if (i + 4 <= n && S[i] == 't' && S[i + 1] == 'r' && S[i + 2] == 'u' && S[i + 3] == 'e') { if (!push_value(JV_TRUE, i, i + 4)) { o.status = 1; return o; } i += 4; continue; }
-        if (i + 5 <= n && S[i] == 'f' && S[i + 1] == 'a' && S[i + 2] == 'l' && S[i + 3] == 's' && S[i + 4] == 'e') { if (!push_value(JV_FALSE, i, i + 5)) { o.status = 1; return o; } i += 5; continue; }
-        if (i + 4 <= n && S[i] == 'n' && S[i + 1] == 'u' && S[i + 2] == 'l' && S[i + 3] == 'l') { if (!push_value(JV_NULL, i, i + 4)) { o.status = 1; return o; } i += 4; continue; }
+        if (ch == '[') { ATOM(JA_OARR, i, i + 1); i++; PUSH(JC_ARRAY); continue; }
+        if (ch == '{') { ATOM(JA_OOBJ, i, i + 1); i++; PUSH(JC_OBJECT); continue; }
+        if (i + 4 <= n && S[i] == 't' && S[i + 1] == 'r' && S[i + 2] == 'u' && S[i + 3] == 'e') { ATOM(JA_TRUE, i, i + 4); if (!push_value(JV_TRUE, i, i + 4)) { o.status = 1; return o; } i += 4; continue; }
+        if (i + 5 <= n && S[i] == 'f' && S[i + 1] == 'a' && S[i + 2] == 'l' && S[i + 3] == 's' && S[i + 4] == 'e') { ATOM(JA_FALSE, i, i + 5); if (!push_value(JV_FALSE, i, i + 5)) { o.status = 1; return o; } i += 5; continue; }
+        if (i + 4 <= n && S[i] == 'n' && S[i + 1] == 'u' && S[i + 2] == 'l' && S[i + 3] == 'l') { ATOM(JA_NULL, i, i + 4); if (!push_value(JV_NULL, i, i + 4)) { o.status = 1; return o; } i += 4; continue; }
         if (ch == '"') {
             uint32_t q = find_byte(S, i + 1, n, '"');
-            if (q >= n) { if (!push_value(JV_JUNK, i + 1, n)) { o.status = 1; return o; } i = n; continue; }
+            if (q >= n) { ATOM(JA_JUNK, i + 1, n); if (!push_value(JV_JUNK, i + 1, n)) { o.status = 1; return o; } i = n; continue; }
+            ATOM(JA_STR, i + 1, q);
             if (!push_value(JV_STRING, i + 1, q)) { o.status = 1; return o; }
             i = q + 1; continue;
         }
         if (!notsep(ch)) { o.status = 1; return o; }
         uint32_t j = i; while (j < n && notsep(S[j])) j++;
+        ATOM(JA_NUM, i, j);
         if (!push_value(JV_NUMBER, i, j)) { o.status = 1; return o; }
         i = j;
     }
@@ -469,18 +480,29 @@ __device__ const char* const c_js_payload[6] = {
     "{\"@class\":\" com.atomikos.icatch.jta.RemoteClientUserTransaction\", \"name_\":\"ldap~suid=somename,ou=someou,dc=somedc\", \"providerUrl_\":\"ldap~s\"}",
 };
 
-// json_mutate/2 :722-731 for a document that is a single scalar token (N = 1, NT = 0) or nothing at all (N = 0)
+}  // namespace eb
+#include "eb_mut_json.cuh"
+namespace eb {
+
+// json_mutate/2 :722-731; a document that is a single scalar token (N = 1, NT = 0) or nothing at all (N = 0) is handled
+// here, one with arrays / objects in eb_mut_json.cuh
 template <bool TOP_LEVEL>
 EB_DEV void mut_js(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     r.rechunk = 0; r.consumed_next = 0; r.kind = RES_SAME; r.delta = -1;
     uint32_t cap = n < 65536u ? n + 16 : 65536u;
     uint8_t* stk = temp_alloc(c, cap);
-    if (!stk) { r.delta = 0; return; }
-    JsScan js = js_tokenize(p, n, stk, cap);
+    uint32_t acap = n / 2 + 16;                                          // denser than an atom every two bytes ("[[[[...") flags the case
+    JAtom* atoms = (JAtom*)temp_alloc(c, (uint64_t)acap * sizeof(JAtom));
+    if (!stk || !atoms) { r.delta = 0; return; }
+    JsScan js = js_tokenize(p, n, stk, cap, atoms, acap);
     if (js.status == 1) return;                                          // incorrect_json :728-730
     if (js.status == 2) { r.kind = RES_UNSUPPORTED; return; }
-    if (js.ntop == 1 && js.kind == JV_CONTAINER) { r.kind = RES_UNSUPPORTED; return; }
+    if (js.ntop == 1 && js.kind == JV_CONTAINER) {
+        if (js.irregular) { r.kind = RES_UNSUPPORTED; return; }
+        mut_js_document<TOP_LEVEL>(c, p, n, atoms, js.natoms, r);
+        return;
+    }
     // fold of the lone token: its source text (a string with its quotes; a junk string gets both quotes again, :263-264)
     Seg v0 = seg_copy(p, 0), v1 = seg_copy(p, 0);
     if (js.ntop == 1) {

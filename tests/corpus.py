@@ -81,6 +81,8 @@ def mixed_corpus(seed, count, max_len=5000, kinds=("bin", "num", "lines", "tiny"
 
 def uniform_corpus(seed, count, size, kind="bin"):
     r = rng(seed)
+    if kind == "markup":   # C4: SGML / JSON documents, blank-padded to the exact size (both tokenizers skip trailing blanks)
+        return [(sgml_doc(r, size) if i % 2 == 0 else json_doc(r, size)).ljust(size, b" ") for i in range(count)]
     f = {"bin": random_bytes, "num": numeric_text, "lines": text_lines}[kind]
     return [f(r, size) for _ in range(count)]
 
@@ -125,3 +127,81 @@ def web_corpus(seed, count):
         else:
             out.append(structured_text(r, int(r.integers(1, 400))))
     return out
+
+
+def sgml_doc(r, n):
+    """random tag tree (depth <= 8, 0-3 attributes, text leaves 8-64 chars), SURVEY.md 8d config C4"""
+    names = [b"a", b"div", b"p", b"item", b"Node", b"x:y", b"li", b"span"]
+    attrs = [b"id", b"class", b"href", b"xmlns", b"xmlns:xsi", b"data-k", b"checked"]
+    out = bytearray(b"<?xml version=\"1.0\"?>")
+    stack = []
+    letters = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz ABCDEFGH 0123456789.,;-", dtype=np.uint8)
+    while len(out) < n:
+        k = int(r.integers(0, 10))
+        if k < 4 and len(stack) < 8:
+            t = names[int(r.integers(0, len(names)))]
+            out += b"<" + t
+            for _ in range(int(r.integers(0, 4))):
+                a = attrs[int(r.integers(0, len(attrs)))]
+                v = bytes(letters[r.integers(0, 36, size=int(r.integers(0, 12)))])
+                q = int(r.integers(0, 3))
+                out += b" " + a + (b"" if q == 2 and not v else b"=" + [b'"', b"'", b""][q] + (v.replace(b" ", b"_") if q == 2 else v) + [b'"', b"'", b""][q])
+            if r.random() < 0.15:
+                out += b"/>"
+            else:
+                out += b">"
+                stack.append(t)
+        elif k < 7 and stack:
+            out += b"</" + stack.pop() + b">"
+        elif k == 7:
+            out += b"<!-- " + bytes(letters[r.integers(0, len(letters), size=int(r.integers(4, 24)))]) + b" -->"
+        else:
+            out += bytes(letters[r.integers(0, len(letters), size=int(r.integers(8, 65)))])
+    while stack and r.random() < 0.9:
+        out += b"</" + stack.pop() + b">"
+    return bytes(out[:n])
+
+
+def json_doc(r, n):
+    """nested objects / arrays with strings, ints, null / bool until n bytes (C4); always a complete document"""
+    letters = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz_ ABCDEF0123456789", dtype=np.uint8)
+
+    def scalar():
+        k = int(r.integers(0, 6))
+        if k == 0:
+            return str(int(r.integers(-10**9, 10**9))).encode()
+        if k == 1:
+            return [b"true", b"false", b"null"][int(r.integers(0, 3))]
+        if k == 2:
+            return b'"http://h.example/' + bytes(letters[r.integers(0, 26, size=int(r.integers(1, 10)))]) + b'"'
+        return b'"' + bytes(letters[r.integers(0, len(letters), size=int(r.integers(0, 24)))]) + b'"'
+
+    def value(depth, budget):
+        k = int(r.integers(0, 10))
+        if depth >= 6 or budget < 16 or k < 4:
+            return scalar()
+        parts = []
+        used = 2
+        is_obj = k < 7
+        while used < budget and (not parts or r.random() < 0.85):
+            v = value(depth + 1, (budget - used) // 2)
+            item = (b'"' + bytes(letters[r.integers(0, 27, size=int(r.integers(1, 9)))]) + b'":' + (b" " if r.random() < 0.3 else b"") + v) if is_obj else v
+            parts.append(item)
+            used += len(item) + 1
+        sep = b"," if r.random() < 0.7 else b", "
+        return (b"{" + sep.join(parts) + b"}") if is_obj else (b"[" + sep.join(parts) + b"]")
+
+    parts = []
+    used = 2
+    while used < n - 64:
+        v = value(1, min(4096, n - used))
+        parts.append(v)
+        used += len(v) + 1
+    doc = b"[" + b",".join(parts) + b"]"
+    return doc[:n] if len(doc) <= n else (b"[" + b",".join(parts[:-1]) + b"]")
+
+
+def markup_corpus(seed, count, size):
+    """C4: half SGML, half JSON documents of about `size` bytes"""
+    r = rng(seed)
+    return [sgml_doc(r, size) if i % 2 == 0 else json_doc(r, size) for i in range(count)]

@@ -84,9 +84,19 @@ def test_b64_mutator_nested_round(engine, oracle):
 def test_sgm_js_refusals_and_scalar_documents(engine, oracle):
     blobs = corpus.web_corpus(0xE21A0902, 300) + corpus.mixed_corpus(0xE21A0903, 60, 300)
     n = compare(engine, oracle, blobs, {"sgm": 10, "js": 3, "nil": 0}, {"od": 1}, seed=(7, 5, 5), allow_unsupported=True)
-    assert n >= len(blobs) * 0.7
+    assert n >= len(blobs) * 0.93
     n = compare(engine, oracle, blobs, {"js": 1}, {"od": 1}, seed=(8, 5, 5), allow_unsupported=True)
-    assert n >= len(blobs) * 0.8
+    assert n >= len(blobs) * 0.93
+
+
+def test_sgm_js_documents(engine, oracle):
+    """C4-style documents: every sgm mutation and every js mutation on arrays / objects, exact"""
+    blobs = corpus.uniform_corpus(0xE21A0906, 60, 3000, "markup") + corpus.uniform_corpus(0xE21A0907, 20, 20000, "markup")
+    for seed in ((1, 1, 1), (2, 3, 4)):
+        n = compare(engine, oracle, blobs, {"sgm": 10, "js": 3}, {"od": 1}, seed=seed, n_cases=240, allow_unsupported=True)
+        assert n >= 240 * 0.9           # inner-text rounds that open a second nested round (base64-looking text inside a document) are flagged
+    n = compare(engine, oracle, blobs, {"sgm": 1, "js": 1, "ab": 1, "tr2": 1}, {"nd": 1, "bu": 1}, seed=(5, 1, 1), n_cases=160, allow_unsupported=True)
+    assert n >= 160 * 0.85
 
 
 def test_true_default_mutator_mix(engine, oracle):
@@ -95,7 +105,7 @@ def test_true_default_mutator_mix(engine, oracle):
     muts = dict(eo.default_mutations())
     blobs = corpus.mixed_corpus(0xE21A0904, 200, 2000) + corpus.web_corpus(0xE21A0905, 100)
     n = compare(engine, oracle, blobs, muts, {"od": 1, "nd": 2, "bu": 1, "sk": 2, "sz": 2, "cs": 1, "ar": 1, "cp": 1}, seed=(9, 5, 5), allow_unsupported=True)
-    assert n >= len(blobs) * 0.6
+    assert n >= len(blobs) * 0.9
 
 
 def framed_corpus(seed, count):
