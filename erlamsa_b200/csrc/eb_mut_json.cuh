@@ -135,7 +135,7 @@ EB_DEV void js_emit_plan(JEmit& e, const JDoc& d, const JPlan& pl) {
     }
 }
 
-template <bool TOP_LEVEL>
+template <int LVL>
 EB_DEV void mut_js_document(CaseCtx& c, const uint8_t* p, uint32_t n, JAtom* atoms, uint32_t natoms, MutResult& r) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     JDoc d; d.S = p; d.n = n; d.at = atoms; d.nat = natoms; d.el = nullptr; d.nel = 0; d.ov = nullptr;
@@ -186,7 +186,7 @@ EB_DEV void mut_js_document(CaseCtx& c, const uint8_t* p, uint32_t n, JAtom* ato
         break;
     }
     default: {                                                           // inner values :670-718
-        if (!TOP_LEVEL) { r.kind = RES_UNSUPPORTED; return; }
+        if (LVL >= MAX_NEST) { r.kind = RES_UNSUPPORTED; return; }
         const int kind0 = c.snand_kind;
         const int inner_kind = (int)g.rand_elem_idx(3); (void)g.rand_elem_idx(1);
         const uint8_t ids[9] = {M_SGM, M_AB, M_AD, M_NUM, M_SP, M_SR, M_SD, M_B64, M_URI};
@@ -209,7 +209,7 @@ EB_DEV void mut_js_document(CaseCtx& c, const uint8_t* p, uint32_t n, JAtom* ato
                 if (rnd > (el.slot == JS_PKEY ? pk : pn)) continue;
                 c.temp_floor = c.temp_used; c.snand_kind = inner_kind;
                 InnerRes res; res.kind = 0; res.len = a.b - a.a;
-                if constexpr (TOP_LEVEL) res = inner_round(c, rows, nr, p + a.a, a.b - a.a, true);
+                if constexpr (LVL < MAX_NEST) res = inner_round<LVL>(c, rows, nr, p + a.a, a.b - a.a, true);
                 c.snand_kind = kind0; c.temp_floor = floor0;
                 if (ws->status != CASE_OK) break;
                 if (res.kind == 0) continue;

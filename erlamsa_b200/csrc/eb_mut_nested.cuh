@@ -17,7 +17,10 @@ namespace eb {
 __device__ const int8_t c_default_pri[M_COUNT] = {10, 3, 1, 2, 1, 1, 1, 1, 3, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
                                                   1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 2, 2, 7, 1, 1, 0};
 
-EB_DEV void mut_apply_inner(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r);   // eb_mutators.cuh
+// nesting levels: 0 = the case's own scheduler, 1 / 2 = inside one / two nested rounds. A mutator at level MAX_NEST
+// cannot open another round and flags the case instead.
+constexpr int MAX_NEST = 2;
+template <int LVL> EB_DEV void mut_apply_level(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r);   // eb_mutators.cuh
 
 // ------------------------------------------------------------------ small helpers
 // cooperative output builder over a preallocated buffer (literals by lane 0, ranges by the warp)
@@ -119,6 +122,8 @@ EB_DEV int inner_table(CaseCtx& c, const uint8_t* ids, int n_ids, bool b64_style
     return n_ids;
 }
 
+// LVL = level of the mutator that opens the round; the round's own mutators run at LVL + 1
+template <int LVL>
 EB_DEV InnerRes inner_round(CaseCtx& c, const MutRow* rows, int nr, const uint8_t* p, uint32_t n, bool head_only) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     InnerRes out; out.kind = 0; out.len = n;
@@ -153,7 +158,7 @@ EB_DEV InnerRes inner_round(CaseCtx& c, const MutRow* rows, int nr, const uint8_
         MutRow row = rows[order[t]];
         temp_reset(c);
         MutResult r; r.kind = RES_SAME; r.delta = 0; r.rechunk = 0; r.consumed_next = 0;
-        mut_apply_inner(c, row, p, n, r);
+        mut_apply_level<LVL + 1>(c, row, p, n, r);
         if (r.kind == RES_UNSUPPORTED) ws->status = CASE_UNSUPPORTED;
         if (ws->status != CASE_OK) break;
         bool changed = false;
@@ -322,9 +327,9 @@ EB_DEV uint32_t b64_encode_dev(const uint8_t* in, uint32_t m, uint8_t* out) {   
     return 4 * ng;
 }
 
-// TOP_LEVEL false: the attempt happens inside a nested round; it is exact as long as no chunk decodes (the usual
+// At LVL == MAX_NEST the attempt cannot open another round: it is exact as long as no chunk decodes (the usual
 // outcome on decoded bytes) and flags the case when a second level of nesting would be needed.
-template <bool TOP_LEVEL>
+template <int LVL>
 EB_DEV void mut_b64(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     r.rechunk = 0; r.consumed_next = 0; r.kind = RES_SAME; r.delta = -1;
@@ -350,13 +355,13 @@ EB_DEV void mut_b64(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
         if (!vals || !dec) { r.delta = 0; break; }
         int dl = b64_decode_dev(p + cs, len, vals, dec);
         if (dl < 0) continue;                                            // error:badarg -> the chunk stays
-        if (!TOP_LEVEL) { r.kind = RES_UNSUPPORTED; break; }
+        if (LVL >= MAX_NEST) { r.kind = RES_UNSUPPORTED; break; }
         int dd = g.rand_delta();
         (void)inner_table(c, nullptr, 0, true, rows);                    // mutators_mutator(MutasList, []): 41 score draws
         if (np >= MAX_PIECES) { r.kind = RES_UNSUPPORTED; break; }
         c.temp_floor = c.temp_used; c.snand_kind = inner_kind;
         InnerRes res; res.kind = 0; res.len = (uint32_t)dl;
-        if constexpr (TOP_LEVEL) res = inner_round(c, rows, M_COUNT, dec, (uint32_t)dl, false);
+        if constexpr (LVL < MAX_NEST) res = inner_round<LVL>(c, rows, M_COUNT, dec, (uint32_t)dl, false);
         c.snand_kind = kind0;
         if (ws->status != CASE_OK) break;
         uint8_t* nb = temp_alloc(c, res.len);                            // above whatever the winning attempt still references
@@ -486,7 +491,7 @@ namespace eb {
 
 // json_mutate/2 :722-731; a document that is a single scalar token (N = 1, NT = 0) or nothing at all (N = 0) is handled
 // here, one with arrays / objects in eb_mut_json.cuh
-template <bool TOP_LEVEL>
+template <int LVL>
 EB_DEV void mut_js(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     r.rechunk = 0; r.consumed_next = 0; r.kind = RES_SAME; r.delta = -1;
@@ -500,7 +505,7 @@ EB_DEV void mut_js(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     if (js.status == 2) { r.kind = RES_UNSUPPORTED; return; }
     if (js.ntop == 1 && js.kind == JV_CONTAINER) {
         if (js.irregular) { r.kind = RES_UNSUPPORTED; return; }
-        mut_js_document<TOP_LEVEL>(c, p, n, atoms, js.natoms, r);
+        mut_js_document<LVL>(c, p, n, atoms, js.natoms, r);
         return;
     }
     // fold of the lone token: its source text (a string with its quotes; a junk string gets both quotes again, :263-264)
@@ -549,7 +554,7 @@ EB_DEV void mut_js(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
             t_push(ws, seg_copy(buf, b.n)); D = -2; break;
         }
         default: {                                                                                             // inner text :670-718, N = 1
-            if (!TOP_LEVEL) { r.kind = RES_UNSUPPORTED; return; }
+            if (LVL >= MAX_NEST) { r.kind = RES_UNSUPPORTED; return; }
             const int kind0 = c.snand_kind;
             const int inner_kind = (int)g.rand_elem_idx(3); (void)g.rand_elem_idx(1);                          // inner_mutations(json) -> mutations([])
             const uint8_t ids[9] = {M_SGM, M_AB, M_AD, M_NUM, M_SP, M_SR, M_SD, M_B64, M_URI};
@@ -569,7 +574,7 @@ EB_DEV void mut_js(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
             if (js.kind == JV_STRING) {                                  // mutate_innertext_prob/4 :620-627
                 const uint64_t floor0 = c.temp_floor; c.temp_floor = c.temp_used; c.snand_kind = inner_kind;
                 InnerRes res; res.kind = 0; res.len = js.b - js.a;
-                if constexpr (TOP_LEVEL) res = inner_round(c, rows, nr, p + js.a, js.b - js.a, true);
+                if constexpr (LVL < MAX_NEST) res = inner_round<LVL>(c, rows, nr, p + js.a, js.b - js.a, true);
                 c.snand_kind = kind0; c.temp_floor = floor0;
                 if (ws->status != CASE_OK) return;
                 uint8_t* lit = scratch_alloc(c, (uint64_t)res.len + 2);

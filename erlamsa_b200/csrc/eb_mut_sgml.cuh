@@ -316,7 +316,7 @@ EB_DEV void sg_emit_plan(SgEmit& e, const SgDoc& d, const SgPlan& pl) {
     }
 }
 
-template <bool TOP_LEVEL>
+template <int LVL>
 EB_DEV void mut_sgm(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     r.rechunk = 0; r.consumed_next = 0; r.kind = RES_SAME; r.delta = -1;
@@ -422,7 +422,7 @@ EB_DEV void mut_sgm(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
         break;
     }
     default: {                                                           // inner text :721-733
-        if (!TOP_LEVEL) { r.kind = RES_UNSUPPORTED; return; }
+        if (LVL >= MAX_NEST) { r.kind = RES_UNSUPPORTED; return; }
         const int kind0 = c.snand_kind;
         const int inner_kind = (int)g.rand_elem_idx(3); (void)g.rand_elem_idx(1);
         const uint8_t ids[11] = {M_AB, M_AD, M_NUM, M_BD, M_SD, M_LD, M_LRI, M_LR, M_LP, M_B64, M_URI};
@@ -438,7 +438,7 @@ EB_DEV void mut_sgm(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
             if (rnd > 3.0 / (double)nt) return;
             c.temp_floor = c.temp_used; c.snand_kind = inner_kind;
             InnerRes res; res.kind = 0; res.len = tl;
-            if constexpr (TOP_LEVEL) res = inner_round(c, rows, nr, tp, tl, true);
+            if constexpr (LVL < MAX_NEST) res = inner_round<LVL>(c, rows, nr, tp, tl, true);
             c.snand_kind = kind0;
             if (ws->status == CASE_OK && res.kind != 0) {
                 uint8_t* lit = scratch_alloc(c, res.len);

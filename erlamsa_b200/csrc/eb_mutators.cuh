@@ -363,22 +363,16 @@ __device__ __forceinline__ bool mut_apply_base(CaseCtx& c, MutRow& row, const ui
     default: return false;
     }
 }
-// dispatch for a round of the case's own scheduler
-EB_DEV void mut_apply(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) {
+// dispatch at nesting level LVL (0 = the case's own scheduler; eb_mut_nested.cuh runs rounds at 1 and 2). The three
+// mutators that can open a nested round are instantiated per level so that the call graph stays acyclic.
+template <int LVL>
+EB_DEV void mut_apply_level(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) {
     if (mut_apply_base(c, row, p, n, r)) return;
-    if (row.fn == M_B64) { mut_b64<true>(c, p, n, r); return; }
-    if (row.fn == M_JS) { mut_js<true>(c, p, n, r); return; }
-    if (row.fn == M_SGM) { mut_sgm<true>(c, p, n, r); return; }
+    if (row.fn == M_B64) { mut_b64<LVL>(c, p, n, r); return; }
+    if (row.fn == M_JS) { mut_js<LVL>(c, p, n, r); return; }
+    if (row.fn == M_SGM) { mut_sgm<LVL>(c, p, n, r); return; }
     r.kind = RES_UNSUPPORTED; r.delta = 0; r.rechunk = 0; r.consumed_next = 0;
 }
-// dispatch inside a nested round (eb_mut_nested.cuh): one level of nesting is executed on the device; a nested
-// round that would itself open one (b64 inside decoded base64, inner-text js) flags the case instead
-EB_DEV void mut_apply_inner(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) {
-    if (mut_apply_base(c, row, p, n, r)) return;
-    if (row.fn == M_JS) { mut_js<false>(c, p, n, r); return; }
-    if (row.fn == M_B64) { mut_b64<false>(c, p, n, r); return; }
-    if (row.fn == M_SGM) { mut_sgm<false>(c, p, n, r); return; }
-    r.kind = RES_UNSUPPORTED; r.delta = 0; r.rechunk = 0; r.consumed_next = 0;
-}
+EB_DEV void mut_apply(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) { mut_apply_level<0>(c, row, p, n, r); }
 
 }  // namespace eb

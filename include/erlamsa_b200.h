@@ -109,8 +109,11 @@ void eb200_shutdown(eb200_ctx* ctx);
  * Whole batch, host buffers in, host buffers out (what the NIF calls).
  *   data/off : packed corpus, blob b = data[off[b] .. off[b+1]);  n_blobs >= 1
  *   n_cases  : number of cases; case k (0-based) has I = first_case + k and reads blob (I-1) mod n_blobs
- *   out_data : *out_data receives a malloc()ed buffer with the packed outputs (free with eb200_free)
- *   out_off  : caller array of n_cases+1 entries: case k output = (*out_data)[out_off[k] .. out_off[k]+out_len[k])
+ *   out_data : *out_data receives a malloc()ed buffer with the outputs (free with eb200_free)
+ *   out_off  : caller array of n_cases+1 entries: case k output = (*out_data)[out_off[k] .. out_off[k]+out_len[k]);
+ *              out_off[n_cases] = bytes used in the buffer. Case regions are 16-byte aligned and do not overlap, but
+ *              they are NOT back to back: in the default single-pass mode each case owns a slot sized from its input
+ *              (plus slack) and larger results live behind the slots, so always go through out_off / out_len.
  *   out_len  : caller array of n_cases entries
  *   meta     : optional caller array of n_cases entries
  */
@@ -120,8 +123,9 @@ int  eb200_fuzz_batch(eb200_ctx* ctx, const eb200_opts* opts,
                       eb200_meta* meta, eb200_stats* stats);
 void eb200_free(void* p);
 
-/* Same as eb200_fuzz_batch, but the packed outputs are written into a caller buffer (e.g. a resource
- * binary or pinned staging memory owned by the NIF); EB200_ERR_NOMEM when out_capacity is too small. */
+/* Same as eb200_fuzz_batch, but the outputs are written into a caller buffer (e.g. a resource binary or pinned
+ * staging memory owned by the NIF); EB200_ERR_NOMEM when out_capacity is too small. Size it as
+ * sum(input of the cases) * 17/16 + 512 * n_cases + room for the cases that outgrow their slot. */
 int  eb200_fuzz_batch_into(eb200_ctx* ctx, const eb200_opts* opts,
                            const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases,
                            uint8_t* out_buf, uint64_t out_capacity, uint64_t* out_off, uint64_t* out_len,
