@@ -9,7 +9,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "liberlamsa_b200.so")
+LIB_PATH = os.environ.get("EB200_LIB") or os.path.join(PKG_DIR, "liberlamsa_b200.so")   # EB200_LIB: A/B builds of the same engine
 SRC = os.path.join(PKG_DIR, "csrc", "eb_engine.cu")
 
 N_MUTATORS = 41

@@ -96,6 +96,7 @@ EB_DEV double adjust_priority(double pri, double delta) {   // :1238-1242
     if (delta == 0.0) return pri;
     return fmax(2.0, fmin(10.0, pri + delta));
 }
+template <bool FULL>
 EB_DEV void mux_fuzzers(CaseCtx& c) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     if (active_count(ws) == 0 || active_is_single_empty(ws)) return;
@@ -122,7 +123,7 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
         if (!big) {
             MutRow row = ws->rows[ws->order[t]];
             temp_reset(c);
-            mut_apply(c, row, p, n, r);
+            if (FULL) mut_apply(c, row, p, n, r); else mut_apply_light(c, row, p, n, r);
             if (r.kind == RES_UNSUPPORTED) ws->status = CASE_UNSUPPORTED;
             if (ws->status != CASE_OK) return;
             row.score = adjust_priority(row.score, r.delta);
@@ -269,6 +270,8 @@ enum { CONT_OD = 0, CONT_ND = 1, CONT_BU = 2, CONT_PAT = 3 };
 
 __host__ EB_DEV bool pat_supported(int id) { return id >= 0 && id < P_COUNT; }
 
+// FULL false: od nd bu co nu only (the host never launches that flavour with another pattern selected)
+template <bool FULL>
 EB_DEV void run_case_machine(CaseCtx& c, int pat) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     int cont = CONT_OD, next = 0;
@@ -284,6 +287,7 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             ip = g.rand(INITIAL_IP);
             if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
             split_big(c);
+        } else if (!FULL) { ws->status = CASE_UNSUPPORTED; return;
         } else if (pat == P_SK) {
             // make_complex_pat + mutate_once_skipper :148-161,352-361
             next = (int)g.rand_elem_idx(P_COUNT);
@@ -371,7 +375,7 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             emit_head(c);
             if (ws->status != CASE_OK) return;
         }
-        mux_fuzzers(c);
+        mux_fuzzers<FULL>(c);
         if (ws->status != CASE_OK) return;
         // ---- continuation
         if (cont == CONT_OD) { emit_all(c); return; }
@@ -383,7 +387,7 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             for (int nb = 1;; nb++) {
                 bool pr = g.rand_occurs_fixed(4, 5);
                 if (!(pr || nb < 2)) break;
-                mux_fuzzers(c);
+                mux_fuzzers<FULL>(c);
                 if (ws->status != CASE_OK) return;
             }
             emit_all(c); return;
@@ -434,6 +438,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+template <bool FULL>
 EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideArgs& a, uint64_t k, int32_t pa1, int32_t pa2, int32_t pa3, uint64_t* mbar) {
     const uint8_t* data = a.data; const uint64_t* off = a.off; const Arenas& ar = a.ar;
     CaseOut* cases = a.cases; uint64_t* out_len = a.out_len; uint64_t* out_sz16 = a.out_sz16; MetaDev* meta = a.meta;
@@ -462,8 +467,8 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
             // mux_patterns :438-443 + choose_pri (reference src/erlamsa_utils.erl:155-160)
             int64_t x = (int64_t)c.rng.rand((uint64_t)bp.pat_sum);
             for (int i = 0; i < bp.n_pats; i++) { if (x == 0 || x < bp.pat_pri[i]) { pat = bp.pat_id[i]; break; } x -= bp.pat_pri[i]; }
-            if (pat < 0) ws->status = CASE_DIED; else run_case_machine(c, pat);
-            if (ws->status == CASE_OK) unwind_wrappers(c);
+            if (pat < 0) ws->status = CASE_DIED; else run_case_machine<FULL>(c, pat);
+            if (FULL && ws->status == CASE_OK) unwind_wrappers(c);
         }
         if (ws->status == CASE_OK && ws->olen > bp.max_case_out) { ws->status = CASE_OVERFLOW; ws->reason = 5; }
         if (ws->status == CASE_UNSUPPORTED || ws->status == CASE_OVERFLOW) { ws->noseg = 0; ws->olen = 0; o_push(c, seg_copy(blob, blen)); }
@@ -517,7 +522,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
 // lines: profiles/decide_r1b showed 53% of stall samples on instruction fetch with free-running warps.
 // Measured on C3 in single-pass mode (profiles/variants_r1.txt): barrier per case 4.3 ms, every 2nd case 5.2,
 // every 4th 5.9, split-phase (SYNC -1) 4.7, an extra barrier before the copy 4.6, free-running 6.3-6.4.
-template <int WARPS, int SYNC, int MINB>
+template <int WARPS, int SYNC, int MINB, bool FULL>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 eb_decide_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ off, BatchParams bp, Arenas ar,
                  CaseOut* __restrict__ cases, uint64_t* __restrict__ out_len, uint64_t* __restrict__ out_sz16, MetaDev* __restrict__ meta, FusedArgs fa) {
@@ -541,7 +546,7 @@ eb_decide_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ 
     for (uint64_t r = 0; r < rounds; r++) {
         if (SYNC > 0) __syncthreads();
         uint64_t k = r * nwarps + warp_global;
-        if (k < bp.n_cases) decide_one_case(ws, bp, a, k, par.a1, par.a2, par.a3, mbar);
+        if (k < bp.n_cases) decide_one_case<FULL>(ws, bp, a, k, par.a1, par.a2, par.a3, mbar);
         else if (SYNC < 0) mbar_arrive_warp(mbar);
         if (SYNC < 0) mbar_wait(mbar, (uint32_t)(r & 1));
         par.a1 = (int32_t)(((uint32_t)par.a1 * s1) % 30269u); par.a2 = (int32_t)(((uint32_t)par.a2 * s2) % 30307u); par.a3 = (int32_t)(((uint32_t)par.a3 * s3) % 30323u);

@@ -75,20 +75,34 @@ static const ApplyVariant apply_variants[] = {AV(16, 2, 8), AV(16, 1, 8), AV(16,
 static const int n_apply_variants = (int)(sizeof(apply_variants) / sizeof(apply_variants[0]));
 
 // decide-kernel configurations (warps per CTA, per-case CTA barrier, min CTAs/SM); env EB200_DECIDE_VARIANT
+// Every configuration exists in two flavours: FULL (all mutators and patterns) and LIGHT (byte / sequence / number /
+// line mutators under od nd bu co nu): the light call graph has a fraction of the static stack and code, which the
+// streaming configs (C3) feel directly -- the same source measured 4.30 / 4.42 / 4.52 ms at 3.1 / 3.6 / 4.5 KB of stack.
 struct DecideVariant {
     int warps; int ctas_per_sm; const char* name;
-    cudaError_t (*prepare)();
-    void (*launch)(int, cudaStream_t, const uint8_t*, const uint64_t*, const BatchParams&, const Arenas&, CaseOut*, uint64_t*, uint64_t*, MetaDev*, const FusedArgs&);
+    cudaError_t (*prepare)(bool);
+    void (*launch)(bool, int, cudaStream_t, const uint8_t*, const uint64_t*, const BatchParams&, const Arenas&, CaseOut*, uint64_t*, uint64_t*, MetaDev*, const FusedArgs&);
 };
 template <int W, int S, int M>
-static cudaError_t prepare_decide() { return cudaFuncSetAttribute(eb_decide_kernel<W, S, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpState) * W)); }
+static cudaError_t prepare_decide(bool full) {
+    return full ? cudaFuncSetAttribute(eb_decide_kernel<W, S, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpState) * W))
+                : cudaFuncSetAttribute(eb_decide_kernel<W, S, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpState) * W));
+}
 template <int W, int S, int M>
-static void launch_decide(int grid, cudaStream_t st, const uint8_t* d, const uint64_t* o, const BatchParams& bp, const Arenas& ar, CaseOut* c, uint64_t* ol, uint64_t* sz, MetaDev* m, const FusedArgs& fa) {
-    eb_decide_kernel<W, S, M><<<grid, W * 32, sizeof(WarpState) * W, st>>>(d, o, bp, ar, c, ol, sz, m, fa);
+static void launch_decide(bool full, int grid, cudaStream_t st, const uint8_t* d, const uint64_t* o, const BatchParams& bp, const Arenas& ar, CaseOut* c, uint64_t* ol, uint64_t* sz, MetaDev* m, const FusedArgs& fa) {
+    if (full) eb_decide_kernel<W, S, M, true><<<grid, W * 32, sizeof(WarpState) * W, st>>>(d, o, bp, ar, c, ol, sz, m, fa);
+    else eb_decide_kernel<W, S, M, false><<<grid, W * 32, sizeof(WarpState) * W, st>>>(d, o, bp, ar, c, ol, sz, m, fa);
 }
 #define DV(W, S, M) {W, M, #W "w" #S #M "m", prepare_decide<W, S, M>, launch_decide<W, S, M>}
-// measured on C3 (profiles/variants_r1.txt): 32w-sync 2.55 ms | 16w-sync 2.76 | 4w-free 3.55 | 32w-free 3.55
-static const DecideVariant decide_variants[] = {DV(32, 1, 1), DV(32, -1, 1), DV(16, 1, 2), DV(4, 0, 8)};
+// measured on C3 (profiles/variants_r1.txt): barrier per case wins over every relaxation; 4 free-running warps x 8 CTAs kept for A/B
+static const DecideVariant decide_variants[] = {DV(32, 1, 1), DV(4, 0, 8)};
+// does this batch fit the LIGHT flavour?
+static bool batch_is_light(const BatchParams& bp) {
+    if (getenv("EB200_FORCE_FULL")) return false;
+    for (int i = 0; i < bp.n_rows; i++) if (!mut_is_light(bp.row_id[i])) return false;
+    for (int i = 0; i < bp.n_pats; i++) { int p = bp.pat_id[i]; if (!(p == P_OD || p == P_ND || p == P_BU || p == P_CO || p == P_NU)) return false; }
+    return true;
+}
 static const int n_decide_variants = (int)(sizeof(decide_variants) / sizeof(decide_variants[0]));
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_); return EB200_ERR_CUDA; } } while (0)
@@ -202,7 +216,7 @@ int eb200_init(int device, eb200_ctx** out) {
     if (cudaMemcpyToSymbol(c_funny, f.data(), sizeof(FunnyEntry) * 192) != cudaSuccess || cudaMemcpyToSymbol(c_funny_n, &fn, sizeof(int)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
     if (const char* v = getenv("EB200_MODE")) ctx->fused = strcmp(v, "twopass") != 0;
     if (const char* v = getenv("EB200_DECIDE_VARIANT")) { int k = atoi(v); if (k >= 0 && k < n_decide_variants) ctx->decide_variant = k; }
-    if (decide_variants[ctx->decide_variant].prepare() != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
+    if (decide_variants[ctx->decide_variant].prepare(true) != cudaSuccess || decide_variants[ctx->decide_variant].prepare(false) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
     *out = ctx; return EB200_OK;
 }
 
@@ -256,7 +270,7 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
         }
         CK(cudaEventRecord(ctx->ev[0], st));
         FusedArgs fa; memset(&fa, 0, sizeof(fa));
-        dv.launch(grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
+        dv.launch(!batch_is_light(bp), grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], st));
         (*launches)++;
@@ -343,7 +357,7 @@ static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* op
         FusedArgs fa; fa.fused = 1; fa.out = d_out; fa.out_capacity = out_capacity; fa.slot_off = (const uint64_t*)ctx->slot_off.p; fa.out_off = d_out_off;
         fa.ovf_base = slots; fa.ovf_used = (unsigned long long*)ctx->counters.p + 3; fa.data_bytes = data_bytes;
         CK(cudaEventRecord(ctx->ev[0], st));
-        dv.launch(grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
+        dv.launch(!batch_is_light(bp), grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[3], st));
         (*launches)++;

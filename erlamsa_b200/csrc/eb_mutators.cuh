@@ -375,4 +375,28 @@ EB_DEV void mut_apply_level(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t 
 }
 EB_DEV void mut_apply(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) { mut_apply_level<0>(c, row, p, n, r); }
 
+// The LIGHT kernel flavour: byte / sequence / number / line / utf-8 mutators only -- no lexer, trees, fuse, field
+// search or nested rounds in its call graph, so its static stack and its instruction footprint stay small. The host
+// picks it when the selected mutators and patterns allow (eb_engine.cu); results are identical by construction.
+__host__ __device__ inline bool mut_is_light(int id) {
+    switch (id) {
+    case M_BD: case M_BEI: case M_BED: case M_BF: case M_BI: case M_BER: case M_BR: case M_UW: case M_UI:
+    case M_SP: case M_SR: case M_SD: case M_SNAND: case M_SRND: case M_NUM:
+    case M_LD: case M_LDS: case M_LR2: case M_LRI: case M_LR: case M_LS: case M_LP: case M_LIS: case M_LRS: case M_NIL: return true;
+    default: return false;
+    }
+}
+EB_DEV void mut_apply_light(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutResult& r) {
+    int id = row.fn;
+    switch (id) {
+    case M_BD: case M_BEI: case M_BED: case M_BF: case M_BI: case M_BER: case M_BR: case M_UW: case M_UI: mut_byte(c, id, p, n, r); return;
+    case M_SP: case M_SR: case M_SD: case M_SNAND: case M_SRND: mut_bytes(c, id, p, n, r); return;
+    case M_NUM: mut_num(c, p, n, r); return;
+    case M_LD: case M_LDS: case M_LR2: case M_LRI: case M_LR: case M_LS: case M_LP: mut_line(c, id, p, n, r); return;
+    case M_LIS: case M_LRS: mut_st_line(c, id, p, n, r); return;
+    case M_NIL: r.kind = RES_SAME; r.delta = -1; r.rechunk = 0; r.consumed_next = 0; return;
+    default: r.kind = RES_UNSUPPORTED; r.delta = 0; r.rechunk = 0; r.consumed_next = 0; return;
+    }
+}
+
 }  // namespace eb

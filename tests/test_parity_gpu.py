@@ -185,6 +185,23 @@ def test_c3_mutators_64k(engine, oracle):
     assert n == len(blobs)
 
 
+def test_light_and_full_kernel_flavours_agree(engine):
+    """the host launches a kernel flavour without the heavy mutators in its call graph when the options allow;
+    forcing the full one must not change a byte"""
+    import os
+    blobs = corpus.mixed_corpus(0xE21A0400, 300)
+    opts = {"mutations": {c: 1 for c in ("bd", "bf", "num", "sr", "sp", "ld", "lis", "uw", "snand")}, "patterns": {"od": 1, "nd": 1, "bu": 1},
+            "seed": (3, 3, 3), "max_case_out": CAP}
+    a_out, a_meta = engine.fuzz_batch(blobs, opts, n_cases=600)
+    os.environ["EB200_FORCE_FULL"] = "1"
+    try:
+        b_out, b_meta = engine.fuzz_batch(blobs, opts, n_cases=600)
+    finally:
+        del os.environ["EB200_FORCE_FULL"]
+    assert a_out == b_out
+    assert [(m.status, m.draws, m.pattern, list(m.used)) for m in a_meta] == [(m.status, m.draws, m.pattern, list(m.used)) for m in b_meta]
+
+
 def test_case_window_and_corpus_wraparound(engine, oracle):
     """first_case / n_cases select a window of the reference's case loop; blobs are reused modulo the corpus size"""
     blobs = corpus.mixed_corpus(0xE21A0300, 37)
