@@ -53,7 +53,7 @@ def ncu_traffic(workload, fused):
     return tot or None
 
 
-TRAFFIC_PROFILE = {True: "fused_r1b.txt", False: "apply_r1b.txt"}
+TRAFFIC_PROFILE = {True: "fused_r1c.txt", False: "apply_r1b.txt"}
 
 
 def peak_hbm():
@@ -70,10 +70,13 @@ class ClockSampler:
         self.idx = gpu_index
 
     def start(self):
+        # started BEFORE the warm-up steps: nvidia-smi's own start-up (NVML initialisation on the driver) must not fall
+        # into the timed region (it cost the first measurements of this bench ~10 % of kernel time); once running it only
+        # polls. Every line carries the wall-clock time it was taken, stop() keeps the ones inside the timed window.
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -81,15 +84,20 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
+        inside = [ln for (t, ln) in self.lines if t0 is not None and t0 <= t <= t1 + 0.03]
+        window = "timed region"
+        if not inside:      # a region shorter than the polling period: the samples right around it
+            inside = [ln for (t, ln) in self.lines if t0 is None or t0 - 0.2 <= t <= t1 + 0.1] or [ln for (_, ln) in self.lines]
+            window = "timed region +- 0.2 s"
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -101,7 +109,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def make_corpus_device(torch, kind, n, size, dev, seed):
@@ -167,16 +175,18 @@ def run_ours(args):
         return eng.fuzz_batch_device(o, data.data_ptr(), off.data_ptr(), n_cases, data_bytes, n_cases, d_out.data_ptr(), out_cap,
                                      d_out_off.data_ptr(), d_out_len.data_ptr(), 0, stream.cuda_stream)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    wall0 = time.time()
     ev0.record(stream)
     apply_ms, decide_ms, scan_ms, launches, bytes_out = [], [], [], 0, 0
     flagged = {"unsupported": 0, "died": 0, "overflow": 0}
@@ -187,8 +197,9 @@ def run_ours(args):
         flagged["unsupported"] += st.n_unsupported; flagged["died"] += st.n_died; flagged["overflow"] += st.n_overflow
     ev1.record(stream)
     torch.cuda.synchronize()
+    wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         dist.barrier()
