@@ -11,7 +11,7 @@
 //     insert, pump, break) are re-orderings / repetitions of token ranges;
 //   * pump_path/3 (:496-508), which re-inserts the growing tree at index 2E-1, 4E-3, ..., yields
 //     prefix^(2^k) ++ element ++ suffix^(2^k) with prefix/suffix the parts of the start tag around element E.
-// The oracle (oracle/src/sgml.hpp) keeps the AST form; tests compare the two byte for byte.
+// The CPU restatement used by the tests keeps the AST form; the tests compare the two byte for byte.
 #pragma once
 
 namespace eb {
