@@ -40,7 +40,15 @@ fuzz_batch(Corpus, Opts) when is_list(Corpus) ->
     MutaPri = pri_vector(mutator_table(), maps:get(mutations, Opts, erlamsa_mutations:default([]))),
     PatPri = pri_vector(pattern_table(), maps:get(patterns, Opts, erlamsa_patterns:default())),
     case fuzz_batch_nif(Corpus, N - Skip, Seed, MutaPri, PatPri, Skip + 1, maps:get(blockscale, Opts, 1.0) * 1.0) of
-        {ok, Outs} -> [O || O <- Outs, O =/= <<>>];             %% record_result/2 drops empty results
+        {ok, Outs} ->
+            %% a flagged case (path without a device implementation, capacity limit) is re-run, alone, by the reference:
+            %% case I draws the I-th gen_predictable_seed() there too (skip => I - 1), so the list stays what
+            %% erlamsa_main:fuzzer/1 would have produced
+            Redo = fun(I) ->
+                       B = lists:nth(((I - 1) rem length(Corpus)) + 1, Corpus),
+                       erlamsa_main:fuzzer(maps:merge(Opts, #{paths => [direct], output => return, input => B, n => I, skip => I - 1}))
+                   end,
+            lists:append([case O of {flagged, I} -> Redo(I); <<>> -> []; _ -> [O] end || O <- Outs]);   %% record_result/2 drops empty results
         {error, _Why} ->                                          %% unsupported mutator, no GPU, ...: the reference path
             lists:append([erlamsa_main:fuzzer(maps:merge(Opts, #{paths => [direct], output => return, input => B, n => 1}))
                           || B <- Corpus])

@@ -65,21 +65,30 @@ static ERL_NIF_TERM fuzz_batch_nif(ErlNifEnv* env, int argc, const ERL_NIF_TERM 
     uint8_t* out = NULL;
     uint64_t* out_off = (uint64_t*)enif_alloc(sizeof(uint64_t) * (n_cases + 1));
     uint64_t* out_len = (uint64_t*)enif_alloc(sizeof(uint64_t) * (n_cases ? n_cases : 1));
-    int rc = eb200_fuzz_batch(g_ctx, &o, data, off, n_blobs, n_cases, &out, out_off, out_len, NULL, NULL);
+    eb200_meta* meta = (eb200_meta*)enif_alloc(sizeof(eb200_meta) * (n_cases ? n_cases : 1));
+    int rc = eb200_fuzz_batch(g_ctx, &o, data, off, n_blobs, n_cases, &out, out_off, out_len, meta, NULL);
     ERL_NIF_TERM res;
     if (rc != EB200_OK) {
         res = err(env, rc == EB200_ERR_UNSUPPORTED ? "unsupported" : rc == EB200_ERR_SCRATCH ? "scratch" : "engine");
     } else {
+        /* {ok, [Binary | {flagged, CaseNo}]}: a case the engine flagged (unsupported path / capacity)
+         * is handed back by number so that the Erlang side re-runs exactly that case on the reference path;
+         * a case whose worker died (status 2) is an empty binary, as in the reference */
         ERL_NIF_TERM list = enif_make_list(env, 0);
         for (uint64_t k = n_cases; k-- > 0;) {   /* build back to front; empty outputs are kept, the caller filters (record_result/2) */
-            ERL_NIF_TERM b; unsigned char* p = enif_make_new_binary(env, out_len[k], &b);
-            memcpy(p, out + out_off[k], out_len[k]);
+            ERL_NIF_TERM b;
+            if (meta[k].status == EB200_CASE_UNSUPPORTED || meta[k].status == EB200_CASE_OVERFLOW) {
+                b = enif_make_tuple2(env, enif_make_atom(env, "flagged"), enif_make_uint64(env, first_case + k));
+            } else {
+                unsigned char* p = enif_make_new_binary(env, out_len[k], &b);
+                memcpy(p, out + out_off[k], out_len[k]);
+            }
             list = enif_make_list_cell(env, b, list);
         }
         res = enif_make_tuple2(env, enif_make_atom(env, "ok"), list);
         eb200_free(out);
     }
-    enif_free(bins); enif_free(off); enif_free(data); enif_free(out_off); enif_free(out_len);
+    enif_free(bins); enif_free(off); enif_free(data); enif_free(out_off); enif_free(out_len); enif_free(meta);
     return res;
 }
 
