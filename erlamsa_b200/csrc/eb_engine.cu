@@ -604,6 +604,7 @@ static int fuzz_batch_host(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t
         fill_stats(ctx, stats); cudaEventElapsedTime(&stats->ms_total, ctx->ev[5], evEnd);
         stats->n_cases = n_cases; stats->kernels_launched = launches; stats->bytes_out = 0; stats->bytes_in = 0;
         for (uint64_t k = 0; k < n_cases; k++) { stats->bytes_out += out_len[k]; uint64_t b = (bp.first_case - 1 + k) % n_blobs; stats->bytes_in += off[b + 1] - off[b]; }
+        if (meta) { stats->n_unsupported = stats->n_died = stats->n_overflow = 0; }   // recount from the per-case records
         if (meta) for (uint64_t k = 0; k < n_cases; k++) { if (meta[k].status == EB200_CASE_UNSUPPORTED) stats->n_unsupported++; else if (meta[k].status == EB200_CASE_DIED) stats->n_died++; else if (meta[k].status == EB200_CASE_OVERFLOW) stats->n_overflow++; }
     }
     return EB200_OK;

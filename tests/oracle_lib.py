@@ -116,7 +116,8 @@ def fuzzer(blobs, opts=None, n_cases=None, first_case=1, **kw):
     if rc != 0:
         raise RuntimeError("oracle eo_fuzzer rc=%d" % rc)
     total = out_off[n_cases]
-    raw = C.string_at(out_p, total) if total else b""
+    # (ctypes.string_at takes a C int size: a few GB of outputs -- bench.py's CPU legs -- would wrap negative)
+    raw = bytes((C.c_char * total).from_address(out_p.value)) if total else b""
     outs = [raw[out_off[i]:out_off[i + 1]] for i in range(n_cases)]
     return outs, list(meta)
 
