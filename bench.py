@@ -151,13 +151,13 @@ def run_ours(args):
         muts = {c: p for c, p in erlamsa_b200.default_mutations() if c in erlamsa_b200.supported_mutations()}
     else:
         muts = {c: 1 for c in muts}
-    eng = erlamsa_b200.Engine(local)
     data, off = make_corpus_device(torch, kind, n_cases, size, dev, 0xE21A0003 + rank)
     data_bytes = n_cases * size
     out_cap = data_bytes + data_bytes // 12 + 512 * n_cases + (256 << 20)   # output slots (input + 1/16 slack) + overflow region
     d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
     d_out_off = torch.empty(n_cases + 1, dtype=torch.int64, device=dev)
     d_out_len = torch.empty(n_cases, dtype=torch.int64, device=dev)
+    eng = erlamsa_b200.Engine(local)
     base_opts = {"mutations": muts, "patterns": pats, "seed": (1, 2, 3), "rng": args.rng, "scratch_bytes": 512 << 20}
     if args.workload == "c2":   # repeat mutators compounded by nd/bu rounds: cap a case at 128 KiB = 32 x its seed (flagged, not dropped)
         base_opts.update({"scratch_bytes": 8 << 30, "max_case_out": 128 << 10})
@@ -198,6 +198,8 @@ def run_ours(args):
     ev1.record(stream)
     torch.cuda.synchronize()
     wall1 = time.time()
+    if os.environ.get("EB200_BENCH_VERBOSE"):
+        print("per-step kernel ms:", " ".join("%.3f" % x for x in decide_ms), file=sys.stderr)
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     if world > 1:

@@ -25,11 +25,13 @@ for v in range(nvar + ndec):
     os.environ["EB200_DECIDE_VARIANT"] = str(0 if v < nvar else v - nvar)
     eng = erlamsa_b200.Engine(0)
     res = []
-    for i in range(6):
+    for i in range(int(os.environ.get("PERF_ITERS", "6"))):
         st = eng.fuzz_batch_device({"mutations": muts, "patterns": {"od": 1}, "seed": (1, 2, 3), "first_case": 1 + i * n_cases, "scratch_bytes": 256 << 20},
                                    data.data_ptr(), off.data_ptr(), n_cases, n_cases * size, n_cases, d_out.data_ptr(), out_cap, d_off.data_ptr(),
                                    d_len.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
         res.append((st.ms_decide, st.ms_scan, st.ms_apply, st.ms_total))
+    if os.environ.get("PERF_ITERS"):
+        print("per-step decide ms:", " ".join("%.3f" % r[0] for r in res), flush=True)
     res = res[2:]
     avg = [sum(r[k] for r in res) / len(res) for k in range(4)]
     gbs = (2 * n_cases * size) / ((avg[2] or avg[0]) * 1e-3) / 1e9
