@@ -47,3 +47,31 @@ def test_shard_windows_partition_the_case_range():
             first, cnt = shard_window(n, r, world, first_case=11)
             got.extend(range(first, first + cnt))
         assert got == list(range(11, 11 + n))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) runs without a GPU and prints one JSON
+    line with the keys of the bench contract"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "cases/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_markup_corpus_shapes():
+    """C4 documents: exact size, SGML ones tokenise as markup, JSON ones as a complete document (oracle-side check)"""
+    import oracle_lib as O
+    blobs = corpus.uniform_corpus(11, 6, 3000, "markup")
+    assert all(len(b) == 3000 for b in blobs)
+    outs, meta = O.fuzzer(blobs, mutations={"sgm": 1, "js": 1}, patterns={"od": 1}, seed=(1, 2, 3), n_cases=48, max_case_out=1 << 20)
+    assert all(m.status == 0 for m in meta)
+    assert sum(1 for m in meta if m.n_used) >= 40          # refusals would leave the case unused
