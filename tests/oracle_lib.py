@@ -122,6 +122,27 @@ def fuzzer(blobs, opts=None, n_cases=None, first_case=1, **kw):
     return outs, list(meta)
 
 
+def fuzzer_total_bytes(blobs, opts, n_cases, first_case=1):
+    """Same run as fuzzer() but the outputs stay in the library's buffer: returns only their total size. For timing
+    the restatement itself (bench.py's CPU legs) without a multi-GB copy into Python objects on the clock."""
+    data = b"".join(blobs)
+    off = (C.c_uint64 * (len(blobs) + 1))()
+    acc = 0
+    for i, b in enumerate(blobs):
+        off[i] = acc
+        acc += len(b)
+    off[len(blobs)] = acc
+    buf = C.create_string_buffer(data, len(data) + 1)
+    out_p = C.c_void_p()
+    out_off = (C.c_uint64 * (n_cases + 1))()
+    meta = (Meta * n_cases)()
+    rc = lib().eo_fuzzer(C.byref(opts), C.cast(buf, C.c_void_p), off, len(blobs), first_case, n_cases,
+                         C.byref(out_p), out_off, meta)
+    if rc != 0:
+        raise RuntimeError("oracle eo_fuzzer rc=%d" % rc)
+    return int(out_off[n_cases])
+
+
 def run_mutator(code, data, seed, next_block=None, rounds=1, opts=None):
     """Seed the RNG, apply one mutator `rounds` times to [data | next_block]; mirrors the reference's
     eunit helpers (src/erlamsa_mutations_test.erl:40-49). Returns (bytes, delta, rc)."""
