@@ -100,6 +100,7 @@ struct Arenas {
     // temp + w * temp_per_warp; reset for every mutator attempt, never referenced by a result
     uint8_t* temp; uint64_t temp_per_warp;
     unsigned long long* flagged;   // [3]: cases that ended unsupported / died / over a cap
+    uint8_t* case_status;          // [n_cases]: status | reason << 4 (the host re-runs arena-overflow cases from it)
 };
 
 struct __align__(8) MetaDev {

@@ -406,7 +406,10 @@ struct DecideArgs {
     int fused; uint8_t* out; uint64_t out_capacity; const uint64_t* slot_off; uint64_t* out_off;
     uint64_t ovf_base; unsigned long long* ovf_used; uint64_t data_bytes;
 };
-struct FusedArgs { int fused; uint8_t* out; uint64_t out_capacity; const uint64_t* slot_off; uint64_t* out_off; uint64_t ovf_base; unsigned long long* ovf_used; uint64_t data_bytes; };
+// case_list: a follow-up launch over the cases a previous launch had to flag for lack of arena space re-runs exactly
+// those case numbers (same seeds, same slots; what outgrows the slot goes to the overflow region as before)
+struct FusedArgs { int fused; uint8_t* out; uint64_t out_capacity; const uint64_t* slot_off; uint64_t* out_off; uint64_t ovf_base; unsigned long long* ovf_used; uint64_t data_bytes;
+                   const uint32_t* case_list; uint64_t n_list; unsigned long long* case_counter; int deciders; };
 
 // slot sizes for the single-pass mode: input length + slack, 16-byte aligned (the common mutations change a
 // case by a few bytes; anything bigger spills to the overflow region)
@@ -419,37 +422,17 @@ __global__ void __launch_bounds__(256) eb_slot_sizes(const uint64_t* __restrict_
     sz16[k] = align16(len + slack);
 }
 
-// one test case, start to finish, by one warp
-// split-phase CTA barrier on a shared-memory mbarrier (one arrival per warp): a warp arrives when its case is
-// DECIDED and waits only before it starts deciding the next one, so its copy runs inside the barrier's slack
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
-    __syncwarp();
-    if (lane_id() == 0) {
-        uint64_t st;
-        asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-        (void)st;
-    }
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0, addr = (uint32_t)__cvta_generic_to_shared(bar);
-    while (!done) {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    }
-}
-
+// one test case, start to finish, decided by one warp (bulk byte work goes to the CTA's workers through q)
 template <bool FULL>
-EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideArgs& a, uint64_t k, int32_t pa1, int32_t pa2, int32_t pa3, uint64_t* mbar) {
+EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideArgs& a, uint64_t k, int32_t pa1, int32_t pa2, int32_t pa3, JobQ* q, uint32_t temp_slot) {
     const uint8_t* data = a.data; const uint64_t* off = a.off; const Arenas& ar = a.ar;
     CaseOut* cases = a.cases; uint64_t* out_len = a.out_len; uint64_t* out_sz16 = a.out_sz16; MetaDev* meta = a.meta;
     {
         uint64_t I = bp.first_case + k;                 // the reference's 1-based case number
         uint64_t b = (I - 1) % bp.n_blobs;
         const uint8_t* blob = data + off[b]; uint32_t blen = (uint32_t)(off[b + 1] - off[b]);
-        CaseCtx c; c.ws = ws; c.bp = &bp; c.ar = ar;
-        c.temp_base = ar.temp ? ar.temp + (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ar.temp_per_warp : nullptr;
+        CaseCtx c; c.ws = ws; c.bp = &bp; c.ar = ar; c.q = q;
+        c.temp_base = ar.temp ? ar.temp + (uint64_t)temp_slot * ar.temp_per_warp : nullptr;
         c.temp_used = 0; c.temp_floor = 0; c.snand_kind = bp.snand_kind;
         // thread seed: three erand(99999) at parent draw index 3*(I-1) (the caller keeps the parent state there)
         Rng par; par.mode = 0; par.a1 = pa1; par.a2 = pa2; par.a3 = pa3; par.draws = 0; par.key = 0; par.ctr_hi = 0;
@@ -476,7 +459,6 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         if (ws->status == CASE_UNSUPPORTED || ws->status == CASE_OVERFLOW) { ws->noseg = 0; ws->olen = 0; o_push(c, seg_copy(blob, blen)); }
         if (ws->status == CASE_DIED) { ws->noseg = 0; ws->olen = 0; }
         __syncwarp();
-        if (mbar) mbar_arrive_warp(mbar);
         unsigned long long sb = 0; int ns = ws->noseg;
         if (a.fused) {
             // single-pass mode: the output slot of case k was fixed before the kernel (prefix sum over INPUT sizes +
@@ -485,15 +467,24 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
             uint64_t s0 = a.slot_off[k], cap = a.slot_off[k + 1] - s0;
             uint64_t dsto = s0;
             if (ws->olen > cap) {
-                unsigned long long o = 0, need = align16(ws->olen);
-                if (lane_id() == 0) o = atomicAdd(a.ovf_used, need);
+                // bump allocation by compare-and-swap: the fill level only ever advances by GRANTED requests, so a
+                // follow-up launch over the flagged cases continues exactly behind the bytes that are in use
+                unsigned long long o = ~0ull, need = align16(ws->olen);
+                if (lane_id() == 0) {
+                    unsigned long long cur = *(volatile unsigned long long*)a.ovf_used;
+                    while (a.ovf_base + cur + need <= a.out_capacity) {
+                        unsigned long long prev = atomicCAS(a.ovf_used, cur, cur + need);
+                        if (prev == cur) { o = cur; break; }
+                        cur = prev;
+                    }
+                }
                 o = __shfl_sync(0xffffffffu, o, 0);
-                if (a.ovf_base + o + need > a.out_capacity) {   // no room: flag the case, emit the input unchanged (always fits its slot)
+                if (o == ~0ull) {   // no room: flag the case, emit the input unchanged (always fits its slot)
                     if (lane_id() == 0) atomicOr(ar.overflow, 4u);
                     ws->status = CASE_OVERFLOW; ws->reason = 11; ws->noseg = 0; ws->olen = 0; o_push(c, seg_copy(blob, blen)); ns = ws->noseg;
                 } else dsto = a.ovf_base + o;
             }
-            segs_write_stream(ws->oseg, ws->noseg, a.out + dsto, data, data + a.data_bytes);
+            segs_write_stream(q, ws->oseg, ws->noseg, a.out + dsto, data, data + a.data_bytes);
             if (lane_id() == 0) { a.out_off[k] = dsto; out_len[k] = ws->olen; }
         } else {
             // two-pass mode: publish the edit script for the apply kernel
@@ -504,6 +495,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         }
         if (lane_id() == 0 && ws->status != CASE_OK && ar.flagged) atomicAdd(&ar.flagged[ws->status - 1], 1ull);
         if (lane_id() == 0) {
+            if (ar.case_status) ar.case_status[k] = (uint8_t)(ws->status | (ws->reason << 4));
             if (!a.fused) {
                 CaseOut co; co.seg_begin = sb; co.nseg = (uint32_t)ns; co.status = ws->status; co.out_len = ws->olen; co.pad = 0;
                 cases[k] = co; out_len[k] = ws->olen; out_sz16[k] = align16(ws->olen);
@@ -519,40 +511,56 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
     }
 }
 
-// WARPS warps per CTA, each taking whole cases. With SYNC 1 the CTA re-converges before every case so
-// that its warps walk the (large, branchy) scalar program in step and share instruction-cache
-// lines: profiles/decide_r1b showed 53% of stall samples on instruction fetch with free-running warps.
-// Measured on C3 in single-pass mode (profiles/variants_r1.txt): barrier per case 4.3 ms, every 2nd case 5.2,
-// every 4th 5.9, split-phase (SYNC -1) 4.7, an extra barrier before the copy 4.6, free-running 6.3-6.4.
-template <int WARPS, int SYNC, int MINB, bool FULL>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-eb_decide_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ off, BatchParams bp, Arenas ar,
-                 CaseOut* __restrict__ cases, uint64_t* __restrict__ out_len, uint64_t* __restrict__ out_sz16, MetaDev* __restrict__ meta, FusedArgs fa) {
+// The engine's one kernel: a persistent CTA per SM whose first `deciders` warps each take whole test cases from a global
+// counter and run the scalar per-case program; the remaining warps are workers that execute the bulk copies and block
+// scans the deciders post to the CTA's job queue (eb_jobs.cuh). deciders == all warps gives the round-1 arrangement
+// (every warp does its own byte work inline) for A/B runs. FULL / LIGHT: see mut_is_light().
+constexpr int CASE_THREADS = 1024;
+constexpr int PW_BITS = 48;
+template <bool FULL>
+__global__ void __launch_bounds__(CASE_THREADS, 1)
+eb_case_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ off, BatchParams bp, Arenas ar,
+               CaseOut* __restrict__ cases, uint64_t* __restrict__ out_len, uint64_t* __restrict__ out_sz16, MetaDev* __restrict__ meta, FusedArgs fa) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    WarpState* ws = reinterpret_cast<WarpState*>(smem_raw) + (threadIdx.x >> 5);
+    const int nwarps = (int)(blockDim.x >> 5), warp = (int)(threadIdx.x >> 5);
+    const int deciders = fa.deciders < nwarps ? fa.deciders : nwarps;
+    JobQ* q = reinterpret_cast<JobQ*>(smem_raw);
+    uint32_t* pw = reinterpret_cast<uint32_t*>(smem_raw + sizeof(JobQ));                 // [3][PW_BITS]: a^(3 * 2^j) mod p
+    WarpState* wsbase = reinterpret_cast<WarpState*>(smem_raw + ((sizeof(JobQ) + 3 * PW_BITS * 4 + 15) & ~(size_t)15));
+    jobq_init(q, deciders);
+    if (threadIdx.x < 3 * PW_BITS) {
+        int comp = threadIdx.x / PW_BITS, j = threadIdx.x % PW_BITS;
+        uint32_t m = comp == 0 ? 30269u : comp == 1 ? 30307u : 30323u, a0 = comp == 0 ? AS_M1 : comp == 1 ? AS_M2 : AS_M3;
+        uint32_t v = (a0 * a0 % m) * a0 % m;
+        for (int i = 0; i < j; i++) v = v * v % m;
+        pw[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (warp >= deciders) { worker_loop(q); return; }
+    JobQ* qq = deciders < nwarps ? q : nullptr;
+    WarpState* ws = wsbase + warp;
     DecideArgs a; a.data = data; a.off = off; a.ar = ar; a.cases = cases; a.out_len = out_len; a.out_sz16 = out_sz16; a.meta = meta;
     a.fused = fa.fused; a.out = fa.out; a.out_capacity = fa.out_capacity; a.slot_off = fa.slot_off; a.out_off = fa.out_off;
     a.ovf_base = fa.ovf_base; a.ovf_used = fa.ovf_used; a.data_bytes = fa.data_bytes;
-    uint64_t warp_global = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
-    uint64_t nwarps = (uint64_t)gridDim.x * WARPS;
-    uint64_t rounds = (bp.n_cases + nwarps - 1) / nwarps;
-    // parent stream position of this warp's first case, and the multipliers that advance it by one
-    // round (3 draws per case, nwarps cases per round): x_{k+s} = x_k * a^s mod p per AS183 component
-    Rng par; par.mode = 0; par.a1 = bp.parent_a1; par.a2 = bp.parent_a2; par.a3 = bp.parent_a3; par.draws = 0; par.key = 0; par.ctr_hi = 0;
-    par.jump(3 * (bp.first_case - 1 + warp_global));
-    uint32_t s1 = modpow_u32<30269>(AS_M1, 3 * nwarps), s2 = modpow_u32<30307>(AS_M2, 3 * nwarps), s3 = modpow_u32<30323>(AS_M3, 3 * nwarps);
-    // SYNC -1: split-phase barrier (arrive after deciding, wait before the next decision)
-    __shared__ uint64_t mbar_store;
-    uint64_t* mbar = SYNC < 0 ? &mbar_store : nullptr;
-    if (SYNC < 0) { if (threadIdx.x == 0) mbar_init(mbar, WARPS); __syncthreads(); }
-    for (uint64_t r = 0; r < rounds; r++) {
-        if (SYNC > 0) __syncthreads();
-        uint64_t k = r * nwarps + warp_global;
-        if (k < bp.n_cases) decide_one_case<FULL>(ws, bp, a, k, par.a1, par.a2, par.a3, mbar);
-        else if (SYNC < 0) mbar_arrive_warp(mbar);
-        if (SYNC < 0) mbar_wait(mbar, (uint32_t)(r & 1));
-        par.a1 = (int32_t)(((uint32_t)par.a1 * s1) % 30269u); par.a2 = (int32_t)(((uint32_t)par.a2 * s2) % 30307u); par.a3 = (int32_t)(((uint32_t)par.a3 * s3) % 30323u);
+    const uint64_t total = fa.case_list ? fa.n_list : bp.n_cases;
+    const uint32_t temp_slot = blockIdx.x * (uint32_t)deciders + (uint32_t)warp;
+    for (;;) {
+        unsigned long long idx = 0;
+        if (lane_id() == 0) idx = atomicAdd(fa.case_counter, 1ull);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= total) break;
+        uint64_t k = fa.case_list ? (uint64_t)fa.case_list[idx] : (uint64_t)idx;
+        // parent stream at case k: x0 * (a^3)^(first_case - 1 + k) mod p per AS183 component, from the power table
+        uint64_t e = bp.first_case - 1 + k;
+        uint32_t a1 = (uint32_t)bp.parent_a1, a2 = (uint32_t)bp.parent_a2, a3 = (uint32_t)bp.parent_a3;
+        for (int j = 0; e && j < PW_BITS; j++, e >>= 1) if (e & 1) { a1 = a1 * pw[j] % 30269u; a2 = a2 * pw[PW_BITS + j] % 30307u; a3 = a3 * pw[2 * PW_BITS + j] % 30323u; }
+        if (e) {   // beyond 2^48 cases: finish with the generic jump
+            Rng t; t.mode = 0; t.a1 = (int32_t)a1; t.a2 = (int32_t)a2; t.a3 = (int32_t)a3; t.draws = 0; t.key = 0; t.ctr_hi = 0; t.jump(3 * (e << PW_BITS));
+            a1 = (uint32_t)t.a1; a2 = (uint32_t)t.a2; a3 = (uint32_t)t.a3;
+        }
+        decide_one_case<FULL>(ws, bp, a, k, (int32_t)a1, (int32_t)a2, (int32_t)a3, qq, temp_slot);
     }
+    if (qq) jobq_decider_done(q);
 }
 
 }  // namespace eb

@@ -55,7 +55,9 @@ struct eb200_ctx {
     cudaEvent_t ev[6];
     bool funny_loaded = false;
     int apply_variant = 0;
-    int decide_variant = 0;
+    int threads = CASE_THREADS;   // eb_case_kernel: threads per CTA (EB200_THREADS) ...
+    int deciders = 12;            // ... of which this many warps decide cases and the rest are copy/scan workers (EB200_DECIDERS)
+    DevBuf case_status, retry_list;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // host-path pipeline (created on first use)
 };
 
@@ -74,28 +76,6 @@ static void launch_apply(unsigned ctas, cudaStream_t st, const CaseOut* c, const
 static const ApplyVariant apply_variants[] = {AV(16, 2, 8), AV(16, 1, 8), AV(16, 2, 6), AV(32, 2, 8), AV(8, 2, 8), AV(32, 1, 8)};
 static const int n_apply_variants = (int)(sizeof(apply_variants) / sizeof(apply_variants[0]));
 
-// decide-kernel configurations (warps per CTA, per-case CTA barrier, min CTAs/SM); env EB200_DECIDE_VARIANT
-// Every configuration exists in two flavours: FULL (all mutators and patterns) and LIGHT (byte / sequence / number /
-// line mutators under od nd bu co nu): the light call graph has a fraction of the static stack and code, which the
-// streaming configs (C3) feel directly -- the same source measured 4.30 / 4.42 / 4.52 ms at 3.1 / 3.6 / 4.5 KB of stack.
-struct DecideVariant {
-    int warps; int ctas_per_sm; const char* name;
-    cudaError_t (*prepare)(bool);
-    void (*launch)(bool, int, cudaStream_t, const uint8_t*, const uint64_t*, const BatchParams&, const Arenas&, CaseOut*, uint64_t*, uint64_t*, MetaDev*, const FusedArgs&);
-};
-template <int W, int S, int M>
-static cudaError_t prepare_decide(bool full) {
-    return full ? cudaFuncSetAttribute(eb_decide_kernel<W, S, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpState) * W))
-                : cudaFuncSetAttribute(eb_decide_kernel<W, S, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpState) * W));
-}
-template <int W, int S, int M>
-static void launch_decide(bool full, int grid, cudaStream_t st, const uint8_t* d, const uint64_t* o, const BatchParams& bp, const Arenas& ar, CaseOut* c, uint64_t* ol, uint64_t* sz, MetaDev* m, const FusedArgs& fa) {
-    if (full) eb_decide_kernel<W, S, M, true><<<grid, W * 32, sizeof(WarpState) * W, st>>>(d, o, bp, ar, c, ol, sz, m, fa);
-    else eb_decide_kernel<W, S, M, false><<<grid, W * 32, sizeof(WarpState) * W, st>>>(d, o, bp, ar, c, ol, sz, m, fa);
-}
-#define DV(W, S, M) {W, M, #W "w" #S #M "m", prepare_decide<W, S, M>, launch_decide<W, S, M>}
-// measured on C3 (profiles/variants_r1.txt): barrier per case wins over every relaxation; 4 free-running warps x 8 CTAs kept for A/B
-static const DecideVariant decide_variants[] = {DV(32, 1, 1), DV(4, 0, 8)};
 // does this batch fit the LIGHT flavour?
 static bool batch_is_light(const BatchParams& bp) {
     if (getenv("EB200_FORCE_FULL")) return false;
@@ -103,7 +83,10 @@ static bool batch_is_light(const BatchParams& bp) {
     for (int i = 0; i < bp.n_pats; i++) { int p = bp.pat_id[i]; if (!(p == P_OD || p == P_ND || p == P_BU || p == P_CO || p == P_NU)) return false; }
     return true;
 }
-static const int n_decide_variants = (int)(sizeof(decide_variants) / sizeof(decide_variants[0]));
+// shared memory of eb_case_kernel: job queue + parent-stream power table + one WarpState per deciding warp
+static size_t case_smem(int deciders) { return ((sizeof(JobQ) + 3 * PW_BITS * 4 + 15) & ~(size_t)15) + sizeof(WarpState) * (size_t)deciders; }
+// counters block (device, 8 x u64): [0] scratch_used [1] segs_used [2] overflow bits [3] ovf_used [4..6] flagged [7] next case
+enum { CNT_SCRATCH = 0, CNT_SEGS = 1, CNT_OVERFLOW = 2, CNT_OVF_USED = 3, CNT_FLAGGED = 4, CNT_NEXT_CASE = 7 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_); return EB200_ERR_CUDA; } } while (0)
 
@@ -215,26 +198,66 @@ int eb200_init(int device, eb200_ctx** out) {
     int fn = (int)f.size(); f.resize(192);
     if (cudaMemcpyToSymbol(c_funny, f.data(), sizeof(FunnyEntry) * 192) != cudaSuccess || cudaMemcpyToSymbol(c_funny_n, &fn, sizeof(int)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
     if (const char* v = getenv("EB200_MODE")) ctx->fused = strcmp(v, "twopass") != 0;
-    if (const char* v = getenv("EB200_DECIDE_VARIANT")) { int k = atoi(v); if (k >= 0 && k < n_decide_variants) ctx->decide_variant = k; }
-    if (decide_variants[ctx->decide_variant].prepare(true) != cudaSuccess || decide_variants[ctx->decide_variant].prepare(false) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
+    if (const char* v = getenv("EB200_THREADS")) { int k = atoi(v); if (k >= 64 && k <= CASE_THREADS && k % 32 == 0) ctx->threads = k; }
+    if (const char* v = getenv("EB200_DECIDERS")) { int k = atoi(v); if (k >= 1 && k <= 32) ctx->deciders = k; }
+    if (ctx->deciders > ctx->threads / 32) ctx->deciders = ctx->threads / 32;
+    if (cudaFuncSetAttribute(eb_case_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)case_smem(32)) != cudaSuccess ||
+        cudaFuncSetAttribute(eb_case_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)case_smem(32)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
     *out = ctx; return EB200_OK;
 }
 
 void eb200_shutdown(eb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->slot_off, &ctx->temp, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta}) b->release();
+    for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->slot_off, &ctx->temp, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta, &ctx->case_status, &ctx->retry_list}) b->release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_h2d) { cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h); cudaStreamDestroy(ctx->s_comp); }
     delete ctx;
 }
 
-// decide + scan for a batch resident on the device. On return *total_out = packed output size.
+// arenas + launch geometry shared by both modes
+struct LaunchPlan { Arenas ar; int grid; };
+static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_bytes, uint64_t n_launch, LaunchPlan& lp) {
+    unsigned long long* cnt = (unsigned long long*)ctx->counters.p;
+    Arenas& ar = lp.ar;
+    ar.scratch = (uint8_t*)ctx->scratch.p; ar.scratch_cap = ctx->scratch.cap - 64;
+    ar.scratch_used = cnt + CNT_SCRATCH;
+    ar.segs = (Seg*)ctx->segs.p; ar.segs_cap = ctx->segs.cap / sizeof(Seg); ar.segs_used = cnt + CNT_SEGS;
+    ar.overflow = (uint32_t*)(cnt + CNT_OVERFLOW);
+    ar.flagged = cnt + CNT_FLAGGED;
+    ar.case_status = (uint8_t*)ctx->case_status.p;
+    uint64_t want_ctas = (n_launch + ctx->deciders - 1) / ctx->deciders;
+    lp.grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms);
+    if (lp.grid < 1) lp.grid = 1;
+    ar.temp = nullptr; ar.temp_per_warp = 0;
+    bool needs_temp = false;
+    for (int i = 0; i < bp.n_rows; i++) needs_temp |= mut_needs_temp(bp.row_id[i]);
+    for (int i = 0; i < bp.n_pats; i++) needs_temp |= bp.pat_pri[i] > 0 && (bp.pat_id[i] == P_SK || bp.pat_id[i] == P_SZ || bp.pat_id[i] == P_CS);
+    if (needs_temp) {   // parse tables are proportional to the block being mutated: size the per-warp region from the mean blob
+        uint64_t mean = bp.n_blobs ? data_bytes / bp.n_blobs : 0;
+        uint64_t per = std::min<uint64_t>(std::max<uint64_t>(64 * mean, 256u << 10), 16u << 20);
+        per = (per + 255) & ~255ull;
+        uint64_t nw = (uint64_t)ctx->num_sms * ctx->deciders;
+        while (per > (256u << 10) && per * nw > (48ull << 30)) per >>= 1;
+        CK(ctx->temp.ensure(per * nw + 256));
+        ar.temp = (uint8_t*)ctx->temp.p; ar.temp_per_warp = per;
+    }
+    return EB200_OK;
+}
+static void launch_cases(eb200_ctx* ctx, const BatchParams& bp, const LaunchPlan& lp, cudaStream_t st, const uint8_t* d_data, const uint64_t* d_off,
+                         uint64_t* d_out_len, eb200_meta* d_meta, const FusedArgs& fa) {
+    size_t sm = case_smem(ctx->deciders);
+    if (!batch_is_light(bp)) eb_case_kernel<true><<<lp.grid, ctx->threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
+    else eb_case_kernel<false><<<lp.grid, ctx->threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
+}
+
+// decide + scan for a batch resident on the device (two-pass mode). On return *total_out = packed output size.
 static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* opts, const uint8_t* d_data, const uint64_t* d_off,
                            uint64_t data_bytes, uint64_t* d_out_off, uint64_t* d_out_len, eb200_meta* d_meta, cudaStream_t st, uint64_t* total_out, uint32_t* launches) {
     uint64_t n = bp.n_cases;
     CK(ctx->cases.ensure(n * sizeof(CaseOut)));
     CK(ctx->sz16.ensure(n * 8));
+    CK(ctx->case_status.ensure(n + 64));
     uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     CK(ctx->tile_sum.ensure((ntiles + 1) * 8));
     CK(ctx->counters.ensure(64));
@@ -242,41 +265,20 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
     if (seg_cap < n * 6 + 1024) { CK(ctx->segs.ensure((n * 6 + 1024) * sizeof(Seg))); seg_cap = ctx->segs.cap / sizeof(Seg); }
     uint64_t scratch_want = opts->scratch_bytes ? opts->scratch_bytes : std::min<uint64_t>(4 * data_bytes + (64ull << 20), 8ull << 30);
     if (ctx->scratch.cap < scratch_want) CK(ctx->scratch.ensure(scratch_want));
+    // edit scripts published by this mode point into scratch, so an exhausted arena means running the batch again
     for (int attempt = 0;; attempt++) {
         CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
-        Arenas ar;
-        ar.scratch = (uint8_t*)ctx->scratch.p; ar.scratch_cap = ctx->scratch.cap - 64;
-        ar.scratch_used = (unsigned long long*)ctx->counters.p;
-        ar.segs = (Seg*)ctx->segs.p; ar.segs_cap = ctx->segs.cap / sizeof(Seg);
-        ar.segs_used = (unsigned long long*)ctx->counters.p + 1;
-        ar.overflow = (uint32_t*)((unsigned long long*)ctx->counters.p + 2);
-        ar.flagged = (unsigned long long*)ctx->counters.p + 4;
-        const DecideVariant& dv = decide_variants[ctx->decide_variant];
-        uint64_t want_ctas = (n + dv.warps - 1) / dv.warps;
-        int grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * dv.ctas_per_sm);
-        if (grid < 1) grid = 1;
-        ar.temp = nullptr; ar.temp_per_warp = 0;
-        bool needs_temp = false;
-        for (int i = 0; i < bp.n_rows; i++) needs_temp |= mut_needs_temp(bp.row_id[i]);
-        for (int i = 0; i < bp.n_pats; i++) needs_temp |= bp.pat_pri[i] > 0 && (bp.pat_id[i] == P_SK || bp.pat_id[i] == P_SZ || bp.pat_id[i] == P_CS);
-        if (needs_temp) {   // parse tables are proportional to the block being mutated: size the per-warp region from the mean blob
-            uint64_t mean = bp.n_blobs ? data_bytes / bp.n_blobs : 0;
-            uint64_t per = std::min<uint64_t>(std::max<uint64_t>(64 * mean, 256u << 10), 16u << 20);
-            per = (per + 255) & ~255ull;
-            uint64_t nw = (uint64_t)grid * dv.warps;
-            while (per > (256u << 10) && per * nw > (48ull << 30)) per >>= 1;
-            CK(ctx->temp.ensure(per * nw + 256));
-            ar.temp = (uint8_t*)ctx->temp.p; ar.temp_per_warp = per;
-        }
+        LaunchPlan lp; int rc = plan_launch(ctx, bp, data_bytes, n, lp); if (rc) return rc;
         CK(cudaEventRecord(ctx->ev[0], st));
         FusedArgs fa; memset(&fa, 0, sizeof(fa));
-        dv.launch(!batch_is_light(bp), grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
+        fa.case_counter = (unsigned long long*)ctx->counters.p + CNT_NEXT_CASE; fa.deciders = ctx->deciders;
+        launch_cases(ctx, bp, lp, st, d_data, d_off, d_out_len, d_meta, fa);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], st));
         (*launches)++;
         uint32_t ovf = 0;
-        CK(cudaMemcpyAsync(&ovf, ar.overflow, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ctx->flag_counts, ar.flagged, 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ovf, lp.ar.overflow, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->flag_counts, lp.ar.flagged, 24, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (!ovf) break;
         if (attempt >= 3) return EB200_ERR_SCRATCH;
@@ -294,13 +296,30 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
     return EB200_OK;
 }
 
+// grow a device buffer keeping its first `keep` bytes
+static cudaError_t grow_preserving(DevBuf& b, size_t want, size_t keep, cudaStream_t st) {
+    void* np = nullptr;
+    size_t cap = want + want / 8 + 256;
+    cudaError_t e = cudaMalloc(&np, cap);
+    if (e != cudaSuccess) return e;
+    if (keep) e = cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(np); return e; }
+    cudaFree(b.p); b.p = np; b.cap = cap;
+    return cudaSuccess;
+}
+
 // Single-pass mode: slot offsets from INPUT sizes (+ slack) first, then one kernel decides and writes every case.
 // own_out: the output arena is ctx->out (host paths) and may be grown; otherwise the caller's arena is used as is.
+// A case that finds the scratch arena or the overflow region exhausted flags ITSELF (status OVERFLOW, reason 1 / 11, its
+// input copied to its slot); the host then grows the arena and re-runs exactly those case numbers in a follow-up
+// launch -- the batch is never run twice.
 static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* opts, const uint8_t* d_data, const uint64_t* d_off, uint64_t data_bytes,
                      bool own_out, uint8_t* d_out, uint64_t out_capacity, uint64_t out_base, uint64_t* d_out_off, uint64_t* d_out_len, eb200_meta* d_meta,
                      cudaStream_t st, uint64_t* total_out, uint32_t* launches) {
     uint64_t n = bp.n_cases;
     CK(ctx->sz16.ensure(n * 8));
+    CK(ctx->case_status.ensure(n + 64));
     uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     CK(ctx->tile_sum.ensure((ntiles + 1) * 8));
     CK(ctx->slot_off.ensure((n + 1) * 8));
@@ -328,50 +347,58 @@ static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* op
         d_out = (uint8_t*)ctx->out.p + out_base; out_capacity = ctx->out.cap - out_base - 64;
     }
     if (slots > out_capacity) return EB200_ERR_NOMEM;
-    unsigned long long used[2] = {0, 0};
+    unsigned long long used[5] = {0, 0, 0, 0, 0};     // overflow bits, ovf_used, flagged[3]
+    unsigned long long* cnt = (unsigned long long*)ctx->counters.p;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    uint64_t n_retried = 0, n_list = 0;
+    std::vector<uint8_t> status_host;
+    std::vector<uint32_t> list_host;
     for (int attempt = 0;; attempt++) {
-        CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
-        Arenas ar;
-        ar.scratch = (uint8_t*)ctx->scratch.p; ar.scratch_cap = ctx->scratch.cap - 64;
-        ar.scratch_used = (unsigned long long*)ctx->counters.p;
-        ar.segs = (Seg*)ctx->segs.p; ar.segs_cap = 0; ar.segs_used = (unsigned long long*)ctx->counters.p + 1;
-        ar.overflow = (uint32_t*)((unsigned long long*)ctx->counters.p + 2);
-        ar.flagged = (unsigned long long*)ctx->counters.p + 4;
-        const DecideVariant& dv = decide_variants[ctx->decide_variant];
-        uint64_t want_ctas = (n + dv.warps - 1) / dv.warps;
-        int grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * dv.ctas_per_sm);
-        if (grid < 1) grid = 1;
-        ar.temp = nullptr; ar.temp_per_warp = 0;
-        bool needs_temp = false;
-        for (int i = 0; i < bp.n_rows; i++) needs_temp |= mut_needs_temp(bp.row_id[i]);
-        for (int i = 0; i < bp.n_pats; i++) needs_temp |= bp.pat_pri[i] > 0 && (bp.pat_id[i] == P_SK || bp.pat_id[i] == P_SZ || bp.pat_id[i] == P_CS);
-        if (needs_temp) {
-            uint64_t mean = bp.n_blobs ? data_bytes / bp.n_blobs : 0;
-            uint64_t per = std::min<uint64_t>(std::max<uint64_t>(64 * mean, 256u << 10), 16u << 20);
-            per = (per + 255) & ~255ull;
-            uint64_t nw = (uint64_t)grid * dv.warps;
-            while (per > (256u << 10) && per * nw > (48ull << 30)) per >>= 1;
-            CK(ctx->temp.ensure(per * nw + 256));
-            ar.temp = (uint8_t*)ctx->temp.p; ar.temp_per_warp = per;
-        }
-        FusedArgs fa; fa.fused = 1; fa.out = d_out; fa.out_capacity = out_capacity; fa.slot_off = (const uint64_t*)ctx->slot_off.p; fa.out_off = d_out_off;
-        fa.ovf_base = slots; fa.ovf_used = (unsigned long long*)ctx->counters.p + 3; fa.data_bytes = data_bytes;
-        CK(cudaEventRecord(ctx->ev[0], st));
-        dv.launch(!batch_is_light(bp), grid, st, d_data, d_off, bp, ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
+        LaunchPlan lp; int rc = plan_launch(ctx, bp, data_bytes, attempt ? n_list : n, lp); if (rc) return rc;
+        FusedArgs fa; memset(&fa, 0, sizeof(fa));
+        fa.fused = 1; fa.out = d_out; fa.out_capacity = out_capacity; fa.slot_off = (const uint64_t*)ctx->slot_off.p; fa.out_off = d_out_off;
+        fa.ovf_base = slots; fa.ovf_used = cnt + CNT_OVF_USED; fa.data_bytes = data_bytes;
+        fa.case_counter = cnt + CNT_NEXT_CASE; fa.deciders = ctx->deciders;
+        if (attempt) { fa.case_list = (const uint32_t*)ctx->retry_list.p; fa.n_list = n_list; }
+        if (attempt == 0) CK(cudaEventRecord(ctx->ev[0], st));
+        launch_cases(ctx, bp, lp, st, d_data, d_off, d_out_len, d_meta, fa);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[3], st));
         (*launches)++;
-        CK(cudaMemcpyAsync(used, (unsigned long long*)ctx->counters.p + 2, 16, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ctx->flag_counts, (unsigned long long*)ctx->counters.p + 4, 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(used, cnt + CNT_OVERFLOW, 40, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         uint32_t ovf = (uint32_t)used[0];
-        if (!(ovf & 1) && !((ovf & 4) && own_out && !out_base)) break;
-        if (attempt >= 3) { if (ovf & 1) return EB200_ERR_SCRATCH; break; }
-        if (ovf & 1) { size_t nw = ctx->scratch.cap * 2; CK(ctx->scratch.ensure(nw)); }
-        if ((ovf & 4) && own_out && !out_base) { CK(ctx->out.ensure(ctx->out.cap * 2)); d_out = (uint8_t*)ctx->out.p; out_capacity = ctx->out.cap - 64; }
+        bool need_scratch = (ovf & 1) != 0, need_out = (ovf & 4) && own_out && !out_base;
+        if ((!need_scratch && !need_out) || attempt >= 4 || n > 0xffffffffull) break;
+        // which cases ran out of arena space?
+        status_host.resize(n);
+        CK(cudaMemcpyAsync(status_host.data(), ctx->case_status.p, n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        list_host.clear();
+        for (uint64_t k = 0; k < n; k++) {
+            uint32_t stt = status_host[k] & 15u, reason = status_host[k] >> 4;
+            if (stt == CASE_OVERFLOW && ((reason == 1 && need_scratch) || (reason == 11 && need_out))) list_host.push_back((uint32_t)k);
+        }
+        if (list_host.empty()) break;
+        n_list = list_host.size(); n_retried += n_list;
+        CK(ctx->retry_list.ensure(n_list * 4));
+        CK(cudaMemcpyAsync(ctx->retry_list.p, list_host.data(), n_list * 4, cudaMemcpyHostToDevice, st));
+        if (need_scratch) { CK(cudaStreamSynchronize(st)); CK(ctx->scratch.ensure(ctx->scratch.cap * 2)); }
+        if (need_out) {
+            uint64_t keep = slots + used[1];
+            CK(grow_preserving(ctx->out, ctx->out.cap * 2, keep, st));
+            d_out = (uint8_t*)ctx->out.p; out_capacity = ctx->out.cap - 64;
+        }
+        // the follow-up launch starts with an empty scratch arena (finished cases have their bytes in `out` already),
+        // keeps the overflow region's fill level and the flag counters, and restarts the case counter
+        unsigned long long zero = 0; uint32_t zero32 = 0;
+        CK(cudaMemcpyAsync(cnt + CNT_SCRATCH, &zero, 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(cnt + CNT_OVERFLOW, &zero32, 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(cnt + CNT_NEXT_CASE, &zero, 8, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
     }
-    uint64_t ovf_used = std::min<uint64_t>(used[1], out_capacity - slots);
-    *total_out = slots + ovf_used;
+    ctx->flag_counts[0] = used[2]; ctx->flag_counts[1] = used[3]; ctx->flag_counts[2] = used[4] >= n_retried ? used[4] - n_retried : 0;
+    *total_out = slots + used[1];
     CK(cudaMemcpyAsync(d_out_off + n, total_out, 8, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     return EB200_OK;

@@ -1,0 +1,175 @@
+// erlamsa_b200 -- the CTA's job queue: DECIDER warps run the scalar per-case program and hand the bulk byte work
+// (streaming copies of >= 16 KiB, digit-run / newline counts over whole blocks) to WORKER warps of the same CTA.
+//
+// Why (profiles/fused_r1c.txt): with one warp doing everything for its case, (a) `num` read its block
+// twice from DRAM -- 300 MB of blocks in flight chip-wide never survive in the 126 MB L2 between the count and the copy;
+// (b) the copy of a case started only after its own decision, so a CTA-wide barrier per case was needed to keep the
+// big scalar program in the instruction cache, and the slowest case of each round set the pace (25 % barrier stalls).
+// With the split, a block's count and copy are executed by many warps within microseconds of each other (the second
+// read hits L2), the copy loop is a tiny program that never leaves the instruction cache, and cases are taken from a
+// global counter, so nobody waits for anybody else's case.
+//
+// The queue is a bounded multi-producer / multi-consumer ring in shared memory (one sequence word per cell: free for
+// position p when seq == p, ready when seq == p + 1). Producers and consumers claim positions with one shared-memory
+// atomic; workers never wait for anything but the publication of a claimed cell, so the ring cannot deadlock.
+#pragma once
+#include "eb_warp.cuh"
+
+namespace eb {
+
+constexpr uint32_t QCAP = 256;          // cells in the ring
+constexpr uint32_t JOB_TILE = 8192;     // bytes per copy job (two 4 KiB register tiles)
+constexpr uint32_t JOB_MIN_COPY = 16384; // shorter copies are executed inline by the deciding warp
+constexpr uint32_t JOB_MIN_SCAN = 16384; // shorter scans likewise
+
+enum JobKind : uint32_t { JOB_COPY_NC = 0, JOB_COPY = 1, JOB_COUNT_DIGIT = 2, JOB_COUNT_NL = 3 };
+
+struct __align__(16) Job {
+    uint64_t a;       // copy: destination | count: aligned base of the scanned block
+    uint64_t b;       // copy: source      | count: (lead << 32) | span of the scan cursor
+    uint32_t len;     // copy: bytes       | count: superchunk index
+    uint32_t kind;
+    uint32_t res;     // count: shared-window address of the uint16 result slot
+    uint32_t pend;    // count: shared-window address of the poster's pending counter
+};
+
+struct JobQ {
+    Job jobs[QCAP];
+    uint32_t seq[QCAP];
+    unsigned int head, tail;
+    uint32_t closed;
+    unsigned int deciders_left;
+};
+
+__device__ __forceinline__ uint32_t ld_shared_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+
+__device__ __forceinline__ void jobq_init(JobQ* q, int deciders) {
+    for (uint32_t i = threadIdx.x; i < QCAP; i += blockDim.x) q->seq[i] = i;
+    if (threadIdx.x == 0) { q->head = 0; q->tail = 0; q->closed = 0; q->deciders_left = (unsigned)deciders; }
+}
+// claim `cnt` consecutive positions (warp-collective); every lane gets the first one
+__device__ __forceinline__ uint32_t jobq_claim(JobQ* q, uint32_t cnt) {
+    uint32_t pos = 0;
+    if (lane_id() == 0) pos = atomicAdd(&q->tail, cnt);
+    return __shfl_sync(0xffffffffu, pos, 0);
+}
+// publish one job at a claimed position (any single lane)
+__device__ __forceinline__ void jobq_put(JobQ* q, uint32_t pos, const Job& j) {
+    uint32_t cell = pos % QCAP;
+    while (ld_shared_volatile(&q->seq[cell]) != pos) __nanosleep(100);
+    q->jobs[cell] = j;
+    __threadfence_block();
+    *(volatile uint32_t*)&q->seq[cell] = pos + 1;
+}
+// take the next job (warp-collective); false when the queue is closed and drained
+__device__ __forceinline__ bool jobq_get(JobQ* q, Job& j) {
+    uint32_t pos = 0;
+    if (lane_id() == 0) pos = atomicAdd(&q->head, 1u);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    uint32_t cell = pos % QCAP;
+    int ok = 1;
+    if (lane_id() == 0) {
+        while (ld_shared_volatile(&q->seq[cell]) != pos + 1) {
+            if (ld_shared_volatile(&q->closed) && (int32_t)(pos - *(volatile unsigned int*)&q->tail) >= 0) { ok = 0; break; }
+            __nanosleep(200);
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) return false;
+    __threadfence_block();
+    j = q->jobs[cell];
+    __syncwarp();
+    if (lane_id() == 0) *(volatile uint32_t*)&q->seq[cell] = pos + QCAP;
+    return true;
+}
+// a decider is done with its last case
+__device__ __forceinline__ void jobq_decider_done(JobQ* q) {
+    __syncwarp();
+    if (lane_id() == 0) {
+        __threadfence_block();
+        if (atomicSub(&q->deciders_left, 1u) == 1u) { __threadfence_block(); *(volatile uint32_t*)&q->closed = 1u; }
+    }
+}
+
+template <int PRED, bool RUNSTART>
+__device__ __forceinline__ void job_count(const Job& j) {
+    ScanCursor c; c.base = (const uint8_t*)(uintptr_t)j.a; c.lead = (uint32_t)(j.b >> 32); c.span = (uint32_t)j.b; c.n = c.span - c.lead;
+    uint32_t carry = RUNSTART ? scan_carry_in<PRED>(c, j.len) : 0;
+    uint32_t s = scan_count_sc<PRED, RUNSTART>(c, j.len * 8u, carry);
+    if (lane_id() == 0) {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(j.res), "h"((unsigned short)s) : "memory");
+        __threadfence_block();
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(j.pend), "r"(0xffffffffu) : "memory");
+    }
+}
+
+// the worker warps' whole program
+__device__ __noinline__ void worker_loop(JobQ* q) {
+    Job j;
+    while (jobq_get(q, j)) {
+        switch (j.kind) {
+        case JOB_COPY_NC: warp_copy_stream<true>((uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); break;
+        case JOB_COPY: warp_copy_stream<false>((uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); break;
+        case JOB_COUNT_DIGIT: job_count<PRED_DIGIT, true>(j); break;
+        default: job_count<PRED_NEWLINE, false>(j); break;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- decider side
+// stream n bytes src -> dst: inline when short or when the kernel runs without workers, else as tile jobs whose
+// destinations (after the first) start on 16-byte boundaries
+__device__ __noinline__ void post_copy(JobQ* q, uint8_t* dst, const uint8_t* src, uint64_t n, bool nc) {
+    if (!q || n < JOB_MIN_COPY) {
+        if (nc) warp_copy_stream<true>(dst, src, n); else warp_copy_stream<false>(dst, src, n);
+        return;
+    }
+    uint64_t b1 = JOB_TILE + ((16 - ((uintptr_t)dst & 15u)) & 15u);
+    uint64_t ntiles = 1 + (n - b1 + JOB_TILE - 1) / JOB_TILE;
+    for (uint64_t base = 0; base < ntiles; base += 32) {
+        uint32_t cnt = (uint32_t)(ntiles - base < 32 ? ntiles - base : 32);
+        uint32_t pos0 = jobq_claim(q, cnt);
+        uint32_t l = (uint32_t)lane_id();
+        if (l < cnt) {
+            uint64_t t = base + l;
+            uint64_t s = t == 0 ? 0 : b1 + (t - 1) * JOB_TILE;
+            uint64_t e = b1 + t * JOB_TILE; if (e > n) e = n;
+            Job j; j.a = (uint64_t)(uintptr_t)(dst + s); j.b = (uint64_t)(uintptr_t)(src + s); j.len = (uint32_t)(e - s); j.kind = nc ? JOB_COPY_NC : JOB_COPY; j.res = 0; j.pend = 0;
+            jobq_put(q, pos0 + l, j);
+        }
+        __syncwarp();
+    }
+}
+
+// scan_count through the workers: one job per 4 KiB superchunk, results land in sc[] (shared memory), the poster
+// waits on a countdown word next to them
+template <int PRED, bool RUNSTART>
+__device__ __noinline__ uint32_t scan_count_jobs(JobQ* q, const uint8_t* p, uint32_t n, uint16_t* sc, uint32_t* pend) {
+    if (!q || n < JOB_MIN_SCAN) return scan_count<PRED, RUNSTART>(p, n, sc);
+    ScanCursor c = scan_cursor(p, n);
+    uint32_t nsc = (c.span + 4095u) >> 12;
+    if (lane_id() == 0) *(volatile uint32_t*)pend = nsc;
+    __syncwarp();
+    __threadfence_block();
+    uint32_t pend_sa = (uint32_t)__cvta_generic_to_shared(pend), sc_sa = (uint32_t)__cvta_generic_to_shared(sc);
+    for (uint32_t base = 0; base < nsc; base += 32) {
+        uint32_t cnt = nsc - base < 32 ? nsc - base : 32;
+        uint32_t pos0 = jobq_claim(q, cnt);
+        uint32_t l = (uint32_t)lane_id();
+        if (l < cnt) {
+            Job j; j.a = (uint64_t)(uintptr_t)c.base; j.b = ((uint64_t)c.lead << 32) | c.span; j.len = base + l;
+            j.kind = PRED == PRED_DIGIT ? JOB_COUNT_DIGIT : JOB_COUNT_NL; j.res = sc_sa + 2u * (base + l); j.pend = pend_sa;
+            jobq_put(q, pos0 + l, j);
+        }
+        __syncwarp();
+    }
+    if (lane_id() == 0) while (ld_shared_volatile(pend) != 0) __nanosleep(200);
+    __syncwarp();
+    __threadfence_block();
+    uint32_t acc = 0;
+    for (uint32_t i = lane_id(); i < nsc; i += 32) acc += ((volatile uint16_t*)sc)[i];
+    return warp_sum(acc);
+}
+
+}  // namespace eb

@@ -162,7 +162,7 @@ EB_DEV void mut_num(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     r.rechunk = 1; r.consumed_next = 0;
     // numbers = maximal digit runs (get_num/4 :114-124 swallows the '-' run right before one)
-    uint32_t nfound = scan_count<PRED_DIGIT, true>(p, n, ws->sc);
+    uint32_t nfound = scan_count_jobs<PRED_DIGIT, true>(c.q, p, n, ws->sc, &ws->qpend);
     uint64_t which = g.rand(nfound);
     t_reset(ws);
     if (nfound == 0) {
@@ -201,7 +201,7 @@ EB_DEV uint32_t line_end(const LineTab& t, uint32_t i) { return i < t.nl ? scan_
 EB_DEV bool try_lines(CaseCtx& c, const uint8_t* p, uint32_t n, LineTab& t) {   // :341-348
     if (n == 0) return false;
     t.p = p; t.n = n; t.sc = c.ws->sc;
-    t.nl = scan_count<PRED_NEWLINE, false>(p, n, c.ws->sc);
+    t.nl = scan_count_jobs<PRED_NEWLINE, false>(c.q, p, n, c.ws->sc, &c.ws->qpend);
     t.nlines = t.nl + (p[n - 1] != 10 ? 1u : 0u);
     if (mem_binarish(p, n)) return false;
     return true;

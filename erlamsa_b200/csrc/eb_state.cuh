@@ -10,6 +10,7 @@
 #pragma once
 #include "eb_common.cuh"
 #include "eb_warp.cuh"
+#include "eb_jobs.cuh"
 #include "eb_rng.cuh"
 
 namespace eb {
@@ -48,6 +49,7 @@ struct WarpState {
     int nwrap;
     const uint8_t* fo_p; uint32_t fo_n; int fo_has;
     uint16_t sc[SC_MAX];
+    uint32_t qpend;          // countdown of this warp's outstanding scan jobs (eb_jobs.cuh)
     uint32_t status; uint32_t reason;
     int n_used, n_failed; int used[16];
 };
@@ -62,6 +64,7 @@ struct CaseCtx {
     uint64_t temp_used;
     uint64_t temp_floor;     // temp_reset() rewinds to here: a mutator that runs a nested scheduler parks its own tables below
     int snand_kind;          // mask function bound to `snand` when the current table was built (mutations/1 :1313)
+    JobQ* q;                 // the CTA's job queue (nullptr: no worker warps, everything inline)
 };
 
 // ------------------------------------------------------------------ arenas
@@ -177,18 +180,25 @@ EB_DEV void segs_write(const Seg* s, int n, uint8_t* dst) {
 
 // single-pass mode: execute a script into its output slot with streaming copies; sources inside the (read-only)
 // corpus [ro_lo, ro_hi) take the non-coherent load path, scratch written by this kernel takes plain loads
-EB_DEV void segs_write_stream(const Seg* s, int n, uint8_t* dst, const uint8_t* ro_lo, const uint8_t* ro_hi) {
+EB_DEV void segs_write_stream(JobQ* q, const Seg* s, int n, uint8_t* dst, const uint8_t* ro_lo, const uint8_t* ro_hi) {
     int l = lane_id();
     for (int k = 0; k < n; k++) {
         uint32_t sl = s[k].len;
         switch (s[k].kind()) {
         case SEG_COPY: {
             const uint8_t* src = (const uint8_t*)(uintptr_t)s[k].src;
-            if (src >= ro_lo && src + sl <= ro_hi) warp_copy_stream<true>(dst, src, sl); else warp_copy_stream<false>(dst, src, sl);
+            post_copy(q, dst, src, sl, src >= ro_lo && src + sl <= ro_hi);
             break;
         }
         case SEG_INLINE: if ((uint32_t)l < sl) dst[l] = (uint8_t)(s[k].src >> (8 * l)); break;
-        case SEG_REPEAT: { const uint8_t* src = (const uint8_t*)(uintptr_t)s[k].src; uint32_t u = s[k].arg(); for (uint32_t i = l; i < sl; i += 32) dst[i] = src[i % u]; break; }
+        case SEG_REPEAT: {
+            const uint8_t* src = (const uint8_t*)(uintptr_t)s[k].src; uint32_t u = s[k].arg();
+            if (u >= 512) {   // long unit: every repetition is a streaming copy of its own
+                bool nc = src >= ro_lo && src + u <= ro_hi;
+                for (uint32_t o = 0; o < sl; o += u) post_copy(q, dst + o, src, sl - o < u ? sl - o : u, nc);
+            } else for (uint32_t i = l; i < sl; i += 32) dst[i] = src[i % u];
+            break;
+        }
         default: warp_fill(dst, (uint8_t)s[k].arg(), sl);
         }
         dst += sl;

@@ -233,37 +233,56 @@ __device__ __forceinline__ uint32_t scan_chunk_mask(const ScanCursor& c, uint32_
 // One superchunk = 8 warp chunks: all 8 loads are issued before the first is consumed, so a warp
 // keeps 4 KiB in flight instead of serialising on DRAM latency (profiles/decide_r1a: 27% of the
 // decide kernel's stall samples sat on the first use of a single in-flight load).
+// matches inside ONE superchunk (warp chunks it0 .. it0+7); `carry` = "the byte before this superchunk matches"
+// on entry, the same for the next superchunk on return. Returns the warp-wide count (same value in every lane).
+template <int PRED, bool RUNSTART>
+__device__ __forceinline__ uint32_t scan_count_sc(const ScanCursor& c, uint32_t it0, uint32_t& carry) {
+    uint4 w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) w[j] = scan_chunk_load(c, it0 + j);
+    uint32_t acc = 0;
+    if (it0 * 512u >= c.lead && (it0 + 8) * 512u <= c.span) {
+        // interior superchunk: every byte is valid, so count straight on the bit-7 byte flags
+        // (no validity masks, no packing): ~33 integer ops per 16-byte word instead of ~70
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t f0 = pred_flags<PRED>(w[j].x), f1 = pred_flags<PRED>(w[j].y), f2 = pred_flags<PRED>(w[j].z), f3 = pred_flags<PRED>(w[j].w);
+            if (RUNSTART) {
+                uint32_t top = f3 >> 24;                                  // last byte's flag, moved to bit 7
+                uint32_t prev = __shfl_up_sync(0xffffffffu, top, 1);
+                if (lane_id() == 0) prev = carry << 7;
+                carry = __shfl_sync(0xffffffffu, top, 31) >> 7;
+                uint32_t s0 = f0 & ~((f0 << 8) | prev), s1 = f1 & ~((f1 << 8) | (f0 >> 24)), s2 = f2 & ~((f2 << 8) | (f1 >> 24)), s3 = f3 & ~((f3 << 8) | (f2 >> 24));
+                acc += __popc((s0 >> 7) | (s1 >> 6) | (s2 >> 5) | (s3 >> 4));
+            } else {
+                acc += __popc((f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += __popc(scan_chunk_reduce<PRED, RUNSTART>(c, it0 + j, w[j], carry));
+    }
+    return warp_sum(acc);
+}
+// carry-in of superchunk s > 0 computed from the data alone: is the last byte before it a (valid) match?
+template <int PRED>
+__device__ __forceinline__ uint32_t scan_carry_in(const ScanCursor& c, uint32_t s) {
+    if (s == 0) return 0;
+    uint32_t wofs = s * 4096u - 16u;
+    uint32_t m = 0;
+    if (wofs + 16 > c.lead && wofs < c.span) { uint4 w = ldg16(c.base + wofs); m = pred_mask16<PRED>(w); if (wofs < c.lead) m &= 0xffffu << (c.lead - wofs); if (wofs + 16 > c.span) m &= 0xffffu >> (wofs + 16 - c.span); }
+    return m >> 15;
+}
+// count matches; sc[k] receives the count inside superchunk k (4 KiB of aligned coordinates).
+// One superchunk = 8 warp chunks: all 8 loads are issued before the first is consumed, so a warp
+// keeps 4 KiB in flight instead of serialising on DRAM latency (profiles/decide_r1a: 27% of the
+// decide kernel's stall samples sat on the first use of a single in-flight load).
 template <int PRED, bool RUNSTART>
 __device__ __noinline__ uint32_t scan_count(const uint8_t* p, uint32_t n, uint16_t* sc) {
     ScanCursor c = scan_cursor(p, n);
     uint32_t iters = (c.span + 511) >> 9, carry = 0, total = 0;
     for (uint32_t it0 = 0; it0 < iters; it0 += 8) {
-        uint4 w[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) w[j] = scan_chunk_load(c, it0 + j);
-        uint32_t acc = 0;
-        if (it0 * 512u >= c.lead && (it0 + 8) * 512u <= c.span) {
-            // interior superchunk: every byte is valid, so count straight on the bit-7 byte flags
-            // (no validity masks, no packing): ~33 integer ops per 16-byte word instead of ~70
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                uint32_t f0 = pred_flags<PRED>(w[j].x), f1 = pred_flags<PRED>(w[j].y), f2 = pred_flags<PRED>(w[j].z), f3 = pred_flags<PRED>(w[j].w);
-                if (RUNSTART) {
-                    uint32_t top = f3 >> 24;                                  // last byte's flag, moved to bit 7
-                    uint32_t prev = __shfl_up_sync(0xffffffffu, top, 1);
-                    if (lane_id() == 0) prev = carry << 7;
-                    carry = __shfl_sync(0xffffffffu, top, 31) >> 7;
-                    uint32_t s0 = f0 & ~((f0 << 8) | prev), s1 = f1 & ~((f1 << 8) | (f0 >> 24)), s2 = f2 & ~((f2 << 8) | (f1 >> 24)), s3 = f3 & ~((f3 << 8) | (f2 >> 24));
-                    acc += __popc((s0 >> 7) | (s1 >> 6) | (s2 >> 5) | (s3 >> 4));
-                } else {
-                    acc += __popc((f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4));
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) acc += __popc(scan_chunk_reduce<PRED, RUNSTART>(c, it0 + j, w[j], carry));
-        }
-        uint32_t s = warp_sum(acc); total += s;
+        uint32_t s = scan_count_sc<PRED, RUNSTART>(c, it0, carry); total += s;
         if (lane_id() == 0) sc[it0 >> 3] = (uint16_t)s;
     }
     __syncwarp();

@@ -1,5 +1,7 @@
-"""A/B timing of engine build variants on the C3 workload (not a test; run on the GPU box).
-usage: python tests/perf_variants.py [n_variants] [cases]"""
+"""A/B timing of engine configurations on the C3 workload (not a test; run on the GPU box).
+usage: python tests/perf_variants.py "deciders:threads,deciders:threads,..." [cases]
+Every configuration is (EB200_DECIDERS, EB200_THREADS) of eb_case_kernel: how many of the CTA's warps decide cases, the
+rest being copy/scan workers (deciders == threads/32 is the round-1 arrangement: every warp does its own byte work)."""
 import os
 import sys
 
@@ -7,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 import erlamsa_b200  # noqa: E402
 
-nvar = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+configs = [tuple(int(x) for x in c.split(":")) for c in (sys.argv[1] if len(sys.argv) > 1 else "8:1024,12:1024,16:1024,32:1024").split(",")]
 n_cases = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
 size = 65536
 dev = torch.device("cuda", 0)
@@ -18,22 +20,21 @@ out_cap = n_cases * size + n_cases * size // 12 + 512 * n_cases + (256 << 20)
 d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
 d_off = torch.empty(n_cases + 1, dtype=torch.int64, device=dev)
 d_len = torch.empty(n_cases, dtype=torch.int64, device=dev)
-muts = {c: 1 for c in ("bd", "bei", "bed", "bf", "bi", "ber", "br", "num")}
-ndec = int(sys.argv[3]) if len(sys.argv) > 3 else 6
-for v in range(nvar + ndec):
-    os.environ["EB200_APPLY_VARIANT"] = str(v if v < nvar else 0)
-    os.environ["EB200_DECIDE_VARIANT"] = str(0 if v < nvar else v - nvar)
+muts = {c: 1 for c in os.environ.get("PERF_MUTS", "bd,bei,bed,bf,bi,ber,br,num").split(",")}
+for dec, thr in configs:
+    os.environ["EB200_DECIDERS"] = str(dec)
+    os.environ["EB200_THREADS"] = str(thr)
     eng = erlamsa_b200.Engine(0)
     res = []
-    for i in range(int(os.environ.get("PERF_ITERS", "6"))):
+    for i in range(int(os.environ.get("PERF_ITERS", "7"))):
         st = eng.fuzz_batch_device({"mutations": muts, "patterns": {"od": 1}, "seed": (1, 2, 3), "first_case": 1 + i * n_cases, "scratch_bytes": 256 << 20},
                                    data.data_ptr(), off.data_ptr(), n_cases, n_cases * size, n_cases, d_out.data_ptr(), out_cap, d_off.data_ptr(),
                                    d_len.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
         res.append((st.ms_decide, st.ms_scan, st.ms_apply, st.ms_total))
-    if os.environ.get("PERF_ITERS"):
-        print("per-step decide ms:", " ".join("%.3f" % r[0] for r in res), flush=True)
+    print("per-step kernel ms:", " ".join("%.3f" % r[0] for r in res), flush=True)
     res = res[2:]
     avg = [sum(r[k] for r in res) / len(res) for k in range(4)]
     gbs = (2 * n_cases * size) / ((avg[2] or avg[0]) * 1e-3) / 1e9
-    print("variant %d: decide %.3f  scan %.3f  apply %.3f ms (%.0f GB/s)  total %.3f" % (v, avg[0], avg[1], avg[2], gbs, avg[3]), flush=True)
+    print("deciders %d threads %d: kernel %.3f  scan %.3f  apply %.3f ms (%.0f GB/s = %.2f of 6572)  total %.3f  launches %d"
+          % (dec, thr, avg[0], avg[1], avg[2], gbs, gbs / 6572.2, avg[3], st.kernels_launched), flush=True)
     eng.close()
