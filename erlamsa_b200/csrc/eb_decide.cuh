@@ -409,7 +409,7 @@ struct DecideArgs {
 // case_list: a follow-up launch over the cases a previous launch had to flag for lack of arena space re-runs exactly
 // those case numbers (same seeds, same slots; what outgrows the slot goes to the overflow region as before)
 struct FusedArgs { int fused; uint8_t* out; uint64_t out_capacity; const uint64_t* slot_off; uint64_t* out_off; uint64_t ovf_base; unsigned long long* ovf_used; uint64_t data_bytes;
-                   const uint32_t* case_list; uint64_t n_list; unsigned long long* case_counter; int deciders; };
+                   const uint32_t* case_list; uint64_t n_list; unsigned long long* case_counter; int deciders; int fronts; int front_depth; };
 
 // slot sizes for the single-pass mode: input length + slack, 16-byte aligned (the common mutations change a
 // case by a few bytes; anything bigger spills to the overflow region)
@@ -421,6 +421,9 @@ __global__ void __launch_bounds__(256) eb_slot_sizes(const uint64_t* __restrict_
     uint64_t slack = len / 16; if (slack < 256) slack = 256; if (slack > 65536) slack = 65536;
     sz16[k] = align16(len + slack);
 }
+
+constexpr int CASE_THREADS = 1024;
+constexpr int PW_BITS = 48;
 
 // one test case, start to finish, decided by one warp (bulk byte work goes to the CTA's workers through q)
 template <bool FULL>
@@ -509,58 +512,6 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         }
         __syncwarp();
     }
-}
-
-// The engine's one kernel: a persistent CTA per SM whose first `deciders` warps each take whole test cases from a global
-// counter and run the scalar per-case program; the remaining warps are workers that execute the bulk copies and block
-// scans the deciders post to the CTA's job queue (eb_jobs.cuh). deciders == all warps gives the round-1 arrangement
-// (every warp does its own byte work inline) for A/B runs. FULL / LIGHT: see mut_is_light().
-constexpr int CASE_THREADS = 1024;
-constexpr int PW_BITS = 48;
-template <bool FULL>
-__global__ void __launch_bounds__(CASE_THREADS, 1)
-eb_case_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ off, BatchParams bp, Arenas ar,
-               CaseOut* __restrict__ cases, uint64_t* __restrict__ out_len, uint64_t* __restrict__ out_sz16, MetaDev* __restrict__ meta, FusedArgs fa) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int nwarps = (int)(blockDim.x >> 5), warp = (int)(threadIdx.x >> 5);
-    const int deciders = fa.deciders < nwarps ? fa.deciders : nwarps;
-    JobQ* q = reinterpret_cast<JobQ*>(smem_raw);
-    uint32_t* pw = reinterpret_cast<uint32_t*>(smem_raw + sizeof(JobQ));                 // [3][PW_BITS]: a^(3 * 2^j) mod p
-    WarpState* wsbase = reinterpret_cast<WarpState*>(smem_raw + ((sizeof(JobQ) + 3 * PW_BITS * 4 + 15) & ~(size_t)15));
-    jobq_init(q, deciders);
-    if (threadIdx.x < 3 * PW_BITS) {
-        int comp = threadIdx.x / PW_BITS, j = threadIdx.x % PW_BITS;
-        uint32_t m = comp == 0 ? 30269u : comp == 1 ? 30307u : 30323u, a0 = comp == 0 ? AS_M1 : comp == 1 ? AS_M2 : AS_M3;
-        uint32_t v = (a0 * a0 % m) * a0 % m;
-        for (int i = 0; i < j; i++) v = v * v % m;
-        pw[threadIdx.x] = v;
-    }
-    __syncthreads();
-    if (warp >= deciders) { worker_loop(q); return; }
-    JobQ* qq = deciders < nwarps ? q : nullptr;
-    WarpState* ws = wsbase + warp;
-    DecideArgs a; a.data = data; a.off = off; a.ar = ar; a.cases = cases; a.out_len = out_len; a.out_sz16 = out_sz16; a.meta = meta;
-    a.fused = fa.fused; a.out = fa.out; a.out_capacity = fa.out_capacity; a.slot_off = fa.slot_off; a.out_off = fa.out_off;
-    a.ovf_base = fa.ovf_base; a.ovf_used = fa.ovf_used; a.data_bytes = fa.data_bytes;
-    const uint64_t total = fa.case_list ? fa.n_list : bp.n_cases;
-    const uint32_t temp_slot = blockIdx.x * (uint32_t)deciders + (uint32_t)warp;
-    for (;;) {
-        unsigned long long idx = 0;
-        if (lane_id() == 0) idx = atomicAdd(fa.case_counter, 1ull);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= total) break;
-        uint64_t k = fa.case_list ? (uint64_t)fa.case_list[idx] : (uint64_t)idx;
-        // parent stream at case k: x0 * (a^3)^(first_case - 1 + k) mod p per AS183 component, from the power table
-        uint64_t e = bp.first_case - 1 + k;
-        uint32_t a1 = (uint32_t)bp.parent_a1, a2 = (uint32_t)bp.parent_a2, a3 = (uint32_t)bp.parent_a3;
-        for (int j = 0; e && j < PW_BITS; j++, e >>= 1) if (e & 1) { a1 = a1 * pw[j] % 30269u; a2 = a2 * pw[PW_BITS + j] % 30307u; a3 = a3 * pw[2 * PW_BITS + j] % 30323u; }
-        if (e) {   // beyond 2^48 cases: finish with the generic jump
-            Rng t; t.mode = 0; t.a1 = (int32_t)a1; t.a2 = (int32_t)a2; t.a3 = (int32_t)a3; t.draws = 0; t.key = 0; t.ctr_hi = 0; t.jump(3 * (e << PW_BITS));
-            a1 = (uint32_t)t.a1; a2 = (uint32_t)t.a2; a3 = (uint32_t)t.a3;
-        }
-        decide_one_case<FULL>(ws, bp, a, k, (int32_t)a1, (int32_t)a2, (int32_t)a3, qq, temp_slot);
-    }
-    if (qq) jobq_decider_done(q);
 }
 
 }  // namespace eb

@@ -15,7 +15,7 @@
 #include <cmath>
 #include <chrono>
 #include "../../include/erlamsa_b200.h"
-#include "eb_decide.cuh"
+#include "eb_fast.cuh"
 #include "eb_apply.cuh"
 #include "eb_erlsort.hpp"
 
@@ -56,7 +56,9 @@ struct eb200_ctx {
     bool funny_loaded = false;
     int apply_variant = 0;
     int threads = CASE_THREADS;   // eb_case_kernel: threads per CTA (EB200_THREADS) ...
-    int deciders = 12;            // ... of which this many warps decide cases and the rest are copy/scan workers (EB200_DECIDERS)
+    int deciders = 12;            // ... of which this many warps run the general per-case program (EB200_DECIDERS),
+    int front_depth = 8;          // fronts post while fewer than this many jobs are waiting in the ring (EB200_FRONT_DEPTH)
+    int fronts = 1;               // this many decide 32 byte-mutator cases at a time, lane per case (EB200_FRONTS), the rest are copy/scan workers
     DevBuf case_status, retry_list;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // host-path pipeline (created on first use)
 };
@@ -84,7 +86,7 @@ static bool batch_is_light(const BatchParams& bp) {
     return true;
 }
 // shared memory of eb_case_kernel: job queue + parent-stream power table + one WarpState per deciding warp
-static size_t case_smem(int deciders) { return ((sizeof(JobQ) + 3 * PW_BITS * 4 + 15) & ~(size_t)15) + sizeof(WarpState) * (size_t)deciders; }
+static size_t case_smem(int deciders) { return case_smem_layout(deciders, nullptr, nullptr, nullptr); }
 // counters block (device, 8 x u64): [0] scratch_used [1] segs_used [2] overflow bits [3] ovf_used [4..6] flagged [7] next case
 enum { CNT_SCRATCH = 0, CNT_SEGS = 1, CNT_OVERFLOW = 2, CNT_OVF_USED = 3, CNT_FLAGGED = 4, CNT_NEXT_CASE = 7 };
 
@@ -200,6 +202,8 @@ int eb200_init(int device, eb200_ctx** out) {
     if (const char* v = getenv("EB200_MODE")) ctx->fused = strcmp(v, "twopass") != 0;
     if (const char* v = getenv("EB200_THREADS")) { int k = atoi(v); if (k >= 64 && k <= CASE_THREADS && k % 32 == 0) ctx->threads = k; }
     if (const char* v = getenv("EB200_DECIDERS")) { int k = atoi(v); if (k >= 1 && k <= 32) ctx->deciders = k; }
+    if (const char* v = getenv("EB200_FRONT_DEPTH")) { int k = atoi(v); if (k >= 0 && k <= 200) ctx->front_depth = k; }
+    if (const char* v = getenv("EB200_FRONTS")) { int k = atoi(v); if (k >= 0 && k <= MAX_FRONTS) ctx->fronts = k; }
     if (ctx->deciders > ctx->threads / 32) ctx->deciders = ctx->threads / 32;
     if (cudaFuncSetAttribute(eb_case_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)case_smem(32)) != cudaSuccess ||
         cudaFuncSetAttribute(eb_case_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)case_smem(32)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
@@ -271,7 +275,7 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
         LaunchPlan lp; int rc = plan_launch(ctx, bp, data_bytes, n, lp); if (rc) return rc;
         CK(cudaEventRecord(ctx->ev[0], st));
         FusedArgs fa; memset(&fa, 0, sizeof(fa));
-        fa.case_counter = (unsigned long long*)ctx->counters.p + CNT_NEXT_CASE; fa.deciders = ctx->deciders;
+        fa.case_counter = (unsigned long long*)ctx->counters.p + CNT_NEXT_CASE; fa.deciders = ctx->deciders; fa.fronts = 0;
         launch_cases(ctx, bp, lp, st, d_data, d_off, d_out_len, d_meta, fa);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], st));
@@ -358,7 +362,7 @@ static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* op
         FusedArgs fa; memset(&fa, 0, sizeof(fa));
         fa.fused = 1; fa.out = d_out; fa.out_capacity = out_capacity; fa.slot_off = (const uint64_t*)ctx->slot_off.p; fa.out_off = d_out_off;
         fa.ovf_base = slots; fa.ovf_used = cnt + CNT_OVF_USED; fa.data_bytes = data_bytes;
-        fa.case_counter = cnt + CNT_NEXT_CASE; fa.deciders = ctx->deciders;
+        fa.case_counter = cnt + CNT_NEXT_CASE; fa.deciders = ctx->deciders; fa.fronts = ctx->fronts; fa.front_depth = ctx->front_depth;
         if (attempt) { fa.case_list = (const uint32_t*)ctx->retry_list.p; fa.n_list = n_list; }
         if (attempt == 0) CK(cudaEventRecord(ctx->ev[0], st));
         launch_cases(ctx, bp, lp, st, d_data, d_off, d_out_len, d_meta, fa);

@@ -22,7 +22,7 @@ constexpr uint32_t JOB_TILE = 8192;     // bytes per copy job (two 4 KiB registe
 constexpr uint32_t JOB_MIN_COPY = 16384; // shorter copies are executed inline by the deciding warp
 constexpr uint32_t JOB_MIN_SCAN = 16384; // shorter scans likewise
 
-enum JobKind : uint32_t { JOB_COPY_NC = 0, JOB_COPY = 1, JOB_COUNT_DIGIT = 2, JOB_COUNT_NL = 3 };
+enum JobKind : uint32_t { JOB_COPY_NC = 0, JOB_COPY = 1, JOB_COUNT_DIGIT = 2, JOB_COUNT_NL = 3, JOB_EDIT = 4, JOB_SELECT_DIGIT = 5 };
 
 struct __align__(16) Job {
     uint64_t a;       // copy: destination | count: aligned base of the scanned block
@@ -103,11 +103,40 @@ __device__ __forceinline__ void job_count(const Job& j) {
     }
 }
 
+// EDIT job (posted by the front warps, eb_fast.cuh): out = src[0,pos) ++ <ll literal bytes> ++ src[pos+skip, n); src is a
+// corpus blob; the literal bytes are written by the poster itself.
+// a = dst, b = src, len = n, kind = JOB_EDIT | ll << 8 | skip << 16, res = pos
+__device__ __forceinline__ void job_edit(const Job& j) {
+    uint8_t* dst = (uint8_t*)(uintptr_t)j.a; const uint8_t* src = (const uint8_t*)(uintptr_t)j.b;
+    uint32_t n = j.len, pos = j.res, ll = (j.kind >> 8) & 255u, skip = j.kind >> 16;
+    warp_copy_stream<true>(dst, src, pos);
+    warp_copy_stream<true>(dst + pos + ll, src + pos + skip, n - pos - skip);
+}
+// per-lane scratch of a front warp (shared memory): superchunk counts, countdown, selected position
+constexpr uint32_t FRONT_SC = 32;
+struct FrontState { uint16_t sc[32][FRONT_SC]; uint32_t pend[32]; uint32_t sel[32]; };
+// SELECT job: logical index of the k-th digit-run start of a block whose per-superchunk counts are in the poster's
+// FrontState. a = aligned base, b = lead << 32 | span, len = k, kind = JOB_SELECT_DIGIT | lane << 8, res = shared-window
+// address of the FrontState
+__device__ __forceinline__ void job_select(const Job& j) {
+    uint32_t lead = (uint32_t)(j.b >> 32), span = (uint32_t)j.b, lane = (j.kind >> 8) & 31u;
+    const uint8_t* p = (const uint8_t*)(uintptr_t)j.a + lead;
+    FrontState* fs = (FrontState*)__cvta_shared_to_generic((size_t)j.res);
+    uint32_t pos = scan_select<PRED_DIGIT, true>(p, span - lead, fs->sc[lane], j.len);
+    if (lane_id() == 0) {
+        *(volatile uint32_t*)&fs->sel[lane] = pos;
+        __threadfence_block();
+        atomicSub(&fs->pend[lane], 1u);
+    }
+}
+
 // the worker warps' whole program
 __device__ __noinline__ void worker_loop(JobQ* q) {
     Job j;
     while (jobq_get(q, j)) {
-        switch (j.kind) {
+        switch (j.kind & 255u) {
+        case JOB_EDIT: job_edit(j); break;
+        case JOB_SELECT_DIGIT: job_select(j); break;
         case JOB_COPY_NC: warp_copy_stream<true>((uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); break;
         case JOB_COPY: warp_copy_stream<false>((uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); break;
         case JOB_COUNT_DIGIT: job_count<PRED_DIGIT, true>(j); break;

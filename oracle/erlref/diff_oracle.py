@@ -69,6 +69,7 @@ def make_case(idx, mode, base_seed):
 
 
 _ref = None
+TIME_LIMIT = 45
 
 
 def work(args):
@@ -81,12 +82,24 @@ def work(args):
         _ref = Reference()
     blob, seed, case_no, muts, pats = make_case(idx, mode, base_seed)
 
-    def go():
-        return _ref.case(blob, case_no, seed, muts, pats)
+    import signal
+
+    class Timeout(Exception):
+        pass
+
+    def on_alarm(signum, frame):
+        raise Timeout()
+    signal.signal(signal.SIGALRM, on_alarm)
+    signal.alarm(TIME_LIMIT)
     try:
-        rr = run_with_big_stack(go)
+        rr = _ref.case(blob, case_no, seed, muts, pats)     # main thread of the pool worker: the alarm can interrupt it
+    except Timeout:
+        _ref = None                                         # evaluator state may be inconsistent: start afresh
+        return (idx, "skip", "ref=timeout", muts, pats)
     except Exception as e:   # evaluator gap: report, do not hide
         return (idx, "evaluator-error", repr(e)[:300], muts, pats)
+    finally:
+        signal.alarm(0)
     outs, meta = O.fuzzer([blob], mutations=muts, patterns=pats, seed=seed, n_cases=1, first_case=case_no, max_case_out=cap)
     m = meta[0]
     if rr.status != "ok" or m.status != 0:
@@ -107,6 +120,12 @@ def main():
     ap.add_argument("--start", type=int, default=0)
     ap.add_argument("--cap", type=int, default=1 << 20)
     a = ap.parse_args()
+    import resource
+    sys.setrecursionlimit(3000000)
+    try:
+        resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
+    except Exception:
+        pass
     jobs = [(i, a.mode, a.seed, a.cap) for i in range(a.start, a.start + a.n)]
     counts = {}
     with mp.Pool(a.procs, maxtasksperchild=50) as pool:

@@ -1043,6 +1043,7 @@ class Runtime(object):
         self.budget = budget
         self.ets = {}
         self.trace = None
+        self.recent = []
         from . import bifs
         bifs.install(self)
 
@@ -1135,6 +1136,10 @@ class Runtime(object):
             self.steps += 1
             if self.budget is not None and self.steps > self.budget:
                 raise BudgetExceeded()
+            if self.trace:
+                self.recent.append("%s:%s/%d%s" % (fn.module, fn.name, fn.arity, (" " + " ".join(fmt_term(a)[:60] for a in args)) if self.trace == 2 else ""))
+                if len(self.recent) > 4000:
+                    del self.recent[:2000]
             base = fn.env
             n = fn.arity
             res = None
@@ -1177,7 +1182,7 @@ class Runtime(object):
         except ErlError as e:
             self.last_crash = e
             if self.trace:
-                print("spawned process died: %s" % e, file=sys.stderr)
+                print("spawned process died: %s; last calls: %s" % (e, " ".join(self.recent[-12:])), file=sys.stderr)
         finally:
             self.current = saved
             if hasattr(self, "child_draws"):

@@ -246,6 +246,7 @@ struct Fuzzer {
             for (auto& b : res) out += b;
         } catch (const Unsupported&) { meta.status = 1; out.clear(); }
         catch (const CaseDied&) { meta.status = 2; out.clear(); }
+        catch (const std::overflow_error&) { meta.status = 2; out.clear(); }   // badarith inside random:uniform/1 (rnd.hpp rand_big)
         catch (const CaseOverflow&) { meta.status = 3; out = input; }
         meta.draws = rng.draws;
         return out;

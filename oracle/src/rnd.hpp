@@ -12,6 +12,7 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <stdexcept>
 #include "bigint.hpp"
 
 namespace eo {
@@ -42,7 +43,13 @@ struct Rng {
     // rand/1 on arbitrary-size bounds (mutate_num case 9, rand_nbit for wide N)
     BigInt rand_big(const BigInt& n) {
         if (n.is_zero()) return BigInt();
-        double p = uniform() * n.to_double_erl_abs();
+        // random:uniform/1 multiplies a float by the bound: a bignum beyond the double range makes BEAM raise badarith
+        // and the worker process of the case dies (found by running the reference's source: oracle/erlref, input "007"
+        // grown to 1700 digits by line repeats, mutate_num case 9)
+        double u = uniform();                      // the draw is consumed before the multiplication fails
+        double nd = n.to_double_erl_abs();
+        if (std::isinf(nd)) throw std::overflow_error("badarith: bignum bound does not fit a float");
+        double p = u * nd;
         return BigInt::from_double_trunc(std::trunc(p));
     }
     // rand_range/2 :87-92
