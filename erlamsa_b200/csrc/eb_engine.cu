@@ -56,9 +56,9 @@ struct eb200_ctx {
     bool funny_loaded = false;
     int apply_variant = 0;
     int threads = CASE_THREADS;   // eb_case_kernel: threads per CTA (EB200_THREADS) ...
-    int deciders = 12;            // ... of which this many warps run the general per-case program (EB200_DECIDERS),
-    int front_depth = 8;          // fronts post while fewer than this many jobs are waiting in the ring (EB200_FRONT_DEPTH)
-    int fronts = 1;               // this many decide 32 byte-mutator cases at a time, lane per case (EB200_FRONTS), the rest are copy/scan workers
+    int deciders = 0;             // ... of which this many warps run the general per-case program (EB200_DECIDERS; 0 = chosen per batch),
+    int front_depth = 32;         // fronts post while fewer than this many jobs are waiting in the ring (EB200_FRONT_DEPTH)
+    int fronts = -1;              // this many decide 32 byte-mutator cases at a time, lane per case (EB200_FRONTS; -1 = chosen per batch), the rest are copy/scan workers
     DevBuf case_status, retry_list;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // host-path pipeline (created on first use)
 };
@@ -201,9 +201,9 @@ int eb200_init(int device, eb200_ctx** out) {
     if (cudaMemcpyToSymbol(c_funny, f.data(), sizeof(FunnyEntry) * 192) != cudaSuccess || cudaMemcpyToSymbol(c_funny_n, &fn, sizeof(int)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
     if (const char* v = getenv("EB200_MODE")) ctx->fused = strcmp(v, "twopass") != 0;
     if (const char* v = getenv("EB200_THREADS")) { int k = atoi(v); if (k >= 64 && k <= CASE_THREADS && k % 32 == 0) ctx->threads = k; }
-    if (const char* v = getenv("EB200_DECIDERS")) { int k = atoi(v); if (k >= 1 && k <= 32) ctx->deciders = k; }
+    if (const char* v = getenv("EB200_DECIDERS")) { int k = atoi(v); if (k >= 0 && k <= 32) ctx->deciders = k; }
     if (const char* v = getenv("EB200_FRONT_DEPTH")) { int k = atoi(v); if (k >= 0 && k <= 200) ctx->front_depth = k; }
-    if (const char* v = getenv("EB200_FRONTS")) { int k = atoi(v); if (k >= 0 && k <= MAX_FRONTS) ctx->fronts = k; }
+    if (const char* v = getenv("EB200_FRONTS")) { int k = atoi(v); if (k >= -1 && k <= MAX_FRONTS) ctx->fronts = k; }
     if (ctx->deciders > ctx->threads / 32) ctx->deciders = ctx->threads / 32;
     if (cudaFuncSetAttribute(eb_case_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)case_smem(32)) != cudaSuccess ||
         cudaFuncSetAttribute(eb_case_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)case_smem(32)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
@@ -219,9 +219,33 @@ void eb200_shutdown(eb200_ctx* ctx) {
     delete ctx;
 }
 
+// How the CTA's warps are split for a batch. The front warps can decide a case on their own when its pattern is `od` and
+// the first scheduled mutator is a single-byte mutator or sed_num (eb_fast.cuh); `share` estimates how many cases that is
+// from the priorities. Mostly-front batches (C3) want a few general deciders and many copy workers; batches the fronts
+// cannot help keep the warps on the general program. Measured on C3 (profiles/variants_r2.txt): fronts 3 / deciders 2
+// 2.55 ms, 2/2 2.65, 4/2 2.58, 1/2 3.10; without fronts 5.3 ms (32 deciders, inline copies) .. 9.6 ms (8 deciders).
+struct Roles { int fronts, deciders; };
+static Roles choose_roles(const eb200_ctx* ctx, const BatchParams& bp, bool fused) {
+    Roles r;
+    double pod = 0, psum = 0, mfast = 0, msum = 0;
+    for (int i = 0; i < bp.n_pats; i++) { psum += bp.pat_pri[i]; if (bp.pat_id[i] == P_OD) pod += bp.pat_pri[i]; }
+    for (int i = 0; i < bp.n_rows; i++) { double w = bp.row_pri[i] * 5.5; msum += w; if (fast_byte_mut(bp.row_id[i]) || bp.row_id[i] == M_NUM) mfast += w; }
+    double share = (psum > 0 && msum > 0 && fused && bp.generator == 0) ? (pod / psum) * (mfast / msum) : 0.0;
+    int warps = ctx->threads / 32;
+    if (share >= 0.5) { r.fronts = 3; r.deciders = 2; }
+    else if (share >= 0.02) { r.fronts = 1; r.deciders = warps >= 32 ? 20 : warps / 2; }
+    else { r.fronts = 0; r.deciders = warps >= 32 ? 24 : warps / 2; }
+    if (ctx->fronts >= 0) r.fronts = ctx->fronts;
+    if (ctx->deciders > 0) r.deciders = ctx->deciders;
+    if (r.deciders > warps) r.deciders = warps;
+    if (r.fronts + r.deciders >= warps) r.fronts = 0;
+    return r;
+}
 // arenas + launch geometry shared by both modes
-struct LaunchPlan { Arenas ar; int grid; };
-static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_bytes, uint64_t n_launch, LaunchPlan& lp) {
+struct LaunchPlan { Arenas ar; int grid; Roles roles; };
+static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_bytes, uint64_t n_launch, bool fused, LaunchPlan& lp) {
+    lp.roles = choose_roles(ctx, bp, fused);
+    const int deciders = lp.roles.deciders;
     unsigned long long* cnt = (unsigned long long*)ctx->counters.p;
     Arenas& ar = lp.ar;
     ar.scratch = (uint8_t*)ctx->scratch.p; ar.scratch_cap = ctx->scratch.cap - 64;
@@ -230,7 +254,7 @@ static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_byte
     ar.overflow = (uint32_t*)(cnt + CNT_OVERFLOW);
     ar.flagged = cnt + CNT_FLAGGED;
     ar.case_status = (uint8_t*)ctx->case_status.p;
-    uint64_t want_ctas = (n_launch + ctx->deciders - 1) / ctx->deciders;
+    uint64_t want_ctas = (n_launch + deciders - 1) / deciders;
     lp.grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms);
     if (lp.grid < 1) lp.grid = 1;
     ar.temp = nullptr; ar.temp_per_warp = 0;
@@ -241,7 +265,7 @@ static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_byte
         uint64_t mean = bp.n_blobs ? data_bytes / bp.n_blobs : 0;
         uint64_t per = std::min<uint64_t>(std::max<uint64_t>(64 * mean, 256u << 10), 16u << 20);
         per = (per + 255) & ~255ull;
-        uint64_t nw = (uint64_t)ctx->num_sms * ctx->deciders;
+        uint64_t nw = (uint64_t)ctx->num_sms * deciders;
         while (per > (256u << 10) && per * nw > (48ull << 30)) per >>= 1;
         CK(ctx->temp.ensure(per * nw + 256));
         ar.temp = (uint8_t*)ctx->temp.p; ar.temp_per_warp = per;
@@ -250,7 +274,7 @@ static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_byte
 }
 static void launch_cases(eb200_ctx* ctx, const BatchParams& bp, const LaunchPlan& lp, cudaStream_t st, const uint8_t* d_data, const uint64_t* d_off,
                          uint64_t* d_out_len, eb200_meta* d_meta, const FusedArgs& fa) {
-    size_t sm = case_smem(ctx->deciders);
+    size_t sm = case_smem(lp.roles.deciders);
     if (!batch_is_light(bp)) eb_case_kernel<true><<<lp.grid, ctx->threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
     else eb_case_kernel<false><<<lp.grid, ctx->threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
 }
@@ -272,10 +296,10 @@ static int run_decide_scan(eb200_ctx* ctx, const BatchParams& bp, const eb200_op
     // edit scripts published by this mode point into scratch, so an exhausted arena means running the batch again
     for (int attempt = 0;; attempt++) {
         CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
-        LaunchPlan lp; int rc = plan_launch(ctx, bp, data_bytes, n, lp); if (rc) return rc;
+        LaunchPlan lp; int rc = plan_launch(ctx, bp, data_bytes, n, false, lp); if (rc) return rc;
         CK(cudaEventRecord(ctx->ev[0], st));
         FusedArgs fa; memset(&fa, 0, sizeof(fa));
-        fa.case_counter = (unsigned long long*)ctx->counters.p + CNT_NEXT_CASE; fa.deciders = ctx->deciders; fa.fronts = 0;
+        fa.case_counter = (unsigned long long*)ctx->counters.p + CNT_NEXT_CASE; fa.deciders = lp.roles.deciders; fa.fronts = 0;
         launch_cases(ctx, bp, lp, st, d_data, d_off, d_out_len, d_meta, fa);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], st));
@@ -358,11 +382,11 @@ static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* op
     std::vector<uint8_t> status_host;
     std::vector<uint32_t> list_host;
     for (int attempt = 0;; attempt++) {
-        LaunchPlan lp; int rc = plan_launch(ctx, bp, data_bytes, attempt ? n_list : n, lp); if (rc) return rc;
+        LaunchPlan lp; int rc = plan_launch(ctx, bp, data_bytes, attempt ? n_list : n, true, lp); if (rc) return rc;
         FusedArgs fa; memset(&fa, 0, sizeof(fa));
         fa.fused = 1; fa.out = d_out; fa.out_capacity = out_capacity; fa.slot_off = (const uint64_t*)ctx->slot_off.p; fa.out_off = d_out_off;
         fa.ovf_base = slots; fa.ovf_used = cnt + CNT_OVF_USED; fa.data_bytes = data_bytes;
-        fa.case_counter = cnt + CNT_NEXT_CASE; fa.deciders = ctx->deciders; fa.fronts = ctx->fronts; fa.front_depth = ctx->front_depth;
+        fa.case_counter = cnt + CNT_NEXT_CASE; fa.deciders = lp.roles.deciders; fa.fronts = lp.roles.fronts; fa.front_depth = ctx->front_depth;
         if (attempt) { fa.case_list = (const uint32_t*)ctx->retry_list.p; fa.n_list = n_list; }
         if (attempt == 0) CK(cudaEventRecord(ctx->ev[0], st));
         launch_cases(ctx, bp, lp, st, d_data, d_off, d_out_len, d_meta, fa);

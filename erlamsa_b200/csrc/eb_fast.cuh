@@ -70,29 +70,46 @@ __host__ __device__ inline bool fast_byte_mut(int id) {
 
 struct FastOut { uint32_t pos; uint32_t skip; uint32_t ll; uint32_t name; uint8_t lit[88]; };
 
-// sed_num for one lane (reference src/erlamsa_mutations.erl:114-169; same draws as mut_num): the block scan and the
-// selection of the number are done by the workers (COUNT / SELECT jobs), the arithmetic here
-__device__ __noinline__ bool fast_num_lane(Rng& g, JobQ* q, FrontState* fs, const uint8_t* blob, uint32_t blen, FastOut& fo) {
+// lane-level post of a streaming copy (tile jobs; destinations after the first start on 16-byte boundaries)
+__device__ __forceinline__ void post_copy_lane(JobQ* q, uint8_t* dst, const uint8_t* src, uint32_t n) {
+    uint32_t s = 0;
+    while (s < n) {
+        uint32_t e = s + JOB_TILE + ((16u - ((uint32_t)(uintptr_t)(dst + s) & 15u)) & 15u);
+        if (e > n || n - e < 1024) e = n;
+        Job j; j.a = (uint64_t)(uintptr_t)(dst + s); j.b = (uint64_t)(uintptr_t)(src + s); j.len = e - s; j.kind = JOB_COPY_NC; j.res = 0; j.pend = 0;
+        uint32_t pos = atomicAdd(&q->tail, 1u);
+        jobq_put(q, pos, j);
+        s = e;
+    }
+}
+
+constexpr uint32_t NUM_PAD = 96;    // room in front of the speculative copy for a result that grows at the front
+
+// sed_num for one lane (reference src/erlamsa_mutations.erl:114-169; same draws as mut_num). The workers count the digit
+// runs of the block while copying it into the slot (COUNTCOPY jobs), select the number (SELECT job); the arithmetic is
+// here; then the shorter of prefix / suffix is copied again at its shifted place. dst0 = 16-byte aligned address inside the
+// slot that stands for the block's aligned coordinate 0. On success *out_start = where the result begins.
+__device__ __noinline__ bool fast_num_lane(Rng& g, JobQ* q, FrontState* fs, const uint8_t* blob, uint32_t blen, uint8_t* dst0, FastOut& fo, uint8_t** out_start) {
     const uint32_t l = (uint32_t)lane_id();
     if (blen < 2304) return false;                      // shorter blocks: "did the head block change" needs the general path
     ScanCursor c = scan_cursor(blob, blen);
     uint32_t nsc = (c.span + 4095u) >> 12;
     if (nsc > FRONT_SC) return false;
     uint32_t fs_sa = (uint32_t)__cvta_generic_to_shared(fs);
-    uint32_t pend_sa = (uint32_t)__cvta_generic_to_shared(&fs->pend[l]), sc_sa = (uint32_t)__cvta_generic_to_shared(&fs->sc[l][0]);
     *(volatile uint32_t*)&fs->pend[l] = nsc;
     __threadfence_block();
     uint32_t pos0 = atomicAdd(&q->tail, nsc);
     for (uint32_t i = 0; i < nsc; i++) {
-        Job j; j.a = (uint64_t)(uintptr_t)c.base; j.b = ((uint64_t)c.lead << 32) | c.span; j.len = i; j.kind = JOB_COUNT_DIGIT; j.res = sc_sa + 2u * i; j.pend = pend_sa;
+        Job j; j.a = (uint64_t)(uintptr_t)c.base; j.b = (uint64_t)(uintptr_t)dst0; j.len = i; j.kind = JOB_COUNTCOPY_DIGIT | (l << 8) | (c.lead << 16); j.res = fs_sa; j.pend = c.span;
         jobq_put(q, pos0 + i, j);
     }
     while (ld_shared_volatile(&fs->pend[l]) != 0) __nanosleep(200);
-    __threadfence_block();
+    __threadfence();
     uint32_t nfound = 0;
     for (uint32_t i = 0; i < nsc; i++) nfound += ((volatile uint16_t*)fs->sc[l])[i];
     uint64_t which = g.rand(nfound);
-    if (nfound == 0) { (void)g.rand(10); fo.pos = 0; fo.skip = 0; fo.ll = 0; fo.name = M_NUM; return true; }
+    uint8_t* x = dst0 + c.lead;                        // the speculative copy of the block starts here
+    if (nfound == 0) { (void)g.rand(10); fo.pos = 0; fo.skip = 0; fo.ll = 0; fo.name = M_NUM; *out_start = x; return true; }
     *(volatile uint32_t*)&fs->pend[l] = 1;
     __threadfence_block();
     { Job j; j.a = (uint64_t)(uintptr_t)c.base; j.b = ((uint64_t)c.lead << 32) | c.span; j.len = nfound - 1 - (uint32_t)which; j.kind = JOB_SELECT_DIGIT | (l << 8); j.res = fs_sa; j.pend = 0;
@@ -102,20 +119,32 @@ __device__ __noinline__ bool fast_num_lane(Rng& g, JobQ* q, FrontState* fs, cons
     uint32_t d0 = *(volatile uint32_t*)&fs->sel[l];
     uint32_t a = d0; while (a > 0 && blob[a - 1] == '-') a--;
     uint32_t b = d0; while (b < blen && (uint32_t)(blob[b] - '0') < 10u) b++;
-    if (b - d0 > 77 || b - a > 255) return false;       // wider numbers / long dash runs: general path (flags what it cannot hold)
+    if (b - d0 > 77 || b - a > 64) return false;        // wider numbers / long dash runs: general path (flags what it cannot hold)
     Big256 v; v.zero();
     for (uint32_t i = d0; i < b; i++) { v.mul_small(10); v.add_small((uint32_t)(blob[i] - '0')); }
     if (a < d0 && !v.is_zero()) v.neg = 1;
     mutate_num(g, v);
     if (v.ovf) return false;
-    fo.ll = (uint32_t)v.to_decimal(fo.lit);
-    fo.pos = a; fo.skip = b - a; fo.name = M_NUM;
+    uint32_t dl = (uint32_t)v.to_decimal(fo.lit);
+    fo.ll = dl; fo.pos = a; fo.skip = b - a; fo.name = M_NUM;
+    // result = blob[0,a) ++ lit ++ blob[b,n): keep the longer side of the speculative copy, redo the shorter one
+    int32_t d = (int32_t)dl - (int32_t)(b - a);
+    if (a <= blen - b) {   // prefix moves by -d, the literal ends where the old number ended
+        uint8_t* start = x - d;
+        if (d != 0) post_copy_lane(q, start, blob, a);
+        for (uint32_t i = 0; i < dl; i++) x[b - dl + i] = fo.lit[i];
+        *out_start = start;
+    } else {               // suffix moves by +d
+        if (d != 0) post_copy_lane(q, x + a + dl, blob + b, blen - b);
+        for (uint32_t i = 0; i < dl; i++) x[a + i] = fo.lit[i];
+        *out_start = x;
+    }
     return true;
 }
 
 // One lane, one case. Returns true when the case is fully decided here: out = blob[0,pos) ++ lit[0,ll) ++ blob[pos+skip, n).
 // Draw order = decide_one_case -> generate -> run_case_machine(P_OD) -> mux_fuzzers -> mut_byte / mut_num, single-block case.
-__device__ __forceinline__ bool fast_decide_lane(const BatchParams& bp, Rng& g, JobQ* q, FrontState* fs, uint32_t blen, const uint8_t* blob, FastOut& fo) {
+__device__ __forceinline__ bool fast_decide_lane(const BatchParams& bp, Rng& g, JobQ* q, FrontState* fs, uint32_t blen, const uint8_t* blob, uint8_t* slot, uint64_t cap, FastOut& fo, uint8_t** num_start) {
     if (bp.generator != 0 || blen == 0 || blen > ABSMAX_BINARY_BLOCK) return false;
     (void)g.rand((uint64_t)bp.rbs_bound);                                   // direct_generator: unused rand_block_size
     if (g.rand((uint64_t)blen + 1) == blen) return false;                    // finish/1 appends a random tail: general path
@@ -134,7 +163,7 @@ __device__ __forceinline__ bool fast_decide_lane(const BatchParams& bp, Rng& g, 
     }
     if (best < 0) return false;
     int id = bp.row_id[best];
-    if (id == M_NUM) return fast_num_lane(g, q, fs, blob, blen, fo);
+    if (id == M_NUM) { if (cap < (uint64_t)blen + NUM_PAD + 112) return false; return fast_num_lane(g, q, fs, blob, blen, slot + NUM_PAD, fo, num_start); }
     if (!fast_byte_mut(id)) return false;
     // mut_byte (sed_byte_* / sed_utf8_widen)
     uint32_t pos = (uint32_t)g.rand(blen);
@@ -175,25 +204,31 @@ __device__ __noinline__ void front_loop(const BatchParams& bp, const DecideArgs&
             Rng g; int64_t ts0 = 0, ts1 = 0, ts2 = 0;
             uint64_t bi = (I - 1) % bp.n_blobs;
             const uint8_t* blob = a.data + a.off[bi]; uint32_t blen = (uint32_t)(a.off[bi + 1] - a.off[bi]);
+            uint64_t s0 = 0, cap = 0;
+            if (fast) { s0 = a.slot_off[k]; cap = a.slot_off[k + 1] - s0; }
+            uint8_t* num_start = nullptr;
             if (fast) {
                 Rng par; par.mode = 0; par.a1 = (int32_t)a1; par.a2 = (int32_t)a2; par.a3 = (int32_t)a3; par.draws = 0; par.key = 0; par.ctr_hi = 0;
                 ts0 = (int64_t)par.erand(99999); ts1 = (int64_t)par.erand(99999); ts2 = (int64_t)par.erand(99999);
                 g.mode = bp.rng_mode; g.key = bp.philox_key; g.ctr_hi = I; g.seed(ts0, ts1, ts2);
-                fast = fast_decide_lane(bp, g, q, fs, blen, blob, fo);
+                fast = fast_decide_lane(bp, g, q, fs, blen, blob, a.out + s0, cap, fo, &num_start);
             }
             uint64_t olen = (uint64_t)blen - fo.skip + fo.ll;
-            uint64_t s0 = 0;
-            if (fast) { s0 = a.slot_off[k]; if (olen > a.slot_off[k + 1] - s0 || olen > bp.max_case_out) fast = false; }
+            if (fast && (olen > cap || olen > bp.max_case_out)) fast = false;
             if (!fast) slow_push(slow, k);
             else {
-                Job j; j.a = (uint64_t)(uintptr_t)(a.out + s0); j.b = (uint64_t)(uintptr_t)blob; j.len = blen; j.kind = JOB_EDIT | (fo.ll << 8) | (fo.skip << 16); j.res = fo.pos; j.pend = 0;
-                for (uint32_t i = 0; i < fo.ll; i++) a.out[s0 + fo.pos + i] = fo.lit[i];
-                // the fronts run far ahead of the workers: keep the ring shallow, so that the scan and copy jobs of the
-                // general deciders (whose cases wait for them) are never queued behind hundreds of whole-case edits
-                while ((int32_t)(*(volatile unsigned int*)&q->tail - *(volatile unsigned int*)&q->head) > fa.front_depth) __nanosleep(500);
-                uint32_t pos = atomicAdd(&q->tail, 1u);
-                jobq_put(q, pos, j);
-                a.out_off[k] = s0; a.out_len[k] = olen;
+                uint64_t oo = s0;
+                if (num_start) oo = (uint64_t)(num_start - a.out);      // sed_num: the workers already moved the bytes
+                else {
+                    Job j; j.a = (uint64_t)(uintptr_t)(a.out + s0); j.b = (uint64_t)(uintptr_t)blob; j.len = blen; j.kind = JOB_EDIT | (fo.ll << 8) | (fo.skip << 16); j.res = fo.pos; j.pend = 0;
+                    for (uint32_t i = 0; i < fo.ll; i++) a.out[s0 + fo.pos + i] = fo.lit[i];
+                    // the fronts run far ahead of the workers: keep the ring shallow, so that the scan and copy jobs of the
+                    // general deciders (whose cases wait for them) are never queued behind hundreds of whole-case edits
+                    while ((int32_t)(*(volatile unsigned int*)&q->tail - *(volatile unsigned int*)&q->head) > fa.front_depth) __nanosleep(500);
+                    uint32_t pos = atomicAdd(&q->tail, 1u);
+                    jobq_put(q, pos, j);
+                }
+                a.out_off[k] = oo; a.out_len[k] = olen;
                 if (a.ar.case_status) a.ar.case_status[k] = 0;
                 if (a.meta) {
                     MetaDev m; m.pattern = P_OD; m.generator = 0; m.n_used = 1; m.n_failed = 0;

@@ -22,7 +22,7 @@ constexpr uint32_t JOB_TILE = 8192;     // bytes per copy job (two 4 KiB registe
 constexpr uint32_t JOB_MIN_COPY = 16384; // shorter copies are executed inline by the deciding warp
 constexpr uint32_t JOB_MIN_SCAN = 16384; // shorter scans likewise
 
-enum JobKind : uint32_t { JOB_COPY_NC = 0, JOB_COPY = 1, JOB_COUNT_DIGIT = 2, JOB_COUNT_NL = 3, JOB_EDIT = 4, JOB_SELECT_DIGIT = 5 };
+enum JobKind : uint32_t { JOB_COPY_NC = 0, JOB_COPY = 1, JOB_COUNT_DIGIT = 2, JOB_COUNT_NL = 3, JOB_EDIT = 4, JOB_SELECT_DIGIT = 5, JOB_COUNTCOPY_DIGIT = 6 };
 
 struct __align__(16) Job {
     uint64_t a;       // copy: destination | count: aligned base of the scanned block
@@ -130,6 +130,43 @@ __device__ __forceinline__ void job_select(const Job& j) {
     }
 }
 
+// COUNT + COPY job (front warps, sed_num): count the digit runs of one 4 KiB superchunk of a block AND copy it, byte for
+// byte at the same 16-byte phase, into the case's output slot. The prefix of a sed_num result is the prefix of its input
+// at the same offsets, so this speculative copy is already final for everything before the edited number; after the
+// decision only the SHORTER side is copied again at its shifted position (eb_fast.cuh) -- the block crosses HBM once.
+// a = aligned source base, b = destination of aligned coordinate 0, len = superchunk, pend = span,
+// kind = JOB_COUNTCOPY_DIGIT | lane << 8 | lead << 16, res = shared-window address of the poster's FrontState
+__device__ __forceinline__ void job_countcopy(const Job& j) {
+    uint32_t lane = (j.kind >> 8) & 31u;
+    ScanCursor c; c.base = (const uint8_t*)(uintptr_t)j.a; c.lead = (j.kind >> 16) & 15u; c.span = j.pend; c.n = c.span - c.lead;
+    uint8_t* dbase = (uint8_t*)(uintptr_t)j.b;
+    FrontState* fs = (FrontState*)__cvta_shared_to_generic((size_t)j.res);
+    uint32_t it0 = j.len * 8u;
+    uint4 w[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) w[k] = scan_chunk_load(c, it0 + k);
+    uint32_t carry = scan_carry_in<PRED_DIGIT>(c, j.len);
+    uint32_t s = scan_count_sc_w<PRED_DIGIT, true>(c, it0, carry, w);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t wofs = ((it0 + k) * 32u + (uint32_t)lane_id()) * 16u;
+        if (wofs >= c.span || wofs + 16 <= c.lead) continue;
+        if (wofs >= c.lead && wofs + 16 <= c.span) *reinterpret_cast<uint4*>(dbase + wofs) = w[k];
+        else {
+            uint32_t lo = wofs < c.lead ? c.lead - wofs : 0, hi = wofs + 16 > c.span ? c.span - wofs : 16;
+            uint32_t ww[4] = {w[k].x, w[k].y, w[k].z, w[k].w};
+            for (uint32_t i = lo; i < hi; i++) dbase[wofs + i] = (uint8_t)(ww[i >> 2] >> (8 * (i & 3)));
+        }
+    }
+    __threadfence();      // every lane's stores must be ordered before the countdown the poster waits on
+    __syncwarp();
+    if (lane_id() == 0) {
+        *(volatile uint16_t*)&fs->sc[lane][j.len] = (uint16_t)s;
+        __threadfence();
+        atomicSub(&fs->pend[lane], 1u);
+    }
+}
+
 // the worker warps' whole program
 __device__ __noinline__ void worker_loop(JobQ* q) {
     Job j;
@@ -137,6 +174,7 @@ __device__ __noinline__ void worker_loop(JobQ* q) {
         switch (j.kind & 255u) {
         case JOB_EDIT: job_edit(j); break;
         case JOB_SELECT_DIGIT: job_select(j); break;
+        case JOB_COUNTCOPY_DIGIT: job_countcopy(j); break;
         case JOB_COPY_NC: warp_copy_stream<true>((uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); break;
         case JOB_COPY: warp_copy_stream<false>((uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); break;
         case JOB_COUNT_DIGIT: job_count<PRED_DIGIT, true>(j); break;

@@ -236,10 +236,7 @@ __device__ __forceinline__ uint32_t scan_chunk_mask(const ScanCursor& c, uint32_
 // matches inside ONE superchunk (warp chunks it0 .. it0+7); `carry` = "the byte before this superchunk matches"
 // on entry, the same for the next superchunk on return. Returns the warp-wide count (same value in every lane).
 template <int PRED, bool RUNSTART>
-__device__ __forceinline__ uint32_t scan_count_sc(const ScanCursor& c, uint32_t it0, uint32_t& carry) {
-    uint4 w[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) w[j] = scan_chunk_load(c, it0 + j);
+__device__ __forceinline__ uint32_t scan_count_sc_w(const ScanCursor& c, uint32_t it0, uint32_t& carry, const uint4* w) {
     uint32_t acc = 0;
     if (it0 * 512u >= c.lead && (it0 + 8) * 512u <= c.span) {
         // interior superchunk: every byte is valid, so count straight on the bit-7 byte flags
@@ -263,6 +260,13 @@ __device__ __forceinline__ uint32_t scan_count_sc(const ScanCursor& c, uint32_t 
         for (int j = 0; j < 8; j++) acc += __popc(scan_chunk_reduce<PRED, RUNSTART>(c, it0 + j, w[j], carry));
     }
     return warp_sum(acc);
+}
+template <int PRED, bool RUNSTART>
+__device__ __forceinline__ uint32_t scan_count_sc(const ScanCursor& c, uint32_t it0, uint32_t& carry) {
+    uint4 w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) w[j] = scan_chunk_load(c, it0 + j);
+    return scan_count_sc_w<PRED, RUNSTART>(c, it0, carry, w);
 }
 // carry-in of superchunk s > 0 computed from the data alone: is the last byte before it a (valid) match?
 template <int PRED>
