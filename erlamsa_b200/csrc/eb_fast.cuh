@@ -104,7 +104,7 @@ __device__ __noinline__ bool fast_num_lane(Rng& g, JobQ* q, FrontState* fs, cons
         jobq_put(q, pos0 + i, j);
     }
     while (ld_shared_volatile(&fs->pend[l]) != 0) __nanosleep(200);
-    __threadfence();
+    __threadfence_block();
     uint32_t nfound = 0;
     for (uint32_t i = 0; i < nsc; i++) nfound += ((volatile uint16_t*)fs->sc[l])[i];
     uint64_t which = g.rand(nfound);

@@ -84,7 +84,7 @@ def work(args):
 
     import signal
 
-    class Timeout(Exception):
+    class Timeout(BaseException):
         pass
 
     def on_alarm(signum, frame):
