@@ -430,6 +430,8 @@ template <bool FULL>
 EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideArgs& a, uint64_t k, int32_t pa1, int32_t pa2, int32_t pa3, JobQ* q, uint32_t temp_slot) {
     const uint8_t* data = a.data; const uint64_t* off = a.off; const Arenas& ar = a.ar;
     CaseOut* cases = a.cases; uint64_t* out_len = a.out_len; uint64_t* out_sz16 = a.out_sz16; MetaDev* meta = a.meta;
+    unsigned long long t_begin = 0;
+    if (ar.case_usec) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
     {
         uint64_t I = bp.first_case + k;                 // the reference's 1-based case number
         uint64_t b = (I - 1) % bp.n_blobs;
@@ -499,6 +501,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         if (lane_id() == 0 && ws->status != CASE_OK && ar.flagged) atomicAdd(&ar.flagged[ws->status - 1], 1ull);
         if (lane_id() == 0) {
             if (ar.case_status) ar.case_status[k] = (uint8_t)(ws->status | (ws->reason << 4));
+            if (ar.case_usec) { unsigned long long t_end; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end)); ar.case_usec[k] = (uint32_t)((t_end - t_begin) / 1000ull); }
             if (!a.fused) {
                 CaseOut co; co.seg_begin = sb; co.nseg = (uint32_t)ns; co.status = ws->status; co.out_len = ws->olen; co.pad = 0;
                 cases[k] = co; out_len[k] = ws->olen; out_sz16[k] = align16(ws->olen);

@@ -59,7 +59,8 @@ struct eb200_ctx {
     int deciders = 0;             // ... of which this many warps run the general per-case program (EB200_DECIDERS; 0 = chosen per batch),
     int front_depth = 32;         // fronts post while fewer than this many jobs are waiting in the ring (EB200_FRONT_DEPTH)
     int fronts = -1;              // this many decide 32 byte-mutator cases at a time, lane per case (EB200_FRONTS; -1 = chosen per batch), the rest are copy/scan workers
-    DevBuf case_status, retry_list;
+    DevBuf case_status, retry_list, case_usec;
+    bool want_case_times = false; uint64_t case_times_n = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // host-path pipeline (created on first use)
 };
 
@@ -200,6 +201,7 @@ int eb200_init(int device, eb200_ctx** out) {
     int fn = (int)f.size(); f.resize(192);
     if (cudaMemcpyToSymbol(c_funny, f.data(), sizeof(FunnyEntry) * 192) != cudaSuccess || cudaMemcpyToSymbol(c_funny_n, &fn, sizeof(int)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
     if (const char* v = getenv("EB200_MODE")) ctx->fused = strcmp(v, "twopass") != 0;
+    if (const char* v = getenv("EB200_CASE_TIMES")) ctx->want_case_times = atoi(v) != 0;
     if (const char* v = getenv("EB200_THREADS")) { int k = atoi(v); if (k >= 64 && k <= CASE_THREADS && k % 32 == 0) ctx->threads = k; }
     if (const char* v = getenv("EB200_DECIDERS")) { int k = atoi(v); if (k >= 0 && k <= 32) ctx->deciders = k; }
     if (const char* v = getenv("EB200_FRONT_DEPTH")) { int k = atoi(v); if (k >= 0 && k <= 200) ctx->front_depth = k; }
@@ -213,7 +215,7 @@ int eb200_init(int device, eb200_ctx** out) {
 void eb200_shutdown(eb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->slot_off, &ctx->temp, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta, &ctx->case_status, &ctx->retry_list}) b->release();
+    for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->slot_off, &ctx->temp, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta, &ctx->case_status, &ctx->retry_list, &ctx->case_usec}) b->release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_h2d) { cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h); cudaStreamDestroy(ctx->s_comp); }
     delete ctx;
@@ -254,6 +256,8 @@ static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_byte
     ar.overflow = (uint32_t*)(cnt + CNT_OVERFLOW);
     ar.flagged = cnt + CNT_FLAGGED;
     ar.case_status = (uint8_t*)ctx->case_status.p;
+    ar.case_usec = nullptr;
+    if (ctx->want_case_times) { CK(ctx->case_usec.ensure(bp.n_cases * 4 + 64)); ar.case_usec = (uint32_t*)ctx->case_usec.p; ctx->case_times_n = bp.n_cases; if (!fused || n_launch == bp.n_cases) CK(cudaMemset(ar.case_usec, 0, bp.n_cases * 4)); }
     uint64_t want_ctas = (n_launch + deciders - 1) / deciders;
     lp.grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms);
     if (lp.grid < 1) lp.grid = 1;
@@ -666,6 +670,16 @@ static int fuzz_batch_host(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t
 }
 
 void eb200_free(void* p) { free(p); }
+
+// profiling aid (EB200_CASE_TIMES=1): microseconds the general per-case program spent on each case of the last launch
+// (0 for cases the front warps decided); returns the number of entries copied
+uint64_t eb200_debug_case_times(eb200_ctx* ctx, uint32_t* out, uint64_t n) {
+    if (!ctx || !ctx->want_case_times || !ctx->case_usec.p) return 0;
+    if (n > ctx->case_times_n) n = ctx->case_times_n;
+    cudaSetDevice(ctx->device);
+    if (cudaMemcpy(out, ctx->case_usec.p, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
 
 const char* eb200_mutator_code(int i) { return (i >= 0 && i < EB200_N_MUTATORS) ? kMutCodes[i] : nullptr; }
 int eb200_mutator_default_pri(int i) { return (i >= 0 && i < EB200_N_MUTATORS) ? kMutPri[i] : -1; }

@@ -122,6 +122,9 @@ int  eb200_fuzz_batch(eb200_ctx* ctx, const eb200_opts* opts,
                       uint8_t** out_data, uint64_t* out_off, uint64_t* out_len,
                       eb200_meta* meta, eb200_stats* stats);
 void eb200_free(void* p);
+/* profiling aid: with EB200_CASE_TIMES=1 in the environment at eb200_init, microseconds the general per-case program spent on
+ * each case of the last launch (0 for cases decided by the front warps). Returns the number of entries copied. */
+uint64_t eb200_debug_case_times(eb200_ctx* ctx, uint32_t* out, uint64_t n);
 
 /* Same as eb200_fuzz_batch, but the outputs are written into a caller buffer (e.g. a resource binary or pinned
  * staging memory owned by the NIF); EB200_ERR_NOMEM when out_capacity is too small. Size it as
