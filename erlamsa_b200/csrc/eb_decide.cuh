@@ -123,7 +123,10 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
         if (!big) {
             MutRow row = ws->rows[ws->order[t]];
             temp_reset(c);
+            unsigned long long t_m0 = 0;
+            if (c.ar.mut_ns) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_m0));
             if (FULL) mut_apply(c, row, p, n, r); else mut_apply_light(c, row, p, n, r);
+            if (c.ar.mut_ns && lane_id() == 0) { unsigned long long t_m1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_m1)); atomicAdd(&c.ar.mut_ns[2 * row.fn], t_m1 - t_m0); atomicAdd(&c.ar.mut_ns[2 * row.fn + 1], 1ull); }
             if (r.kind == RES_UNSUPPORTED) ws->status = CASE_UNSUPPORTED;
             if (ws->status != CASE_OK) return;
             row.score = adjust_priority(row.score, r.delta);

@@ -37,6 +37,8 @@ for rep in range(2):
     wall = time.time() - t0
 st = eng.last_stats
 us = (C.c_uint32 * n)()
+N.lib().eb200_debug_case_times.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint64]
+N.lib().eb200_debug_case_times.restype = C.c_uint64
 got = N.lib().eb200_debug_case_times(eng._ctx, us, n)
 print("%s: %d cases, wall %.1f ms, kernel %.1f ms, launches %d, flagged u/d/o %d/%d/%d, timed entries %d" % (
     which, n, wall * 1e3, st.ms_decide, st.kernels_launched, st.n_unsupported, st.n_died, st.n_overflow, got))
@@ -58,4 +60,11 @@ for k in sorted(range(n), key=lambda k: -us[k])[:25]:
     print("  case %6d  %9.2f ms  pat %-3s used %-40s fails %3d in %7d out %8d status %d/%d draws %d" % (
         k, us[k] / 1e3, PC[m.pattern] if 0 <= m.pattern < len(PC) else "?", ",".join(MC[u] for u in m.used if u >= 0), m.n_failed,
         len(blobs[k % len(blobs)]), len(outs[k]), m.status, m.pad, m.draws))
+mt = (C.c_uint64 * 82)()
+N.lib().eb200_debug_mutator_times.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+if N.lib().eb200_debug_mutator_times(eng._ctx, mt):
+    print("time inside each mutator (all attempts, successful or not):")
+    for i in sorted(range(41), key=lambda i: -mt[2 * i]):
+        if mt[2 * i + 1]:
+            print("  %-6s total %10.1f ms  calls %7d  mean %9.1f us" % (MC[i], mt[2 * i] / 1e6, mt[2 * i + 1], mt[2 * i] / 1e3 / mt[2 * i + 1]))
 # time by mutator TRIED is not recorded; failures dominate when `used` is short and n_failed large
