@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- mutated test cases / s of the erlamsa hot path on B200 (BASELINE.json metric).
 
-A "step" = one pass of the hot path (decide kernel -> prefix sum -> apply kernel) over one batch of
-synthetic seeds resident in HBM. Default workload = BASELINE config C3 (the one the 1e7 cases/s target
+A "step" = one pass of the hot path (slot prefix sum -> eb_case_kernel: the one persistent kernel that decides every case
+and moves its bytes) over one batch of synthetic seeds resident in HBM. Default workload = BASELINE config C3 (the one the 1e7 cases/s target
 is quoted on): 100 000 x 65 536 B uniform-random seeds, mutators bd,bei,bed,bf,bi,ber,br,num at
 priority 1, pattern od, AS183-exact RNG. Every step mutates the NEXT window of case ids (first_case
 advances), so no step repeats work and the 6.5 GB corpus + 6.5 GB of outputs per step never fit L2.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3num|c2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3num|c2|c4|c5]
+
+The default (C3) line also carries `parity_sample` (sampled case ids of the last timed step re-run through the oracle),
+`extra_workloads` (short C2 and C4 runs, value net of flagged cases, all-threads CPU port beside them) and, for c5, `collective`.
 
 Under torchrun (N > 1) every rank owns one GPU and its own shard of case ids (weak scaling: per-GPU work
 fixed; cases are independent, so there is no data-path collective); timing = max over ranks.
@@ -33,6 +36,9 @@ WORKLOADS = {
               "C3(ii): 100000 x 65536 B numeric text; bd,bei,bed,bf,bi,ber,br,num; pattern od"),
     "c4": (12500, 262144, "markup", ["ab", "ad", "tr2", "td", "ts1", "ts2", "tr", "sgm", "js"], {"od": 1},
            "C4 (one GPU's quarter): 12500 x 262144 B documents, half SGML half JSON, tiled from 64 distinct ones; ab,ad,tr2,td,ts1,ts2,tr,sgm,js; pattern od"),
+    "c5": (125000, 4096, "text", ["ft", "fn", "fo"], {"od": 1},
+           "C5 (one GPU's eighth of 1 000 000 seeds): 125000 x 4096 B text-like seeds; ft,fn,fo; pattern od; cross-seed donor pool "
+           "(4096 windows of 2048 B per GPU, all-gathered over NCCL) for fo"),
     "c2": (10000, 4096, "bin", None, {"od": 1, "nd": 2, "bu": 1, "sk": 2, "sz": 2, "cs": 1, "ar": 1, "cp": 1, "co": 0, "nu": 0},
            "C2: 10000 x 4096 B uniform-random seeds; all 41 mutators at the reference's default priorities; default patterns"),
 }
@@ -53,7 +59,7 @@ def ncu_traffic(workload, fused):
     return tot or None
 
 
-TRAFFIC_PROFILE = {True: "fused_r1c.txt", False: "apply_r1b.txt"}
+TRAFFIC_PROFILE = {True: "fused_r2c.txt", False: "apply_r1b.txt"}
 
 
 def peak_hbm():
@@ -122,7 +128,12 @@ def make_corpus_device(torch, kind, n, size, dev, seed):
         import numpy as np
         r = corpus.rng(seed)
         distinct = 64 if kind == "markup" else 256
-        docs = corpus.uniform_corpus(seed, distinct, size, "markup") if kind == "markup" else [corpus.numeric_text(r, size) for _ in range(distinct)]
+        if kind == "markup":
+            docs = corpus.uniform_corpus(seed, distinct, size, "markup")
+        elif kind == "text":
+            docs = [corpus.structured_text(r, size).ljust(size, b" ")[:size] for _ in range(distinct)]
+        else:
+            docs = [corpus.numeric_text(r, size) for _ in range(distinct)]
         base = np.frombuffer(b"".join(docs), dtype=np.uint8)
         t = torch.from_numpy(base.copy()).to(dev)
         reps = (n + distinct - 1) // distinct
@@ -131,22 +142,14 @@ def make_corpus_device(torch, kind, n, size, dev, seed):
     return data, off
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local, n_override=0, want_e2e=True, sampler=None):
+    """W warm-up steps + K timed steps of one workload on this rank's GPU; returns the fields of the JSON line (rank 0) or None"""
     import erlamsa_b200
     from erlamsa_b200 import _native as N
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    n_cases, size, kind, muts, pats, desc = WORKLOADS[args.workload]
-    if args.cases:
-        n_cases = args.cases
+    n_cases, size, kind, muts, pats, desc = WORKLOADS[workload]
+    if n_override:
+        n_cases = n_override
     if muts is None:
         muts = {c: p for c, p in erlamsa_b200.default_mutations() if c in erlamsa_b200.supported_mutations()}
     else:
@@ -154,32 +157,49 @@ def run_ours(args):
     data, off = make_corpus_device(torch, kind, n_cases, size, dev, 0xE21A0003 + rank)
     data_bytes = n_cases * size
     out_cap = data_bytes + data_bytes // 12 + 512 * n_cases + (256 << 20)   # output slots (input + 1/16 slack) + overflow region
+    base_opts = {"mutations": muts, "patterns": pats, "seed": (1, 2, 3), "rng": args.rng, "scratch_bytes": 512 << 20}
+    if workload == "c2":   # repeat mutators compounded by nd/bu rounds: cap a case at 128 KiB = 32 x its seed (flagged, not dropped)
+        base_opts.update({"scratch_bytes": 8 << 30, "max_case_out": 128 << 10})
+        out_cap += 4 << 30
+    if workload == "c4":   # re-serialised documents and their literals live in scratch; pump / repeat may double a document
+        base_opts.update({"scratch_bytes": 16 << 30, "max_case_out": 4 << 20})
+        out_cap += 8 << 30
+    if workload == "c5":   # fuse splices are at most twice a block
+        base_opts.update({"scratch_bytes": 4 << 30, "max_case_out": 1 << 20})
+        out_cap += 2 << 30
     d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
     d_out_off = torch.empty(n_cases + 1, dtype=torch.int64, device=dev)
     d_out_len = torch.empty(n_cases, dtype=torch.int64, device=dev)
-    eng = erlamsa_b200.Engine(local)
-    base_opts = {"mutations": muts, "patterns": pats, "seed": (1, 2, 3), "rng": args.rng, "scratch_bytes": 512 << 20}
-    if args.workload == "c2":   # repeat mutators compounded by nd/bu rounds: cap a case at 128 KiB = 32 x its seed (flagged, not dropped)
-        base_opts.update({"scratch_bytes": 8 << 30, "max_case_out": 128 << 10})
-        out_cap += 4 << 30
-        d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
-    if args.workload == "c4":   # re-serialised documents and their literals live in scratch; pump / repeat may double a document
-        base_opts.update({"scratch_bytes": 16 << 30, "max_case_out": 4 << 20})
-        out_cap += 8 << 30
-        d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    # config C5: the one exchange step of the path -- every GPU samples donor windows from its shard, the pools are all-gathered
+    donors = None
+    coll_ms, coll_bytes = [], 0
+    if workload == "c5":
+        from erlamsa_b200.donors import DEFAULT_DONORS, DEFAULT_STRIDE, all_gather_pool
+        d_pool = torch.zeros((DEFAULT_DONORS, DEFAULT_STRIDE), dtype=torch.uint8, device=dev)
+        d_len = torch.zeros((DEFAULT_DONORS,), dtype=torch.int32, device=dev)
+        donors = (d_pool, d_len)
+        coll_bytes = (world - 1) * (d_pool.numel() + 4 * d_len.numel())     # bytes this GPU receives over NVLink per step
 
-    def step(i):
+    def step(i, timed=False):
         o = dict(base_opts)
         o["first_case"] = 1 + (rank + world * i) * n_cases       # every rank / step gets its own window of case ids
+        if donors is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            eng.sample_donors(data.data_ptr(), off.data_ptr(), n_cases, donors[0].shape[0], donors[0].shape[1], donors[0].data_ptr(), donors[1].data_ptr(), stream.cuda_stream)
+            e0.record(stream)
+            gp, gl = all_gather_pool(donors[0], donors[1])
+            e1.record(stream)
+            o["donor_pool"] = (gp.data_ptr(), gl.data_ptr(), gp.shape[0], gp.shape[1])
+            st = eng.fuzz_batch_device(o, data.data_ptr(), off.data_ptr(), n_cases, data_bytes, n_cases, d_out.data_ptr(), out_cap,
+                                       d_out_off.data_ptr(), d_out_len.data_ptr(), 0, stream.cuda_stream)
+            if timed:
+                coll_ms.append(e0.elapsed_time(e1))
+            return st
         return eng.fuzz_batch_device(o, data.data_ptr(), off.data_ptr(), n_cases, data_bytes, n_cases, d_out.data_ptr(), out_cap,
                                      d_out_off.data_ptr(), d_out_len.data_ptr(), 0, stream.cuda_stream)
 
-    sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get("EB200_BENCH_NO_SAMPLER"):
-        sampler.start()
-        time.sleep(0.5)
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
@@ -190,8 +210,8 @@ def run_ours(args):
     ev0.record(stream)
     apply_ms, decide_ms, scan_ms, launches, bytes_out = [], [], [], 0, 0
     flagged = {"unsupported": 0, "died": 0, "overflow": 0}
-    for i in range(args.steps):
-        st = step(args.warmup + i)
+    for i in range(steps):
+        st = step(warmup + i, timed=True)
         apply_ms.append(st.ms_apply); decide_ms.append(st.ms_decide); scan_ms.append(st.ms_scan)
         launches += st.kernels_launched; bytes_out += st.bytes_out
         flagged["unsupported"] += st.n_unsupported; flagged["died"] += st.n_died; flagged["overflow"] += st.n_overflow
@@ -201,20 +221,53 @@ def run_ours(args):
     if os.environ.get("EB200_BENCH_VERBOSE"):
         print("per-step kernel ms:", " ".join("%.3f" % x for x in decide_ms), file=sys.stderr)
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if (sampler is not None and rank == 0) else None
+    nflag = flagged["unsupported"] + flagged["overflow"]
     if world > 1:
-        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        t = torch.tensor([ms, float(nflag)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        ms = float(t[0].item()); nflag = int(t[1].item())
         dist.barrier()
     out_len_sum = int(d_out_len.sum().item())
 
+    # ---- parity sample: case ids of the LAST timed step, re-run through the oracle on the host (checker only, after the clock)
+    parity = None
+    if rank == 0 and not args.no_parity and workload != "c5":
+        import numpy as np
+        import oracle_lib
+        r = np.random.Generator(np.random.PCG64(12345))
+        n_s = min(args.parity_cases, n_cases)
+        ks = sorted(int(k) for k in r.choice(n_cases, size=n_s, replace=False))
+        last_first = 1 + (rank + world * (warmup + steps - 1)) * n_cases
+        offs = d_out_off[ks].cpu().tolist(); lens = d_out_len[ks].cpu().tolist()
+        oo = oracle_lib.make_opts(seed=(1, 2, 3), mutations=muts, patterns=pats, max_case_out=base_opts.get("max_case_out", 0))
+        bad, checked, skipped = 0, 0, 0
+        for k, o_, l_ in zip(ks, offs, lens):
+            blob = bytes(data[k * size:(k + 1) * size].cpu().numpy().tobytes())
+            # case I reads blob (I-1) mod n_blobs: hand the oracle a one-blob corpus and the same case number
+            want, wm = oracle_lib.fuzzer([blob], opts=oo, n_cases=1, first_case=last_first + k)
+            got = bytes(d_out[o_:o_ + l_].cpu().numpy().tobytes())
+            if wm[0].status != 0:
+                skipped += 1
+                continue
+            checked += 1
+            if got != want[0]:
+                # a case the engine flagged comes back unchanged: not a mismatch, but not a mutated case either
+                if got == blob and (flagged["unsupported"] or flagged["overflow"]):
+                    skipped += 1; checked -= 1
+                else:
+                    bad += 1
+        parity = {"checked": checked, "mismatches": bad, "skipped_flagged_or_capped": skipped, "against": "oracle (C++ restatement, pinned to the reference's own source by tests/golden/reference_vectors.json)"}
+
     # ---- e2e: the C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
-    if not args.no_e2e:
+    if want_e2e and not args.no_e2e:
         e2e_cases = min(n_cases, args.e2e_cases)
         hb = torch.empty(e2e_cases * size + 64, dtype=torch.uint8, pin_memory=True)
         hb[: e2e_cases * size].copy_(data[: e2e_cases * size])
         hoff = (C.c_uint64 * (e2e_cases + 1))(*[i * size for i in range(e2e_cases + 1)])
-        hout = torch.empty(e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + ((3 << 30) if args.workload == "c2" else (128 << 20)),
+        hout = torch.empty(e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + ((3 << 30) if workload == "c2" else (128 << 20)),
                            dtype=torch.uint8, pin_memory=True)
         ho_off = (C.c_uint64 * (e2e_cases + 1))(); ho_len = (C.c_uint64 * e2e_cases)()
         st2 = N.Stats()
@@ -229,54 +282,99 @@ def run_ours(args):
             assert rc == 0, rc
             if i > 0:
                 times.append(t1 - t0)
-            launches_e2e = st2.kernels_launched
         dt = max(times)
         if world > 1:
             t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         e2e = {"value": e2e_cases * world / dt, "unit": "cases/s", "h2d_bytes_per_step": e2e_cases * size + 8 * (e2e_cases + 1),
                "d2h_bytes_per_step": int(sum(ho_len)) + 16 * e2e_cases + 8, "cases_per_step": e2e_cases * world,
-               "note": "eb200_fuzz_batch_into: pinned host corpus -> H2D -> decide/scan/apply -> D2H of packed outputs, offsets and lengths"}
-
+               "note": "eb200_fuzz_batch_into: pinned host corpus -> H2D -> eb_case_kernel -> D2H of outputs, offsets and lengths"}
+        del hb, hout
+    del d_out, data
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    total_cases = n_cases * world * args.steps
+        return None
+    total_cases = n_cases * world * steps
     peak, peak_src = peak_hbm()
-    # algorithmic bytes of the apply kernel per launch: len_in + len_out + 16 per case
+    # algorithmic bytes of the dominant kernel per launch: len_in + len_out + 16 per case
     alg_bytes = data_bytes + out_len_sum + 16 * n_cases
     avg_apply = sum(apply_ms) / len(apply_ms)
-    fused = avg_apply == 0.0          # single-pass mode: the decide kernel executes the edit scripts itself
+    fused = avg_apply == 0.0          # single-pass mode: one kernel decides and moves the bytes
     dom_ms = sum(decide_ms) / len(decide_ms) if fused else avg_apply
-    dom_kernel = "eb_decide_kernel (single pass: decide + copy)" if fused else "eb_apply_kernel"
+    dom_kernel = "eb_case_kernel (single pass: decide + copy)" if fused else "eb_apply_kernel"
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     line = {
-        "metric": "mutated testcases/sec", "value": total_cases / (ms * 1e-3), "unit": "cases/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "metric": "mutated testcases/sec", "value": (total_cases - nflag) / (ms * 1e-3), "unit": "cases/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": desc, "cases_per_gpu_per_step": n_cases, "seed_bytes": size, "rng": args.rng,
                    "l2_policy": "inputs larger than L2 (%.2f GB in + %.2f GB out per step, 126 MB L2)" % (data_bytes / 1e9, out_len_sum / 1e9),
-                   "parallelism": "cases sharded by id, no collective"},
-        "gb_per_s_mutated": (data_bytes + out_len_sum) * world * args.steps / (ms * 1e-3) / 1e9,
+                   "parallelism": "cases sharded by id, no collective" if workload != "c5" else "cases sharded by id; one all-gather of the donor pool per step"},
+        "gb_per_s_mutated": (data_bytes + out_len_sum) * world * steps / (ms * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args.workload, fused) if not args.cases else None,
+                     "traffic": ncu_traffic(workload, fused) if not n_override else None,
                      "traffic_source": "ncu --set full capture, profiles/" + TRAFFIC_PROFILE[bool(fused)],
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": dom_ms},
         "kernel_ms": {"decide": sum(decide_ms) / len(decide_ms), "scan": sum(scan_ms) / len(scan_ms), "apply": avg_apply},
         "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
-        # rank 0's cases the engine did not mutate: paths without a device implementation (output = input, reported per
-        # case in eb200_meta.status), worker crashes the reference has too, per-case output cap
-        "flagged_cases": dict(flagged, of=n_cases * args.steps),
+        # cases the engine did not mutate (paths without a device implementation, per-case output cap: output = input, reported
+        # per case in eb200_meta.status) are NOT counted in `value`; worker crashes the reference has too (died) are
+        "flagged_cases": dict(flagged, of=n_cases * steps, note="rank 0; unsupported + overflow are subtracted from value"),
     }
-    if not args.no_cpu:
+    if parity is not None:
+        line["parity_sample"] = parity
+    if workload == "c5":
+        cm = sum(coll_ms) / max(len(coll_ms), 1)
+        line["collective"] = {"op": "all_gather (NCCL) of the donor pool + lengths", "ms_per_step": cm, "share_of_step": cm / (ms / steps),
+                              "nvlink_bytes_received_per_gpu_per_step": coll_bytes, "donors_per_gpu": 4096, "window_bytes": 2048}
+    return line
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import erlamsa_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    eng = erlamsa_b200.Engine(local)
+    sampler = ClockSampler(local)
+    if rank == 0 and not os.environ.get("EB200_BENCH_NO_SAMPLER"):
+        sampler.start()
+        time.sleep(0.5)
+    line = measure(torch, dist, eng, args, args.workload, args.steps, args.warmup, rank, world, local, n_override=args.cases, sampler=sampler)
+    if rank == 0 and not args.no_cpu:
+        n_cases, size, kind, muts, pats, desc = WORKLOADS[args.workload]
+        muts = {c: 1 for c in muts} if muts is not None else {c: p for c, p in erlamsa_b200.default_mutations() if c in erlamsa_b200.supported_mutations()}
         line["cpu_baseline"] = cpu_baseline(args, size, kind, muts, pats, threads=1, budget_s=12.0)
-    print(json.dumps(line))
+    # the other configs, made driver-visible: short runs, value net of flagged cases, the all-threads CPU port beside each
+    if args.workload == "c3" and not args.no_extra and not args.cases:
+        extra = {}
+        for wl, n_x in (("c2", 0), ("c4", 0)):
+            x = measure(torch, dist, eng, args, wl, 2, 3, rank, world, local, n_override=n_x, want_e2e=False)
+            if rank == 0:
+                n_cases, size, kind, muts, pats, desc = WORKLOADS[wl]
+                muts = {c: 1 for c in muts} if muts is not None else {c: p for c, p in erlamsa_b200.default_mutations() if c in erlamsa_b200.supported_mutations()}
+                cb = cpu_baseline(args, size, kind, muts, pats, threads=os.cpu_count() or 1, budget_s=6.0)
+                extra[wl] = {"workload": x["config"]["workload"], "value": x["value"], "unit": "cases/s", "ms_per_step": x["ms_per_step"], "steps": 2, "warmup": 3,
+                             "gb_per_s_mutated": x["gb_per_s_mutated"], "hbm_frac": x["roofline"]["frac"], "flagged_cases": x["flagged_cases"],
+                             "parity_sample": x.get("parity_sample"), "cpu_all_threads": cb, "ratio_vs_cpu_all_threads": x["value"] / cb["value"]}
+        if rank == 0:
+            line["extra_workloads"] = extra
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def cpu_corpus(kind, n, size, seed):
     import corpus
+    if kind == "text":
+        r = corpus.rng(seed)
+        return [corpus.structured_text(r, size).ljust(size, b" ")[:size] for _ in range(n)]
     return corpus.uniform_corpus(seed, n, size, kind)
 
 
@@ -364,6 +462,9 @@ def main():
     ap.add_argument("--rng", default="as183", choices=["as183", "philox"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short C2 / C4 runs appended to the default C3 line")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-cases", type=int, default=256)
     ap.add_argument("--e2e-cases", type=int, default=20000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()

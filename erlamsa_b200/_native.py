@@ -24,7 +24,8 @@ class Opts(C.Structure):
                 ("muta_pri", C.c_int32 * N_MUTATORS), ("pat_pri", C.c_int32 * N_PATTERNS),
                 ("gen_direct_pri", C.c_int32), ("gen_random_pri", C.c_int32),
                 ("ssrf_host", C.c_char * 64), ("ssrf_port", C.c_int32), ("rng_mode", C.c_int32),
-                ("first_case", C.c_uint64), ("max_case_out", C.c_uint64), ("scratch_bytes", C.c_uint64)]
+                ("first_case", C.c_uint64), ("max_case_out", C.c_uint64), ("scratch_bytes", C.c_uint64),
+                ("donor_pool", C.c_void_p), ("donor_len", C.c_void_p), ("n_donors", C.c_uint64), ("donor_stride", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 class Meta(C.Structure):
@@ -73,6 +74,7 @@ def lib():
     L.eb200_fuzz_batch_into.argtypes = [vp, C.POINTER(Opts), vp, vp, C.c_uint64, C.c_uint64,
                                         vp, C.c_uint64, vp, vp, vp, C.POINTER(Stats)]
     L.eb200_free.argtypes = [vp]
+    L.eb200_sample_donors.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, vp]
     for f in ("eb200_mutator_code", "eb200_pattern_code", "eb200_strerror", "eb200_version"):
         getattr(L, f).restype = C.c_char_p
     L.eb200_last_cuda_error.restype = C.c_char_p
@@ -86,4 +88,5 @@ EXPORTED_SYMBOLS = [
     "eb200_fuzz_batch_device", "eb200_mutator_code", "eb200_mutator_default_pri", "eb200_mutator_supported",
     "eb200_pattern_code", "eb200_pattern_default_pri", "eb200_pattern_supported",
     "eb200_strerror", "eb200_last_cuda_error", "eb200_version",
+    "eb200_sample_donors", "eb200_debug_case_times", "eb200_debug_mutator_times",
 ]

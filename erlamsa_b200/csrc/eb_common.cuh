@@ -89,6 +89,8 @@ struct BatchParams {
     uint64_t max_case_out;
     int32_t ssrf_port;
     char ssrf_host[64];
+    // cross-seed donor pool of sed_fuse_old (config C5), device pointers
+    const uint8_t* donor_pool; const uint32_t* donor_len; uint64_t n_donors; uint32_t donor_stride;
 };
 
 // ---- arenas (device) -- bump allocated with atomics; `overflow` is sticky

@@ -447,6 +447,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         int64_t ts0 = (int64_t)par.erand(99999), ts1 = (int64_t)par.erand(99999), ts2 = (int64_t)par.erand(99999);
         c.rng.mode = bp.rng_mode; c.rng.key = bp.philox_key; c.rng.ctr_hi = I;
         c.rng.seed(ts0, ts1, ts2);
+        ws->donor = (uint64_t)(ts0 * 31 + ts1 * 17 + ts2);
         // fresh per-case state (CurMuta is not carried between cases, reference src/erlamsa_main.erl:223-235)
         ws->status = CASE_OK; ws->reason = 0; ws->n_used = 0; ws->n_failed = 0; ws->noseg = 0; ws->olen = 0;
         ws->st_n[0] = ws->st_n[1] = 0; ws->fo_has = 0; ws->nwrap = 0; ws->rrun_n = 0; ws->ntseg = 0; ws->tlen = 0; ws->nvseg = 0; ws->vlen = 0; ws->vchunked = 0;

@@ -171,6 +171,7 @@ static int compute_batch_params(const eb200_opts* o, uint64_t n_blobs, uint64_t 
     if (bp.max_case_out > 0x7fffffffull) bp.max_case_out = 0x7fffffffull;
     bp.ssrf_port = o->ssrf_port;
     memcpy(bp.ssrf_host, o->ssrf_host, 64);
+    bp.donor_pool = o->donor_pool; bp.donor_len = o->donor_len; bp.n_donors = o->donor_pool && o->donor_len ? o->n_donors : 0; bp.donor_stride = o->donor_stride;
     return EB200_OK;
 }
 
@@ -670,6 +671,31 @@ static int fuzz_batch_host(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t
 }
 
 void eb200_free(void* p) { free(p); }
+
+// donor sampling for config C5: one warp per window
+__global__ void __launch_bounds__(256) eb_sample_donors_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ off, uint64_t n_blobs, uint64_t n_donors, uint32_t stride,
+                                                              uint8_t* __restrict__ pool, uint32_t* __restrict__ lens) {
+    uint64_t d = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_donors) return;
+    uint64_t b = (unsigned __int128)d * n_blobs / n_donors;
+    uint64_t len = off[b + 1] - off[b];
+    uint32_t wlen = (uint32_t)(len < stride ? len : stride);
+    uint64_t start = ((d * 2654435761ull) & 0xffffffffull) % (len - wlen + 1);
+    const uint8_t* src = data + off[b] + start;
+    uint8_t* dst = pool + d * stride;
+    for (uint32_t i = threadIdx.x & 31; i < wlen; i += 32) dst[i] = src[i];
+    if ((threadIdx.x & 31) == 0) lens[d] = wlen;
+}
+int eb200_sample_donors(eb200_ctx* ctx, const uint8_t* d_data, const uint64_t* d_off, uint64_t n_blobs, uint64_t n_donors, uint32_t stride,
+                        uint8_t* d_pool, uint32_t* d_len, void* stream) {
+    if (!ctx || !d_data || !d_off || !d_pool || !d_len || n_blobs == 0 || stride == 0) return EB200_ERR_ARG;
+    if (n_donors == 0) return EB200_OK;
+    CK(cudaSetDevice(ctx->device));
+    uint64_t threads = n_donors * 32;
+    eb_sample_donors_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_data, d_off, n_blobs, n_donors, stride, d_pool, d_len);
+    CK(cudaGetLastError());
+    return EB200_OK;
+}
 
 // profiling aid (EB200_CASE_TIMES=1): microseconds the general per-case program spent on each case of the last launch
 // (0 for cases the front warps decided); returns the number of entries copied

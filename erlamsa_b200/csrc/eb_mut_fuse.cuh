@@ -91,6 +91,58 @@ EB_DEV uint32_t fuse_classify(FuseSide& sd, const uint32_t* src, uint32_t k, uin
     return run - base;
 }
 
+// ---- one small node per lane (see fuse_device, path 1)
+constexpr uint32_t FUSE_K = 24;
+struct SmallSide {
+    uint32_t pos[FUSE_K];      // suffix positions in list order
+    uint8_t ch[FUSE_K];        // first byte of each live suffix
+    uint8_t live[FUSE_K];      // 0: the [] suffix (contributes nothing), 1: placed, 2: the dropped special
+    uint32_t n;
+    uint8_t cbyte[FUSE_K];     // classes in ascending byte order (a class whose only member was dropped has size 0)
+    uint8_t csize[FUSE_K];
+    uint8_t cstart[FUSE_K];    // start of the class inside this node's output
+    uint32_t ncls, nplaced;
+};
+__device__ __forceinline__ void small_side_load(SmallSide& s, const uint32_t* src, uint32_t k, const uint8_t* data, uint32_t len) {
+    s.n = k;
+    int special = -1;
+    for (uint32_t i = 0; i < k; i++) {
+        uint32_t p = src[i]; s.pos[i] = p;
+        bool lv = p < len;
+        s.live[i] = lv ? 1 : 0; s.ch[i] = lv ? data[p] : 0;
+        if (lv && p + 1 == len && special < 0) special = (int)i;
+    }
+    // the suffix holding only the block's last byte is dropped when it is the FIRST of its class ([[]] -> [], :68-70)
+    if (special >= 0) {
+        bool before = false;
+        for (int i = 0; i < special; i++) before |= s.live[i] && s.ch[i] == s.ch[special];
+        if (!before) s.live[special] = 2;
+    }
+}
+__device__ __forceinline__ void small_side_classes(SmallSide& s) {
+    s.ncls = 0; s.nplaced = 0;
+    int last = -1;
+    for (;;) {
+        int best = 256;
+        for (uint32_t i = 0; i < s.n; i++) if (s.live[i] && (int)s.ch[i] > last && (int)s.ch[i] < best) best = s.ch[i];
+        if (best == 256) break;
+        uint32_t cnt = 0;
+        for (uint32_t i = 0; i < s.n; i++) cnt += (s.live[i] == 1 && s.ch[i] == best) ? 1u : 0u;
+        s.cbyte[s.ncls] = (uint8_t)best; s.csize[s.ncls] = (uint8_t)cnt; s.cstart[s.ncls] = (uint8_t)s.nplaced;
+        s.ncls++; s.nplaced += cnt; last = best;
+    }
+}
+__device__ __forceinline__ int small_side_find(const SmallSide& s, uint32_t byte) {
+    for (uint32_t i = 0; i < s.ncls; i++) if (s.cbyte[i] == byte) return (int)i;
+    return -1;
+}
+// classes ascending, inside a class the LAST arrival first (char_suffixes prepends)
+__device__ __forceinline__ void small_side_write(const SmallSide& s, uint32_t* dst) {
+    uint32_t w = 0;
+    for (uint32_t ci = 0; ci < s.ncls; ci++)
+        for (int i = (int)s.n - 1; i >= 0; i--) if (s.live[i] == 1 && s.ch[i] == s.cbyte[ci]) dst[w++] = s.pos[i] + 1;
+}
+
 // find_jump_points/2 :103-128 + any_position_pair/1 :73-77
 EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb, uint32_t& from, uint32_t& to) {
     Rng& g = c.rng;
@@ -118,43 +170,55 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
             uint32_t e = ncur;
             const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
             while (e > 0) {
-                // (1) a run of nodes with at most one suffix on each side (what random data degenerates to after two
-                //     levels): one node per lane, same classification rules written out for the one-element lists
+                // (1) a run of SMALL nodes (at most FUSE_K suffixes on each side -- what a level degenerates to after the
+                //     first split or two): one node per LANE, the same classification rules written out serially per lane
+                //     (classes ascending by byte, newest first inside a class, the [[]] -> [] drop, the {Char, []} quirk).
+                //     Measured before this path existed: ft on a 4 KiB random block 24 ms, nearly all of it in the ~256
+                //     sixteen-by-sixteen nodes of the second level taken one node per warp step (profiles/tc_c2_r2a.txt).
                 bool valid = (uint32_t)l < e;
-                FNode nd; nd.fo = nd.to = 0; nd.fc = nd.tc = 2;
+                FNode nd; nd.fo = nd.to = 0; nd.fc = nd.tc = FUSE_K + 1;
                 if (valid) nd = ND[cur][e - 1 - (uint32_t)l];
-                uint32_t sm = __ballot_sync(0xffffffffu, valid && nd.fc <= 1 && nd.tc <= 1);
+                uint32_t sm = __ballot_sync(0xffffffffu, valid && nd.fc <= FUSE_K && nd.tc <= FUSE_K);
                 uint32_t runlen = sm == 0xffffffffu ? 32u : (uint32_t)__ffs(~sm) - 1u;
                 if (runlen > 0) {
                     bool act = (uint32_t)l < runlen;
-                    uint32_t fa = 0, tb = 0, fval = 0, tval = 0, tsize = 0; bool quirk = false, child = false;
+                    SmallSide A, B;
+                    uint32_t nquirk = 0, nchild = 0;
                     if (act) {
-                        bool ha = nd.fc == 1; uint32_t pa = ha ? F[cur][nd.fo] : na; ha = ha && pa < na;
-                        bool hb = nd.tc == 1; uint32_t pb = hb ? T[cur][nd.to] : nb; hb = hb && pb < nb;
-                        uint32_t cha = ha ? a[pa] : 0x100u, chb = hb ? b[pb] : 0x200u;
-                        bool a_drop = ha && pa + 1 == na, b_drop = hb && pb + 1 == nb;
-                        if (ha && !a_drop) { fval = pa + 1; fa = 1; }
-                        if (hb && !b_drop) { tval = pb + 1; tb = 1; }
-                        if (a_drop) quirk = true;                                  // {_Char, []} -> [[[]], []] (:91-93)
-                        else if (ha && cha == chb) { child = true; tsize = tb; }
+                        small_side_load(A, F[cur] + nd.fo, nd.fc, a, na);
+                        small_side_load(B, T[cur] + nd.to, nd.tc, b, nb);
+                        small_side_classes(A); small_side_classes(B);
+                        for (uint32_t ci = 0; ci < A.ncls; ci++) {
+                            if (A.csize[ci] == 0) { nquirk++; nchild++; }
+                            else if (small_side_find(B, A.cbyte[ci]) >= 0) nchild++;
+                        }
                     }
-                    uint32_t fadd = fa + (quirk ? 1u : 0u), tadd = tb + (quirk ? 1u : 0u), cadd = (quirk || child) ? 1u : 0u;
-                    uint32_t fpre = fadd, tpre = tadd;
+                    uint32_t fadd = act ? A.nplaced + nquirk : 0u, tadd = act ? B.nplaced + nquirk : 0u, cadd = act ? nchild : 0u;
+                    uint32_t fpre = fadd, tpre = tadd, cpre = cadd;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, fpre, o), y = __shfl_up_sync(0xffffffffu, tpre, o); if (l >= o) { fpre += x; tpre += y; } }
-                    uint32_t ftot = __shfl_sync(0xffffffffu, fpre, 31), ttot = __shfl_sync(0xffffffffu, tpre, 31);
-                    uint32_t cm = __ballot_sync(0xffffffffu, cadd != 0);
-                    uint32_t ctot = (uint32_t)__popc(cm);
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t x = __shfl_up_sync(0xffffffffu, fpre, o), y = __shfl_up_sync(0xffffffffu, tpre, o), z = __shfl_up_sync(0xffffffffu, cpre, o);
+                        if (l >= o) { fpre += x; tpre += y; cpre += z; }
+                    }
+                    uint32_t ftot = __shfl_sync(0xffffffffu, fpre, 31), ttot = __shfl_sync(0xffffffffu, tpre, 31), ctot = __shfl_sync(0xffffffffu, cpre, 31);
                     if ((uint64_t)fo + ftot > fcap || (uint64_t)to + ttot > tcap || (uint64_t)nnext + ctot > ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
-                    uint32_t f0 = fo + fpre - fadd, t0 = to + tpre - tadd;
-                    if (fa) F[nx][f0] = fval;
-                    if (tb) T[nx][t0] = tval;
-                    if (quirk) { F[nx][f0 + fa] = na; T[nx][t0 + tb] = nb; }
-                    if (cadd) {
-                        FNode ch_n;
-                        if (quirk) { ch_n.fo = f0 + fa; ch_n.fc = 1; ch_n.to = t0 + tb; ch_n.tc = 1; }
-                        else { ch_n.fo = f0; ch_n.fc = 1; ch_n.to = t0; ch_n.tc = tsize; }
-                        ND[nx][nnext + (uint32_t)__popc(cm & ltm)] = ch_n;
+                    if (act) {
+                        uint32_t f0 = fo + fpre - fadd, t0 = to + tpre - tadd, c0 = nnext + cpre - cadd;
+                        small_side_write(A, F[nx] + f0);
+                        small_side_write(B, T[nx] + t0);
+                        uint32_t fq = f0 + A.nplaced, tq = t0 + B.nplaced;
+                        for (uint32_t ci = 0; ci < A.ncls; ci++) {
+                            FNode ch_n;
+                            if (A.csize[ci] == 0) {        // {_Char, []} -> [[[]], []]: the two empty suffixes, whatever B holds (:91-93)
+                                F[nx][fq] = na; T[nx][tq] = nb;
+                                ch_n.fo = fq; ch_n.fc = 1; ch_n.to = tq; ch_n.tc = 1; fq++; tq++;
+                                ND[nx][c0++] = ch_n; continue;
+                            }
+                            int bi = small_side_find(B, A.cbyte[ci]);
+                            if (bi < 0) continue;                                   // notfound
+                            ch_n.fo = f0 + A.cstart[ci]; ch_n.fc = A.csize[ci]; ch_n.to = t0 + B.cstart[bi]; ch_n.tc = B.csize[bi];
+                            ND[nx][c0++] = ch_n;
+                        }
                     }
                     fo += ftot; to += ttot; nnext += ctot; e -= runlen;
                     __syncwarp();
@@ -244,7 +308,12 @@ EB_DEV void mut_fuse(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutResult
         return;
     }
     // sed_fuse_old :404-427 -- remember/1 closure: the first call remembers H itself
-    if (!ws->fo_has) { ws->fo_has = 1; ws->fo_p = p; ws->fo_n = n; }
+    // (with a donor pool -- config C5 -- the first remembered block is a window of another seed, possibly of another GPU's
+    // shard; chosen from the thread seed so that the case's own draws stay the reference's)
+    if (!ws->fo_has) {
+        ws->fo_has = 1; ws->fo_p = p; ws->fo_n = n;
+        if (c.bp->donor_pool && c.bp->n_donors) { uint64_t d = ws->donor % c.bp->n_donors; ws->fo_p = c.bp->donor_pool + d * c.bp->donor_stride; ws->fo_n = c.bp->donor_len[d]; }
+    }
     const uint8_t* op = ws->fo_p; uint32_t on = ws->fo_n; uint32_t o1 = on / 2;
     if (!fuse_push(c, p, h1, op, o1)) { r.kind = RES_SAME; r.delta = 0; return; }          // a -> o
     uint32_t an; const uint8_t* ab = tseg_to_scratch(c, an);

@@ -48,6 +48,7 @@ struct WarpState {
     struct Wrap { uint32_t kind; uint32_t bits; uint32_t big; uint32_t tail_n; uint64_t field_pos; uint64_t mark; const uint8_t* tail_p; } wrap[8];
     int nwrap;
     const uint8_t* fo_p; uint32_t fo_n; int fo_has;
+    uint64_t donor;          // this case's donor index (thread seed hash, see mut_fuse)
     uint16_t sc[SC_MAX];
     uint32_t qpend;          // countdown of this warp's outstanding scan jobs (eb_jobs.cuh)
     uint32_t status; uint32_t reason;

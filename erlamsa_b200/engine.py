@@ -70,6 +70,12 @@ class Engine:
         outs = [raw[out_off[k]:out_off[k] + out_len[k]] for k in range(n_cases)]
         return outs, (list(meta)[:n_cases] if want_meta else None)
 
+    def sample_donors(self, d_data, d_off, n_blobs, n_donors, stride, d_pool, d_len, stream=0):
+        """Config C5: fill a donor pool (device addresses) with n_donors windows of the device-resident corpus."""
+        rc = N.lib().eb200_sample_donors(self._ctx, d_data, d_off, n_blobs, n_donors, stride, d_pool, d_len, stream or None)
+        if rc != 0:
+            raise self._err(rc)
+
     def fuzz_batch_device(self, opts, d_data, d_off, n_blobs, data_bytes, n_cases, d_out, out_capacity,
                           d_out_off, d_out_len, d_meta=0, stream=0):
         """Device path: all arguments are raw device addresses (ints), e.g. torch tensors' data_ptr()."""

@@ -96,4 +96,7 @@ def make_opts(opts=None):
         o.first_case = int(opts["first_case"])
     o.max_case_out = int(opts.get("max_case_out", 0))
     o.scratch_bytes = int(opts.get("scratch_bytes", 0))
+    if "donor_pool" in opts:      # (device address of the windows, device address of the lengths, count, stride) -- config C5
+        pool, lens, n, stride = opts["donor_pool"]
+        o.donor_pool, o.donor_len, o.n_donors, o.donor_stride = int(pool), int(lens), int(n), int(stride)
     return o

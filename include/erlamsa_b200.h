@@ -72,6 +72,16 @@ typedef struct eb200_opts {
                                                shard start when a corpus is split over GPUs) */
     uint64_t max_case_out;                  /* per-case output cap in bytes (0 = default 64 MiB) */
     uint64_t scratch_bytes;                 /* device scratch arena (0 = default: 4 x input bytes + 64 MiB) */
+    /* Cross-seed donor pool for `fo` (BASELINE config C5; NOT a reference option). The reference's sed_fuse_old starts out
+     * remembering the block it was first given (src/erlamsa_mutations.erl:404-427); with a pool the first remembered block of a
+     * case is donor number (31*S1 + 17*S2 + S3) mod n_donors, {S1,S2,S3} = the case's thread seed -- no draw of the case's
+     * stream is consumed. DEVICE pointers: n_donors windows of donor_stride bytes each, and their lengths. NULL / 0 = off.
+     * eb200_sample_donors fills a pool from a device-resident corpus; multi-GPU callers all-gather the per-GPU pools. */
+    const uint8_t*  donor_pool;
+    const uint32_t* donor_len;
+    uint64_t n_donors;
+    uint32_t donor_stride;
+    uint32_t reserved0;
 } eb200_opts;
 
 typedef struct eb200_meta {
@@ -121,6 +131,11 @@ int  eb200_fuzz_batch(eb200_ctx* ctx, const eb200_opts* opts,
                       const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases,
                       uint8_t** out_data, uint64_t* out_off, uint64_t* out_len,
                       eb200_meta* meta, eb200_stats* stats);
+/* Sample n_donors windows (each at most `stride` bytes) from a DEVICE-resident packed corpus into d_pool [n_donors * stride]
+ * and d_len [n_donors]: window d comes from blob floor(d * n_blobs / n_donors), starts at (d * 2654435761 mod 2^32) mod
+ * (len - wlen + 1) with wlen = min(len, stride). Asynchronous on `stream`. */
+int eb200_sample_donors(eb200_ctx* ctx, const uint8_t* d_data, const uint64_t* d_off, uint64_t n_blobs, uint64_t n_donors, uint32_t stride,
+                        uint8_t* d_pool, uint32_t* d_len, void* stream);
 void eb200_free(void* p);
 /* profiling aid: with EB200_CASE_TIMES=1 in the environment at eb200_init, microseconds the general per-case program spent on
  * each case of the last launch (0 for cases decided by the front warps). Returns the number of entries copied. */

@@ -54,6 +54,8 @@ struct Opts {
     int gen_random_pri = 1;
     std::string ssrf_host = "localhost";   // get_ssrf_ep/0 default, src/erlamsa_mutations.erl:697-702
     int ssrf_port = 51234;
+    // cross-seed donor pool for sed_fuse_old (BASELINE config C5; not a reference option, see fuse_old in mutations.hpp)
+    const uint8_t* donor_pool = nullptr; const uint32_t* donor_len = nullptr; uint64_t n_donors = 0; uint32_t donor_stride = 0;
     uint64_t max_case_out = 64ull << 20;   // not a reference option: the harness' guard against runaway repeats (cf. maxrunningtime)
     Opts() {
         for (int i = 0; i < M_COUNT; i++) muta_pri[i] = MUT_DEFAULT_PRI[i];

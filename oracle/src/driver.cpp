@@ -236,6 +236,7 @@ struct Fuzzer {
         meta.thread_seed[0] = ts[0]; meta.thread_seed[1] = ts[1]; meta.thread_seed[2] = ts[2];
         meta.generator = generator;
         Mutations m(rng, opts); m.snand_kind = muts.snand_kind;
+        m.thread_seed[0] = ts[0]; m.thread_seed[1] = ts[1]; m.thread_seed[2] = ts[2];
         Bin out;
         try {
             Blocks ll = generate(rng, input);
@@ -267,6 +268,7 @@ struct eo_opts_c {
     char ssrf_host[64];
     int32_t ssrf_port;
     uint64_t max_case_out;
+    const uint8_t* donor_pool; const uint32_t* donor_len; uint64_t n_donors; uint32_t donor_stride; uint32_t pad;
 };
 struct eo_meta_c {
     int32_t pattern, generator, n_used, n_failed;
@@ -284,6 +286,7 @@ static eo::Opts conv(const eo_opts_c* c) {
     o.gen_direct_pri = c->gen_direct_pri; o.gen_random_pri = c->gen_random_pri;
     o.ssrf_host = std::string(c->ssrf_host, strnlen(c->ssrf_host, 64)); o.ssrf_port = c->ssrf_port;
     if (c->max_case_out) o.max_case_out = c->max_case_out;
+    o.donor_pool = c->donor_pool; o.donor_len = c->donor_len; o.n_donors = c->n_donors; o.donor_stride = c->donor_stride;
     return o;
 }
 static void conv_meta(const eo::Meta& m, eo_meta_c* c) {

@@ -36,6 +36,7 @@ struct MutRes { Blocks ll; double delta = 0; };
 struct Mutations {
     Rng& rng; const Opts& opts;
     int snand_kind = 0;   // 0 nand, 1 or, 2 xor -- fixed when the table is built (:1313)
+    int64_t thread_seed[3] = {0, 0, 0};   // of the case being run (donor choice, see fuse_old)
     Mutations(Rng& r, const Opts& o) : rng(r), opts(o) {}
 
     // mutations/1 :1290-1332 -- building the table costs two draws
@@ -290,7 +291,16 @@ struct Mutations {
     }
     MutRes fuse_old(MutNode& node, const Blocks& ll) {
         const Bin& h = ll[0];
-        if (!node.has_block) { node.has_block = true; node.block = h; }
+        // remember/1: the closure starts out remembering H itself (:424-427). With a donor pool (config C5: windows of
+        // other seeds, all-gathered across GPUs) the FIRST remembered block is a donor instead -- chosen from the case's
+        // thread seed, so that no draw of the case's own stream is consumed and everything else stays the reference's.
+        if (!node.has_block) {
+            node.has_block = true; node.block = h;
+            if (opts.donor_pool && opts.n_donors) {
+                uint64_t d = (uint64_t)(thread_seed[0] * 31 + thread_seed[1] * 17 + thread_seed[2]) % opts.n_donors;
+                node.block = Bin((const char*)opts.donor_pool + d * opts.donor_stride, opts.donor_len[d]);
+            }
+        }
         Bin al1, al2, ol1, ol2; halve(h, al1, al2); halve(node.block, ol1, ol2);
         Bin a = fuse(rng, al1, ol1);
         Bin b = fuse(rng, ol2, al2);

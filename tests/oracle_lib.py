@@ -22,7 +22,8 @@ class Opts(C.Structure):
     _fields_ = [("seed", C.c_int64 * 3), ("blockscale", C.c_double),
                 ("muta_pri", C.c_int32 * 41), ("pat_pri", C.c_int32 * 10),
                 ("gen_direct_pri", C.c_int32), ("gen_random_pri", C.c_int32),
-                ("ssrf_host", C.c_char * 64), ("ssrf_port", C.c_int32), ("max_case_out", C.c_uint64)]
+                ("ssrf_host", C.c_char * 64), ("ssrf_port", C.c_int32), ("max_case_out", C.c_uint64),
+                ("donor_pool", C.c_void_p), ("donor_len", C.c_void_p), ("n_donors", C.c_uint64), ("donor_stride", C.c_uint32), ("pad", C.c_uint32)]
 
 
 class Meta(C.Structure):
@@ -68,7 +69,7 @@ def lib():
 
 
 def make_opts(seed=(1, 2, 3), mutations=None, patterns=None, blockscale=1.0, generators=None,
-              ssrf_host="localhost", ssrf_port=51234, max_case_out=0):
+              ssrf_host="localhost", ssrf_port=51234, max_case_out=0, donors=None):
     """mutations / patterns: None = reference defaults, else dict or list of (code, pri) -- the
     reference's `[{Code, Pri}]` option lists (src/erlamsa_main.erl:129,156)."""
     o = Opts()
@@ -90,6 +91,16 @@ def make_opts(seed=(1, 2, 3), mutations=None, patterns=None, blockscale=1.0, gen
     o.ssrf_host = ssrf_host.encode()
     o.ssrf_port = ssrf_port
     o.max_case_out = max_case_out
+    if donors is not None:
+        # donors = (windows: list of bytes, stride): the cross-seed pool of BASELINE config C5
+        wins, stride = donors
+        pool = b"".join(w.ljust(stride, b"\0") for w in wins)
+        o._pool = C.create_string_buffer(pool, len(pool))
+        o._lens = (C.c_uint32 * len(wins))(*[len(w) for w in wins])
+        o.donor_pool = C.cast(o._pool, C.c_void_p)
+        o.donor_len = C.cast(o._lens, C.c_void_p)
+        o.n_donors = len(wins)
+        o.donor_stride = stride
     return o
 
 
