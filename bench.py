@@ -263,12 +263,16 @@ def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local,
     # ---- e2e: the C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
     if want_e2e and not args.no_e2e:
-        e2e_cases = min(n_cases, args.e2e_cases)
-        hb = torch.empty(e2e_cases * size + 64, dtype=torch.uint8, pin_memory=True)
+        e2e_cases = min(n_cases, args.e2e_cases) if args.e2e_cases else n_cases
+        # host buffers: pinned and on the GPU's NUMA node (eb200_host_alloc), as the NIF's staging rings are
+        in_bytes = e2e_cases * size + 64
+        out_bytes = e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + ((3 << 30) if workload == "c2" else (128 << 20))
+        p_in = N.lib().eb200_host_alloc(eng._ctx, in_bytes)
+        p_out = N.lib().eb200_host_alloc(eng._ctx, out_bytes)
+        assert p_in and p_out, "pinned host allocation failed"
+        hb = torch.frombuffer((C.c_uint8 * in_bytes).from_address(p_in), dtype=torch.uint8)
         hb[: e2e_cases * size].copy_(data[: e2e_cases * size])
         hoff = (C.c_uint64 * (e2e_cases + 1))(*[i * size for i in range(e2e_cases + 1)])
-        hout = torch.empty(e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + ((3 << 30) if workload == "c2" else (128 << 20)),
-                           dtype=torch.uint8, pin_memory=True)
         ho_off = (C.c_uint64 * (e2e_cases + 1))(); ho_len = (C.c_uint64 * e2e_cases)()
         st2 = N.Stats()
         o = erlamsa_b200.make_opts(base_opts)
@@ -276,8 +280,8 @@ def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local,
         for i in range(args.e2e_steps + 1):
             o.first_case = 1 + (10_000 + rank + world * i) * n_cases
             t0 = time.perf_counter()
-            rc = N.lib().eb200_fuzz_batch_into(eng._ctx, C.byref(o), hb.data_ptr(), C.cast(hoff, C.c_void_p), e2e_cases, e2e_cases,
-                                               hout.data_ptr(), hout.numel(), C.cast(ho_off, C.c_void_p), C.cast(ho_len, C.c_void_p), None, C.byref(st2))
+            rc = N.lib().eb200_fuzz_batch_into(eng._ctx, C.byref(o), p_in, C.cast(hoff, C.c_void_p), e2e_cases, e2e_cases,
+                                               p_out, out_bytes, C.cast(ho_off, C.c_void_p), C.cast(ho_len, C.c_void_p), None, C.byref(st2))
             t1 = time.perf_counter()
             assert rc == 0, rc
             if i > 0:
@@ -285,10 +289,12 @@ def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local,
         dt = max(times)
         if world > 1:
             t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
-        e2e = {"value": e2e_cases * world / dt, "unit": "cases/s", "h2d_bytes_per_step": e2e_cases * size + 8 * (e2e_cases + 1),
-               "d2h_bytes_per_step": int(sum(ho_len)) + 16 * e2e_cases + 8, "cases_per_step": e2e_cases * world,
-               "note": "eb200_fuzz_batch_into: pinned host corpus -> H2D -> eb_case_kernel -> D2H of outputs, offsets and lengths"}
-        del hb, hout
+        h2d_b, d2h_b = e2e_cases * size + 8 * (e2e_cases + 1), int(sum(ho_len)) + 16 * e2e_cases + 8
+        e2e = {"value": e2e_cases * world / dt, "unit": "cases/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+               "cases_per_step": e2e_cases * world, "pcie_gb_per_s_each_way": [h2d_b / dt / 1e9, d2h_b / dt / 1e9], "numa_node_of_gpu": N.lib().eb200_numa_node(eng._ctx),
+               "note": "eb200_fuzz_batch_into: pinned NUMA-local host corpus -> H2D (chunks, 2 uploads ahead) -> eb_case_kernel -> D2H of outputs, offsets and lengths"}
+        del hb
+        N.lib().eb200_host_free(eng._ctx, p_in); N.lib().eb200_host_free(eng._ctx, p_out)
     del d_out, data
     torch.cuda.empty_cache()
     if rank != 0:
@@ -403,9 +409,10 @@ def cpu_run(blobs, muts, pats, n_cases, first_case, threads):
 
 def cpu_baseline(args, size, kind, muts, pats, threads, budget_s):
     blobs = cpu_corpus(kind, 64, size, 0xE21A0003)
-    dt, _ = cpu_run(blobs, muts, pats, 64 * threads, 1, threads)           # calibration
-    rate = 64 * threads / dt
-    n = max(64 * threads, int(rate * budget_s))
+    ncal = 64 * threads if threads == 1 else 4 * threads                   # calibration
+    dt, _ = cpu_run(blobs, muts, pats, ncal, 1, threads)
+    rate = ncal / dt
+    n = max(ncal, int(rate * budget_s))
     dt, _ = cpu_run(blobs, muts, pats, n, 1000, threads)
     return {"value": n / dt, "unit": "cases/s", "cores": threads, "kind": "port",
             "sample": "%d cases of the same workload (64 distinct %d-byte seeds reused), oracle C++ restatement, %d thread(s), %.1f s"
@@ -465,8 +472,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the short C2 / C4 runs appended to the default C3 line")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--parity-cases", type=int, default=256)
-    ap.add_argument("--e2e-cases", type=int, default=20000)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-cases", type=int, default=0, help="cases per e2e step (0 = the whole config)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -74,6 +74,10 @@ def lib():
     L.eb200_fuzz_batch_into.argtypes = [vp, C.POINTER(Opts), vp, vp, C.c_uint64, C.c_uint64,
                                         vp, C.c_uint64, vp, vp, vp, C.POINTER(Stats)]
     L.eb200_free.argtypes = [vp]
+    L.eb200_host_alloc.argtypes = [vp, C.c_uint64]
+    L.eb200_host_alloc.restype = vp
+    L.eb200_host_free.argtypes = [vp, vp]
+    L.eb200_numa_node.argtypes = [vp]
     L.eb200_sample_donors.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, vp]
     for f in ("eb200_mutator_code", "eb200_pattern_code", "eb200_strerror", "eb200_version"):
         getattr(L, f).restype = C.c_char_p
@@ -88,5 +92,5 @@ EXPORTED_SYMBOLS = [
     "eb200_fuzz_batch_device", "eb200_mutator_code", "eb200_mutator_default_pri", "eb200_mutator_supported",
     "eb200_pattern_code", "eb200_pattern_default_pri", "eb200_pattern_supported",
     "eb200_strerror", "eb200_last_cuda_error", "eb200_version",
-    "eb200_sample_donors", "eb200_debug_case_times", "eb200_debug_mutator_times",
+    "eb200_sample_donors", "eb200_debug_case_times", "eb200_debug_mutator_times", "eb200_host_alloc", "eb200_host_free", "eb200_numa_node",
 ]

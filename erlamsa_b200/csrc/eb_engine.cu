@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <cmath>
 #include <chrono>
+#include <sched.h>
+#include <cctype>
 #include "../../include/erlamsa_b200.h"
 #include "eb_fast.cuh"
 #include "eb_apply.cuh"
@@ -60,6 +62,8 @@ struct eb200_ctx {
     int front_depth = 32;         // fronts post while fewer than this many jobs are waiting in the ring (EB200_FRONT_DEPTH)
     int fronts = -1;              // this many decide 32 byte-mutator cases at a time, lane per case (EB200_FRONTS; -1 = chosen per batch), the rest are copy/scan workers
     DevBuf case_status, retry_list, case_usec;
+    int chunk_mb = 64, h2d_ahead = 2;      // host pipeline: bytes of input per chunk (EB200_CHUNK_MB), uploads queued ahead of the compute (EB200_H2D_AHEAD)
+    int numa_node = -1;                    // of the GPU (sysfs), -1 unknown
     bool want_case_times = false; uint64_t case_times_n = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // host-path pipeline (created on first use)
 };
@@ -202,6 +206,16 @@ int eb200_init(int device, eb200_ctx** out) {
     int fn = (int)f.size(); f.resize(192);
     if (cudaMemcpyToSymbol(c_funny, f.data(), sizeof(FunnyEntry) * 192) != cudaSuccess || cudaMemcpyToSymbol(c_funny_n, &fn, sizeof(int)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
     if (const char* v = getenv("EB200_MODE")) ctx->fused = strcmp(v, "twopass") != 0;
+    if (const char* v = getenv("EB200_CHUNK_MB")) { int k = atoi(v); if (k >= 4 && k <= 4096) ctx->chunk_mb = k; }
+    if (const char* v = getenv("EB200_H2D_AHEAD")) { int k = atoi(v); if (k >= 1 && k <= 16) ctx->h2d_ahead = k; }
+    {   // the GPU's NUMA node: /sys/bus/pci/devices/<domain:bus:dev.fn>/numa_node
+        char bdf[32] = {0};
+        if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) == cudaSuccess) {
+            for (char* c = bdf; *c; c++) *c = (char)tolower(*c);
+            std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/numa_node";
+            if (FILE* f = fopen(path.c_str(), "r")) { int nn = -1; if (fscanf(f, "%d", &nn) == 1) ctx->numa_node = nn; fclose(f); }
+        }
+    }
     if (const char* v = getenv("EB200_CASE_TIMES")) ctx->want_case_times = atoi(v) != 0;
     if (const char* v = getenv("EB200_THREADS")) { int k = atoi(v); if (k >= 64 && k <= CASE_THREADS && k % 32 == 0) ctx->threads = k; }
     if (const char* v = getenv("EB200_DECIDERS")) { int k = atoi(v); if (k >= 0 && k <= 32) ctx->deciders = k; }
@@ -508,9 +522,11 @@ int eb200_fuzz_batch(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* data
     return fuzz_batch_host(ctx, opts, data, off, n_blobs, n_cases, out_data, nullptr, 0, out_off, out_len, meta, stats);
 }
 // Chunked, copy/compute-overlapped variant of the host path: the corpus is uploaded in chunks of cases on a copy
-// stream while the previous chunk is being decided/applied on the compute stream and the one before that is being
-// downloaded on a third stream. Compute for consecutive chunks stays on ONE stream, so the per-batch arenas
-// (cases, segments, scratch) are reused safely; only PCIe traffic overlaps. Needs pinned host buffers to overlap.
+// stream (EB200_H2D_AHEAD chunks ahead of the compute) while earlier chunks are being decided on the compute stream and
+// downloaded on a third stream. Compute for consecutive chunks stays on ONE stream, so the per-batch arenas (scratch,
+// counters) are reused safely; only PCIe traffic overlaps. Needs pinned host buffers to overlap (eb200_host_alloc gives
+// NUMA-local ones). Every exit, error or not, drains all three streams before returning: the caller's buffers are never
+// the target of a DMA still in flight, and the events are always destroyed.
 static int fuzz_batch_host_pipelined(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases,
                                      uint8_t* user_out, uint64_t user_cap, uint64_t* out_off, uint64_t* out_len, eb200_meta* meta, eb200_stats* stats,
                                      uint64_t chunk) {
@@ -522,66 +538,82 @@ static int fuzz_batch_host_pipelined(eb200_ctx* ctx, const eb200_opts* opts, con
     if (!ctx->s_h2d) { CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
                        CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking)); }
     uint64_t nchunks = (n_cases + chunk - 1) / chunk;
-    std::vector<cudaEvent_t> ev_up(nchunks), ev_done(nchunks);
-    for (uint64_t j = 0; j < nchunks; j++) { CK(cudaEventCreateWithFlags(&ev_up[j], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_done[j], cudaEventDisableTiming)); }
-    CK(ctx->data.ensure(data_bytes + 64));
-    CK(ctx->off.ensure((n_blobs + 1) * 8));
-    CK(ctx->out_off.ensure((n_cases + nchunks + 1) * 8));
-    CK(ctx->out_len.ensure(n_cases * 8));
-    CK(ctx->meta.ensure(n_cases * sizeof(MetaDev)));
-    CK(ctx->out.ensure(data_bytes + data_bytes / 4 + (64ull << 20) * (nchunks + 2)));
-    auto t0 = std::chrono::steady_clock::now();
-    CK(cudaMemcpyAsync(ctx->off.p, off, (n_blobs + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
-    auto upload = [&](uint64_t j) -> cudaError_t {
-        uint64_t k0 = j * chunk, k1 = std::min(n_cases, k0 + chunk);
-        uint64_t lo = off[b0 + k0], hi = off[b0 + k1];
-        cudaError_t e = cudaSuccess;
-        if (hi > lo) e = cudaMemcpyAsync((uint8_t*)ctx->data.p + lo, data + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_h2d);
-        if (e == cudaSuccess) e = cudaEventRecord(ev_up[j], ctx->s_h2d);
-        return e;
-    };
-    CK(upload(0));
-    uint64_t base = 0; uint32_t launches = 0; int rc = EB200_OK;
+    std::vector<cudaEvent_t> ev_up(nchunks, nullptr), ev_done(nchunks, nullptr);
     std::vector<uint64_t> bases(nchunks + 1, 0);
-    for (uint64_t j = 0; j < nchunks && rc == EB200_OK; j++) {
-        if (j + 1 < nchunks) CK(upload(j + 1));                          // next chunk's upload overlaps this chunk's compute
-        uint64_t k0 = j * chunk, k1 = std::min(n_cases, k0 + chunk), nc = k1 - k0;
-        CK(cudaStreamWaitEvent(ctx->s_comp, ev_up[j], 0));
-        eb200_opts o = *opts; o.first_case = first + k0;
-        BatchParams bp; rc = compute_batch_params(&o, n_blobs, nc, bp);
-        if (rc) break;
-        uint64_t* d_off_j = (uint64_t*)ctx->out_off.p + k0 + j;          // nc + 1 entries per chunk
-        uint64_t total = 0;
-        if (ctx->fused) {
-            rc = run_fused(ctx, bp, &o, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, true, nullptr, 0, base, d_off_j,
-                           (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches);
-            if (rc) break;
-            if (base + total > user_cap) { rc = EB200_ERR_NOMEM; break; }
-        } else {
-            rc = run_decide_scan(ctx, bp, &o, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, d_off_j,
-                                 (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches);
-            if (rc) break;
-            if (base + total > user_cap) { rc = EB200_ERR_NOMEM; break; }
-            if (base + total + 64 > ctx->out.cap) {                          // rare: the estimate was too small -- drain and grow
-                CK(cudaStreamSynchronize(ctx->s_d2h)); CK(cudaStreamSynchronize(ctx->s_comp));
-                CK(ctx->out.ensure((base + total) * 2 + 64));
-            }
-            rc = run_apply(ctx, nc, d_off_j, (uint8_t*)ctx->out.p + base, ctx->out.cap - base, total, ctx->s_comp, &launches);
-            if (rc) break;
+    uint64_t base = 0; uint32_t launches = 0; int rc = EB200_OK;
+    cudaError_t ce = cudaSuccess;
+    auto t0 = std::chrono::steady_clock::now();
+#define PCK(call) do { ce = (call); if (ce != cudaSuccess) { ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(ce); rc = EB200_ERR_CUDA; goto drain; } } while (0)
+    {
+        for (uint64_t j = 0; j < nchunks; j++) { PCK(cudaEventCreateWithFlags(&ev_up[j], cudaEventDisableTiming)); PCK(cudaEventCreateWithFlags(&ev_done[j], cudaEventDisableTiming)); }
+        PCK(ctx->data.ensure(data_bytes + 64));
+        PCK(ctx->off.ensure((n_blobs + 1) * 8));
+        PCK(ctx->out_off.ensure((n_cases + nchunks + 1) * 8));
+        PCK(ctx->out_len.ensure(n_cases * 8));
+        PCK(ctx->meta.ensure(n_cases * sizeof(MetaDev)));
+        {   // output arena: the slots of every chunk (same formula as eb_slot_sizes: input + clamp(len/16, 256, 65536), 16-byte
+            // aligned) + an overflow region per chunk. Pipelined chunks cannot move the arena under downloads in flight, so it
+            // is sized here once -- small blobs need several times their input (a 100-byte blob has a 368-byte slot).
+            uint64_t slots = 0;
+            for (uint64_t k = 0; k < n_cases; k++) { uint64_t len = off[b0 + k + 1] - off[b0 + k]; uint64_t slack = std::min<uint64_t>(std::max<uint64_t>(len / 16, 256), 65536); slots += align16(len + slack); }
+            PCK(ctx->out.ensure(slots + std::max<uint64_t>(64ull << 20, slots / 8 / std::max<uint64_t>(nchunks, 1)) * (nchunks + 1) + 4096));
         }
-        CK(cudaEventRecord(ev_done[j], ctx->s_comp));
-        CK(cudaStreamWaitEvent(ctx->s_d2h, ev_done[j], 0));
-        if (total) CK(cudaMemcpyAsync(user_out + base, (uint8_t*)ctx->out.p + base, total, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        CK(cudaMemcpyAsync(out_off + k0, d_off_j, nc * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        CK(cudaMemcpyAsync(out_len + k0, (uint64_t*)ctx->out_len.p + k0, nc * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        if (meta) CK(cudaMemcpyAsync(meta + k0, (MetaDev*)ctx->meta.p + k0, nc * sizeof(MetaDev), cudaMemcpyDeviceToHost, ctx->s_d2h));
-        bases[j] = base; base += total;
+        PCK(cudaMemcpyAsync(ctx->off.p, off, (n_blobs + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+        uint64_t next_up = 0;
+        auto upload_until = [&](uint64_t hi) -> cudaError_t {
+            for (; next_up < std::min(hi, nchunks); next_up++) {
+                uint64_t k0 = next_up * chunk, k1 = std::min(n_cases, k0 + chunk);
+                uint64_t lo = off[b0 + k0], h = off[b0 + k1];
+                cudaError_t e = cudaSuccess;
+                if (h > lo) e = cudaMemcpyAsync((uint8_t*)ctx->data.p + lo, data + lo, h - lo, cudaMemcpyHostToDevice, ctx->s_h2d);
+                if (e == cudaSuccess) e = cudaEventRecord(ev_up[next_up], ctx->s_h2d);
+                if (e != cudaSuccess) return e;
+            }
+            return cudaSuccess;
+        };
+        for (uint64_t j = 0; j < nchunks; j++) {
+            PCK(upload_until(j + 1 + (uint64_t)ctx->h2d_ahead));               // uploads run ahead of the compute
+            uint64_t k0 = j * chunk, k1 = std::min(n_cases, k0 + chunk), nc = k1 - k0;
+            PCK(cudaStreamWaitEvent(ctx->s_comp, ev_up[j], 0));
+            eb200_opts o = *opts; o.first_case = first + k0;
+            BatchParams bp; rc = compute_batch_params(&o, n_blobs, nc, bp);
+            if (rc) goto drain;
+            uint64_t* d_off_j = (uint64_t*)ctx->out_off.p + k0 + j;          // nc + 1 entries per chunk
+            uint64_t total = 0;
+            if (ctx->fused) {
+                rc = run_fused(ctx, bp, &o, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, true, nullptr, 0, base, d_off_j,
+                               (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches);
+                if (rc) goto drain;
+                if (base + total > user_cap) { rc = EB200_ERR_NOMEM; goto drain; }
+            } else {
+                rc = run_decide_scan(ctx, bp, &o, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, d_off_j,
+                                     (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches);
+                if (rc) goto drain;
+                if (base + total > user_cap) { rc = EB200_ERR_NOMEM; goto drain; }
+                if (base + total + 64 > ctx->out.cap) {                          // rare: the estimate was too small -- drain and grow
+                    PCK(cudaStreamSynchronize(ctx->s_d2h)); PCK(cudaStreamSynchronize(ctx->s_comp));
+                    PCK(grow_preserving(ctx->out, (base + total) * 2 + 64, base, ctx->s_comp));
+                }
+                rc = run_apply(ctx, nc, d_off_j, (uint8_t*)ctx->out.p + base, ctx->out.cap - base, total, ctx->s_comp, &launches);
+                if (rc) goto drain;
+            }
+            PCK(cudaEventRecord(ev_done[j], ctx->s_comp));
+            PCK(cudaStreamWaitEvent(ctx->s_d2h, ev_done[j], 0));
+            if (total) PCK(cudaMemcpyAsync(user_out + base, (uint8_t*)ctx->out.p + base, total, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            PCK(cudaMemcpyAsync(out_off + k0, d_off_j, nc * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            PCK(cudaMemcpyAsync(out_len + k0, (uint64_t*)ctx->out_len.p + k0, nc * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (meta) PCK(cudaMemcpyAsync(meta + k0, (MetaDev*)ctx->meta.p + k0, nc * sizeof(MetaDev), cudaMemcpyDeviceToHost, ctx->s_d2h));
+            bases[j] = base; base += total;
+        }
     }
-    cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_comp);
-    cudaError_t e = cudaStreamSynchronize(ctx->s_d2h);
-    for (uint64_t j = 0; j < nchunks; j++) { cudaEventDestroy(ev_up[j]); cudaEventDestroy(ev_done[j]); }
+drain:
+#undef PCK
+    {   // one way out: nothing may still be writing into the caller's buffers, and nothing leaks
+        cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(ctx->s_comp), e3 = cudaStreamSynchronize(ctx->s_d2h);
+        for (uint64_t j = 0; j < nchunks; j++) { if (ev_up[j]) cudaEventDestroy(ev_up[j]); if (ev_done[j]) cudaEventDestroy(ev_done[j]); }
+        if (rc == EB200_OK) { cudaError_t e = e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3; if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); rc = EB200_ERR_CUDA; } }
+    }
     if (rc) return rc;
-    if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return EB200_ERR_CUDA; }
     for (uint64_t j = 0; j < nchunks; j++) { uint64_t k0 = j * chunk, k1 = std::min(n_cases, k0 + chunk); for (uint64_t k = k0; k < k1; k++) out_off[k] += bases[j]; }
     out_off[n_cases] = base;
     if (stats) {
@@ -605,7 +637,7 @@ int eb200_fuzz_batch_into(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t*
         if (!ok) return EB200_ERR_ARG;
         if (b0 + n_cases <= n_blobs && data_bytes >= (256ull << 20) && n_cases >= 4096) {
             uint64_t avg = std::max<uint64_t>(1, data_bytes / n_blobs);
-            uint64_t chunk = std::max<uint64_t>(1024, (128ull << 20) / avg);
+            uint64_t chunk = std::max<uint64_t>(1024, ((uint64_t)ctx->chunk_mb << 20) / avg);
             if (chunk * 2 <= n_cases) return fuzz_batch_host_pipelined(ctx, opts, data, off, n_blobs, n_cases, out_buf, out_capacity, out_off, out_len, meta, stats, chunk);
         }
     }
@@ -671,6 +703,37 @@ static int fuzz_batch_host(eb200_ctx* ctx, const eb200_opts* opts, const uint8_t
 }
 
 void eb200_free(void* p) { free(p); }
+
+// Pinned host memory on the GPU's NUMA node (staging rings of the NIF, bench.py's e2e buffers). The pages are first-touched by
+// this thread while it is bound to the CPUs of that node, then the thread's affinity is restored: a DMA out of remote-node
+// memory crosses the socket interconnect and showed up as 38 GB/s per direction instead of the link's ~55.
+void* eb200_host_alloc(eb200_ctx* ctx, uint64_t bytes) {
+    if (!ctx || bytes == 0) return nullptr;
+    cudaSetDevice(ctx->device);
+    cpu_set_t old_set, node_set; bool bound = false;
+    if (ctx->numa_node >= 0 && sched_getaffinity(0, sizeof(old_set), &old_set) == 0) {
+        char path[96]; snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", ctx->numa_node);
+        if (FILE* f = fopen(path, "r")) {
+            char buf[4096] = {0};
+            if (fgets(buf, sizeof(buf), f)) {
+                CPU_ZERO(&node_set); int any = 0;
+                for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+                    int a = 0, b = 0; int n = sscanf(tok, "%d-%d", &a, &b); if (n == 1) b = a; if (n < 1) continue;
+                    for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &node_set); any = 1; }
+                }
+                if (any && sched_setaffinity(0, sizeof(node_set), &node_set) == 0) bound = true;
+            }
+            fclose(f);
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+    if (p) { volatile uint8_t* q = (volatile uint8_t*)p; for (uint64_t i = 0; i < bytes; i += 4096) q[i] = 0; }   // first touch (cudaHostAlloc usually did already)
+    if (bound) sched_setaffinity(0, sizeof(old_set), &old_set);
+    return p;
+}
+void eb200_host_free(eb200_ctx* ctx, void* p) { if (ctx) cudaSetDevice(ctx->device); if (p) cudaFreeHost(p); }
+int eb200_numa_node(eb200_ctx* ctx) { return ctx ? ctx->numa_node : -1; }
 
 // donor sampling for config C5: one warp per window
 __global__ void __launch_bounds__(256) eb_sample_donors_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ off, uint64_t n_blobs, uint64_t n_donors, uint32_t stride,

@@ -1,13 +1,16 @@
 %% erlamsa_b200 -- Erlang side of the B200 batch engine (binding over include/erlamsa_b200.h).
 %%
-%% NOT COMPILED IN THIS REPOSITORY'S CI (no OTP in the build image); see INTEGRATION.md.
+%% The build image has no OTP, so this module is not compiled in CI; the NIF underneath is (against a mock erl_nif.h,
+%% tests/test_nif_harness.py). See INTEGRATION.md.
 %%
 %%   erlamsa_b200:fuzz_batch(Corpus :: [binary()], Opts :: map()) -> [binary()]
-%%       same option map as erlamsa_main:fuzzer/1 (seed, mutations, patterns, n, skip, blockscale);
-%%       case I mutates lists:nth(((I-1) rem length(Corpus)) + 1, Corpus).
+%%       same option map as erlamsa_main:fuzzer/1 (seed, mutations, patterns, generators, n, skip, blockscale);
+%%       case I (skip < I =< n) mutates lists:nth(((I-1) rem length(Corpus)) + 1, Corpus) with the I-th per-case seed of the
+%%       parent stream -- for a one-element corpus exactly erlamsa_main:fuzzer(#{paths => [direct], input => B, ...}).
 %%   erlamsa_b200:fuzzer(Opts) / fuzz(Opts)
-%%       drop-in for erlamsa_main:fuzzer/1: routes paths == [direct] / output == return to the GPU and
-%%       everything else (stdin, files, network outputs, external modules) to the untouched Erlang path.
+%%       drop-in for erlamsa_main:fuzzer/1: routes paths == [direct] with output == return to the GPU and everything else
+%%       (stdin, files, network outputs, external modules, unseeded runs) to the untouched Erlang path.
+%%   Option `gpu_device` (default 0) picks the GPU; every device has its own engine context inside the NIF.
 -module(erlamsa_b200).
 -export([fuzz_batch/2, fuzzer/1, fuzz/1, supported/1]).
 -on_load(init/0).
@@ -16,10 +19,10 @@ init() ->
     Path = filename:join(code:priv_dir(erlamsa), "erlamsa_b200_nif"),
     case erlang:load_nif(Path, 0) of
         ok -> ok;
-        {error, _} -> ok      %% no GPU / no engine: fuzz_batch_nif/7 stays a stub and we fall back to Erlang
+        {error, _} -> ok      %% no GPU / no engine: fuzz_batch_nif/10 stays a stub and every call takes the Erlang path
     end.
 
-fuzz_batch_nif(_Blobs, _N, _Seed, _MutaPri, _PatPri, _First, _BlockScale) -> {error, nif_not_loaded}.
+fuzz_batch_nif(_Blobs, _N, _Seed, _MutaPri, _PatPri, _First, _BlockScale, _Ssrf, _Gens, _Device) -> {error, nif_not_loaded}.
 
 %% priorities in table order, -1 = not selected (the engine's eb200_opts.muta_pri / pat_pri)
 pri_vector(Table, Selected) ->
@@ -29,29 +32,50 @@ pri_vector(Table, Selected) ->
 mutator_table() -> [Name || {_, _, _, Name, _} <- erlamsa_mutations:mutations()].
 pattern_table() -> [Name || {_, _, Name, _} <- erlamsa_patterns:patterns()].
 
-supported(Opts) ->
-    maps:get(paths, Opts, ["-"]) =:= [direct] andalso maps:get(output, Opts, return) =:= return
-        andalso maps:get(external_mutations, Opts, nil) =:= nil andalso maps:is_key(seed, Opts).
+%% the engine implements the `direct` and `random` generators; anything else in the list keeps the Erlang path
+generator_pris(Gens) ->
+    M = maps:from_list(Gens),
+    case maps:keys(M) -- [direct, random] of
+        [] -> {ok, {maps:get(direct, M, -1), maps:get(random, M, -1)}};
+        _ -> unsupported
+    end.
 
-fuzz_batch(Corpus, Opts) when is_list(Corpus) ->
+%% `output => return` must be asked for: the reference's default output is "-" (stdout), src/erlamsa_main.erl:245
+supported(Opts) ->
+    maps:get(paths, Opts, ["-"]) =:= [direct] andalso maps:get(output, Opts, "-") =:= return
+        andalso maps:get(external_mutations, Opts, nil) =:= nil andalso maps:get(external_post, Opts, nil) =:= nil
+        andalso maps:get(sequence_muta, Opts, false) =:= false andalso maps:is_key(seed, Opts)
+        andalso generator_pris(maps:get(generators, Opts, erlamsa_gen:default())) =/= unsupported.
+
+%% one case, by the reference, with the seeds the batch semantics give it: case I draws the I-th gen_predictable_seed() of
+%% the parent stream (skip => I - 1 makes the reference burn the first I - 1 without running them). This is O(I) cheap
+%% draws per call and cannot be made O(1) through the public API: the scores, the snand mask and the generator choice of a
+%% run are themselves drawn from the parent stream right after seeding (src/erlamsa_mutations.erl:1313-1314,1390-1395,
+%% src/erlamsa_gen.erl:197-198), so re-seeding "closer to case I" would change them.
+reference_case(Corpus, Opts, I) ->
+    B = lists:nth(((I - 1) rem length(Corpus)) + 1, Corpus),
+    erlamsa_main:fuzzer(maps:merge(Opts, #{paths => [direct], output => return, input => B, n => I, skip => I - 1})).
+
+fuzz_batch(Corpus, Opts) when is_list(Corpus), Corpus =/= [] ->
     Seed = maps:get(seed, Opts),
     N = maps:get(n, Opts, length(Corpus)),
     Skip = maps:get(skip, Opts, 0),
     MutaPri = pri_vector(mutator_table(), maps:get(mutations, Opts, erlamsa_mutations:default([]))),
     PatPri = pri_vector(pattern_table(), maps:get(patterns, Opts, erlamsa_patterns:default())),
-    case fuzz_batch_nif(Corpus, N - Skip, Seed, MutaPri, PatPri, Skip + 1, maps:get(blockscale, Opts, 1.0) * 1.0) of
-        {ok, Outs} ->
-            %% a flagged case (path without a device implementation, capacity limit) is re-run, alone, by the reference:
-            %% case I draws the I-th gen_predictable_seed() there too (skip => I - 1), so the list stays what
-            %% erlamsa_main:fuzzer/1 would have produced
-            Redo = fun(I) ->
-                       B = lists:nth(((I - 1) rem length(Corpus)) + 1, Corpus),
-                       erlamsa_main:fuzzer(maps:merge(Opts, #{paths => [direct], output => return, input => B, n => I, skip => I - 1}))
-                   end,
-            lists:append([case O of {flagged, I} -> Redo(I); <<>> -> []; _ -> [O] end || O <- Outs]);   %% record_result/2 drops empty results
-        {error, _Why} ->                                          %% unsupported mutator, no GPU, ...: the reference path
-            lists:append([erlamsa_main:fuzzer(maps:merge(Opts, #{paths => [direct], output => return, input => B, n => 1}))
-                          || B <- Corpus])
+    {ok, Gens} = generator_pris(maps:get(generators, Opts, erlamsa_gen:default())),
+    {Host, Port} = erlamsa_mutations:get_ssrf_ep(),
+    case fuzz_batch_nif(Corpus, N - Skip, Seed, MutaPri, PatPri, Skip + 1, maps:get(blockscale, Opts, 1.0) * 1.0,
+                        {iolist_to_binary(Host), Port}, Gens, maps:get(gpu_device, Opts, 0)) of
+        {ok, Outs, _Metas} ->
+            %% a flagged case (path without a device implementation, capacity limit) is re-run, alone, by the reference
+            lists:append([case O of {flagged, I, _St, _Why} -> reference_case(Corpus, Opts, I); <<>> -> []; _ -> [O] end || O <- Outs]);   %% record_result/2 drops empty results
+        {error, _Why} ->
+            %% NIF not loaded (no GPU) or the engine refused the batch: the reference path, with the caller's n and skip and
+            %% the same case numbering -- never a different number of results than the GPU path would give
+            case Corpus of
+                [_Single] -> erlamsa_main:fuzzer(maps:merge(Opts, #{paths => [direct], output => return, input => hd(Corpus)}));
+                _ -> lists:append([reference_case(Corpus, Opts, I) || I <- lists:seq(Skip + 1, N)])
+            end
     end.
 
 fuzzer(Opts) ->
@@ -59,7 +83,7 @@ fuzzer(Opts) ->
         true ->
             Input = maps:get(input, Opts),
             Corpus = case is_list(Input) of true -> Input; false -> [Input] end,
-            fuzz_batch(Corpus, maps:merge(#{n => max(1, length(Corpus))}, Opts));
+            fuzz_batch(Corpus, maps:merge(#{n => 1}, Opts));       %% the reference's default n is 1 (src/erlamsa_main.erl:130)
         false -> erlamsa_main:fuzzer(Opts)
     end.
 

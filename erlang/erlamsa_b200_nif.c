@@ -1,30 +1,72 @@
 /*
  * erlamsa_b200_nif.c -- the Erlang NIF shim over include/erlamsa_b200.h.
  *
- * NOT BUILT IN THIS REPOSITORY'S CI: the build image has no Erlang/OTP (no erl_nif.h). It is the binding a
- * maintainer adds to erlamsa so that erlamsa_main:fuzzer/1 (reference src/erlamsa_main.erl:124) can hand a whole
- * corpus to the GPU engine; the same C ABI is exercised in CI through Python ctypes (tests/).
+ * The build image has no Erlang/OTP, so CI compiles this file against erlang/mock/erl_nif.h (a small stand-in for the
+ * part of the NIF API used here) and drives fuzz_batch_nif from a C harness (tests/test_nif_harness.py); with a real OTP
+ * it builds as is:
+ *   gcc -O2 -fPIC -shared -I$ERL_INCLUDE -I../include erlamsa_b200_nif.c -L../erlamsa_b200 -lerlamsa_b200 -o priv/erlamsa_b200_nif.so
  *
- *   erlamsa_b200:fuzz_batch_nif(Blobs :: [binary()], NCases, Seed :: {A,B,C}, MutaPri :: [integer()] (41),
- *                               PatPri :: [integer()] (10), FirstCase, BlockScale :: float())
- *       -> {ok, [binary()]} | {error, Reason :: atom()}
+ *   erlamsa_b200:fuzz_batch_nif(Blobs :: [binary()], NCases, Seed :: {A,B,C}, MutaPri :: [integer()] (41), PatPri :: [integer()] (10),
+ *                               FirstCase, BlockScale :: float(), {SsrfHost :: binary(), SsrfPort}, {GenDirectPri, GenRandomPri},
+ *                               Device :: non_neg_integer())
+ *       -> {ok, [binary() | {flagged, CaseNo, Status, Reason}], [{Pattern, NUsed, Draws}]} | {error, Reason :: atom()}
  *
- * Build (where OTP and the engine are installed):
- *   gcc -O2 -fPIC -shared -I$ERL_INCLUDE -I../include erlamsa_b200_nif.c -L../erlamsa_b200 -lerlamsa_b200 \
- *       -o priv/erlamsa_b200_nif.so
+ * Data path = the one bench.py's `e2e` measures: the input binaries are copied ONCE, straight into a pinned staging buffer on
+ * the GPU's NUMA node (eb200_host_alloc), eb200_fuzz_batch_into overlaps upload / kernel / download in chunks, and the results
+ * are handed to the VM as RESOURCE BINARIES that point into the pinned output buffer -- no second copy; the buffer goes back to
+ * a small free list when the VM has collected every binary of the batch.
  */
 #include <string.h>
 #include <stdlib.h>
+#include <stdint.h>
 #include "erl_nif.h"
 #include "erlamsa_b200.h"
 
-static eb200_ctx* g_ctx = NULL;   /* one context per VM; the engine serialises batches on its stream */
+#define MAX_DEVICES 16
+#define POOL_SLOTS 4
+
+typedef struct { void* p; uint64_t cap; } HostBuf;
+typedef struct {
+    eb200_ctx* ctx;
+    HostBuf in;                      /* pinned input staging, grown on demand, reused by every call (calls are serialised per device) */
+    HostBuf free_out[POOL_SLOTS];    /* pinned output buffers returned by the resource destructor */
+} Device;
+typedef struct { int dev; void* p; uint64_t cap; } OutRes;   /* owns one pinned output buffer while binaries point into it */
+
+static Device g_dev[MAX_DEVICES];
+static ErlNifMutex* g_lock = NULL;
+static ErlNifResourceType* g_out_type = NULL;
+
+static void out_dtor(ErlNifEnv* env, void* obj) {
+    (void)env;
+    OutRes* r = (OutRes*)obj;
+    if (!r->p) return;
+    enif_mutex_lock(g_lock);
+    Device* d = &g_dev[r->dev];
+    int kept = 0;
+    for (int i = 0; i < POOL_SLOTS && !kept; i++) if (!d->free_out[i].p) { d->free_out[i].p = r->p; d->free_out[i].cap = r->cap; kept = 1; }
+    enif_mutex_unlock(g_lock);
+    if (!kept) eb200_host_free(d->ctx, r->p);
+}
 
 static int load(ErlNifEnv* env, void** priv, ERL_NIF_TERM info) {
-    (void)env; (void)priv; (void)info;
-    return eb200_init(0, &g_ctx) == EB200_OK ? 0 : 1;   /* no GPU => the NIF refuses to load; erlamsa keeps its Erlang path */
+    (void)priv; (void)info;
+    memset(g_dev, 0, sizeof(g_dev));
+    g_lock = enif_mutex_create((char*)"erlamsa_b200");
+    g_out_type = enif_open_resource_type(env, NULL, "erlamsa_b200_out", out_dtor, ERL_NIF_RT_CREATE, NULL);
+    if (!g_lock || !g_out_type) return 1;
+    /* no GPU => the NIF refuses to load and erlamsa keeps its Erlang path: the engine itself never computes on the CPU */
+    return eb200_init(0, &g_dev[0].ctx) == EB200_OK ? 0 : 1;
 }
-static void unload(ErlNifEnv* env, void* priv) { (void)env; (void)priv; if (g_ctx) eb200_shutdown(g_ctx); }
+static void unload(ErlNifEnv* env, void* priv) {
+    (void)env; (void)priv;
+    for (int i = 0; i < MAX_DEVICES; i++) if (g_dev[i].ctx) {
+        if (g_dev[i].in.p) eb200_host_free(g_dev[i].ctx, g_dev[i].in.p);
+        for (int k = 0; k < POOL_SLOTS; k++) if (g_dev[i].free_out[k].p) eb200_host_free(g_dev[i].ctx, g_dev[i].free_out[k].p);
+        eb200_shutdown(g_dev[i].ctx);
+    }
+    if (g_lock) enif_mutex_destroy(g_lock);
+}
 
 static ERL_NIF_TERM err(ErlNifEnv* env, const char* why) {
     return enif_make_tuple2(env, enif_make_atom(env, "error"), enif_make_atom(env, why));
@@ -38,59 +80,94 @@ static int get_int_list(ErlNifEnv* env, ERL_NIF_TERM l, int32_t* out, unsigned n
 
 /* runs on a dirty IO scheduler: a batch takes milliseconds to seconds */
 static ERL_NIF_TERM fuzz_batch_nif(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
-    (void)argc;
-    unsigned n_blobs; ErlNifUInt64 n_cases, first_case; double blockscale;
-    const ERL_NIF_TERM* seed; int seed_arity;
+    if (argc != 10) return err(env, "badarg");
+    unsigned n_blobs; ErlNifUInt64 n_cases, first_case; double blockscale; unsigned dev;
+    const ERL_NIF_TERM *seed, *ssrf, *gens; int arity;
     eb200_opts o; eb200_default_opts(&o);
     if (!enif_get_list_length(env, argv[0], &n_blobs) || n_blobs == 0) return err(env, "badarg");
     if (!enif_get_uint64(env, argv[1], &n_cases)) return err(env, "badarg");
-    if (!enif_get_tuple(env, argv[2], &seed_arity, &seed) || seed_arity != 3) return err(env, "badarg");
+    if (!enif_get_tuple(env, argv[2], &arity, &seed) || arity != 3) return err(env, "badarg");
     for (int i = 0; i < 3; i++) { ErlNifSInt64 v; if (!enif_get_int64(env, seed[i], &v)) return err(env, "badarg"); o.seed[i] = v; }
     if (!get_int_list(env, argv[3], o.muta_pri, EB200_N_MUTATORS) || !get_int_list(env, argv[4], o.pat_pri, EB200_N_PATTERNS)) return err(env, "badarg");
     if (!enif_get_uint64(env, argv[5], &first_case) || !enif_get_double(env, argv[6], &blockscale)) return err(env, "badarg");
     o.first_case = first_case; o.blockscale = blockscale;
-
-    /* pack the corpus: one contiguous buffer + offsets (the engine's input layout) */
-    ErlNifBinary* bins = (ErlNifBinary*)enif_alloc(sizeof(ErlNifBinary) * n_blobs);
-    uint64_t* off = (uint64_t*)enif_alloc(sizeof(uint64_t) * (n_blobs + 1));
-    ERL_NIF_TERM h, t = argv[0]; uint64_t total = 0;
-    for (unsigned i = 0; i < n_blobs; i++) {
-        if (!enif_get_list_cell(env, t, &h, &t) || !enif_inspect_binary(env, h, &bins[i])) { enif_free(bins); enif_free(off); return err(env, "badarg"); }
-        off[i] = total; total += bins[i].size;
+    {   /* SSRF endpoint: erlamsa_mutations:get_ssrf_ep/0 (reference src/erlamsa_mutations.erl:697-726) */
+        ErlNifBinary host; int port;
+        if (!enif_get_tuple(env, argv[7], &arity, &ssrf) || arity != 2 || !enif_inspect_iolist_as_binary(env, ssrf[0], &host) || !enif_get_int(env, ssrf[1], &port)
+            || host.size >= sizeof(o.ssrf_host)) return err(env, "badarg");
+        memset(o.ssrf_host, 0, sizeof(o.ssrf_host)); memcpy(o.ssrf_host, host.data, host.size); o.ssrf_port = port;
     }
-    off[n_blobs] = total;
-    uint8_t* data = (uint8_t*)enif_alloc(total ? total : 1);
-    for (unsigned i = 0; i < n_blobs; i++) memcpy(data + off[i], bins[i].data, bins[i].size);
+    if (!enif_get_tuple(env, argv[8], &arity, &gens) || arity != 2 || !enif_get_int(env, gens[0], &o.gen_direct_pri) || !enif_get_int(env, gens[1], &o.gen_random_pri)) return err(env, "badarg");
+    if (!enif_get_uint(env, argv[9], &dev) || dev >= MAX_DEVICES) return err(env, "badarg");
 
-    uint8_t* out = NULL;
+    /* sizes first, then ONE copy of every binary into the pinned staging buffer */
+    uint64_t* off = (uint64_t*)enif_alloc(sizeof(uint64_t) * ((uint64_t)n_blobs + 1));
     uint64_t* out_off = (uint64_t*)enif_alloc(sizeof(uint64_t) * (n_cases + 1));
     uint64_t* out_len = (uint64_t*)enif_alloc(sizeof(uint64_t) * (n_cases ? n_cases : 1));
     eb200_meta* meta = (eb200_meta*)enif_alloc(sizeof(eb200_meta) * (n_cases ? n_cases : 1));
-    int rc = eb200_fuzz_batch(g_ctx, &o, data, off, n_blobs, n_cases, &out, out_off, out_len, meta, NULL);
-    ERL_NIF_TERM res;
-    if (rc != EB200_OK) {
-        res = err(env, rc == EB200_ERR_UNSUPPORTED ? "unsupported" : rc == EB200_ERR_SCRATCH ? "scratch" : "engine");
-    } else {
-        /* {ok, [Binary | {flagged, CaseNo}]}: a case the engine flagged (unsupported path / capacity)
-         * is handed back by number so that the Erlang side re-runs exactly that case on the reference path;
-         * a case whose worker died (status 2) is an empty binary, as in the reference */
-        ERL_NIF_TERM list = enif_make_list(env, 0);
-        for (uint64_t k = n_cases; k-- > 0;) {   /* build back to front; empty outputs are kept, the caller filters (record_result/2) */
-            ERL_NIF_TERM b;
-            if (meta[k].status == EB200_CASE_UNSUPPORTED || meta[k].status == EB200_CASE_OVERFLOW) {
-                b = enif_make_tuple2(env, enif_make_atom(env, "flagged"), enif_make_uint64(env, first_case + k));
-            } else {
-                unsigned char* p = enif_make_new_binary(env, out_len[k], &b);
-                memcpy(p, out + out_off[k], out_len[k]);
-            }
-            list = enif_make_list_cell(env, b, list);
-        }
-        res = enif_make_tuple2(env, enif_make_atom(env, "ok"), list);
-        eb200_free(out);
+    ERL_NIF_TERM res, h, t = argv[0];
+    uint64_t total = 0, slots = 0;
+    OutRes* ores = NULL;
+    if (!off || !out_off || !out_len || !meta) { res = err(env, "enomem"); goto done; }
+    for (unsigned i = 0; i < n_blobs; i++) {
+        ErlNifBinary b;
+        if (!enif_get_list_cell(env, t, &h, &t) || !enif_inspect_binary(env, h, &b)) { res = err(env, "badarg"); goto done; }
+        off[i] = total; total += b.size;
     }
-    enif_free(bins); enif_free(off); enif_free(data); enif_free(out_off); enif_free(out_len); enif_free(meta);
+    off[n_blobs] = total;
+    for (uint64_t k = 0; k < n_cases; k++) {   /* output arena = the engine's slots (input + clamp(len/16, 256, 65536)) + room for results that outgrow them */
+        uint64_t b = (first_case - 1 + k) % n_blobs, len = off[b + 1] - off[b], slack = len / 16;
+        if (slack < 256) slack = 256;
+        if (slack > 65536) slack = 65536;
+        slots += (len + slack + 15) & ~15ull;
+    }
+    enif_mutex_lock(g_lock);
+    {
+        Device* d = &g_dev[dev];
+        int rc = EB200_OK;
+        if (!d->ctx) rc = eb200_init((int)dev, &d->ctx);
+        if (rc != EB200_OK) { enif_mutex_unlock(g_lock); res = err(env, "no_device"); goto done; }
+        if (d->in.cap < total + 64) {
+            if (d->in.p) eb200_host_free(d->ctx, d->in.p);
+            d->in.cap = total + total / 4 + 4096; d->in.p = eb200_host_alloc(d->ctx, d->in.cap);
+            if (!d->in.p) { d->in.cap = 0; enif_mutex_unlock(g_lock); res = err(env, "enomem"); goto done; }
+        }
+        t = argv[0];
+        for (unsigned i = 0; i < n_blobs; i++) { ErlNifBinary b; enif_get_list_cell(env, t, &h, &t); enif_inspect_binary(env, h, &b); memcpy((uint8_t*)d->in.p + off[i], b.data, b.size); }
+        uint64_t want = slots + slots / 4 + (64ull << 20);
+        ores = (OutRes*)enif_alloc_resource(g_out_type, sizeof(OutRes));
+        ores->dev = (int)dev; ores->p = NULL; ores->cap = 0;
+        for (int i = 0; i < POOL_SLOTS && !ores->p; i++) if (d->free_out[i].p && d->free_out[i].cap >= want) { ores->p = d->free_out[i].p; ores->cap = d->free_out[i].cap; d->free_out[i].p = NULL; d->free_out[i].cap = 0; }
+        if (!ores->p) { ores->cap = want; ores->p = eb200_host_alloc(d->ctx, want); }
+        if (!ores->p) { enif_mutex_unlock(g_lock); res = err(env, "enomem"); goto done; }
+        rc = eb200_fuzz_batch_into(d->ctx, &o, (const uint8_t*)d->in.p, off, n_blobs, n_cases, (uint8_t*)ores->p, ores->cap, out_off, out_len, meta, NULL);
+        enif_mutex_unlock(g_lock);
+        if (rc != EB200_OK) { res = err(env, rc == EB200_ERR_UNSUPPORTED ? "unsupported" : rc == EB200_ERR_SCRATCH ? "scratch" : rc == EB200_ERR_NOMEM ? "enomem" : "engine"); goto done; }
+    }
+    {
+        /* {ok, [Binary | {flagged, CaseNo, Status, Reason}], [{Pattern, NUsed, Draws}]}: a case the engine flagged (path without a
+         * device implementation / capacity limit) is handed back by number so that the Erlang side re-runs
+         * exactly that case on the reference path; a case whose worker died (status 2) is an empty binary, as in the reference */
+        ERL_NIF_TERM list = enif_make_list(env, 0), metas = enif_make_list(env, 0);
+        for (uint64_t k = n_cases; k-- > 0;) {
+            ERL_NIF_TERM b;
+            if (meta[k].status == EB200_CASE_UNSUPPORTED || meta[k].status == EB200_CASE_OVERFLOW)
+                b = enif_make_tuple4(env, enif_make_atom(env, "flagged"), enif_make_uint64(env, first_case + k), enif_make_int(env, meta[k].status), enif_make_int(env, meta[k].reason));
+            else
+                b = enif_make_resource_binary(env, ores, (uint8_t*)ores->p + out_off[k], out_len[k]);      /* zero copy: points into the pinned buffer */
+            list = enif_make_list_cell(env, b, list);
+            metas = enif_make_list_cell(env, enif_make_tuple3(env, enif_make_int(env, meta[k].pattern), enif_make_int(env, meta[k].n_used), enif_make_uint64(env, meta[k].draws)), metas);
+        }
+        res = enif_make_tuple3(env, enif_make_atom(env, "ok"), list, metas);
+    }
+done:
+    if (ores) enif_release_resource(ores);      /* the binaries (if any) keep it alive */
+    if (off) enif_free(off);
+    if (out_off) enif_free(out_off);
+    if (out_len) enif_free(out_len);
+    if (meta) enif_free(meta);
     return res;
 }
 
-static ErlNifFunc nif_funcs[] = {{"fuzz_batch_nif", 7, fuzz_batch_nif, ERL_NIF_DIRTY_JOB_IO_BOUND}};
+static ErlNifFunc nif_funcs[] = {{"fuzz_batch_nif", 10, fuzz_batch_nif, ERL_NIF_DIRTY_JOB_IO_BOUND}};
 ERL_NIF_INIT(erlamsa_b200, nif_funcs, load, NULL, NULL, unload)

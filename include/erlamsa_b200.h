@@ -92,7 +92,7 @@ typedef struct eb200_meta {
     int32_t  used[16];       /* first 16 used mutator ids (table index), -1 padded */
     uint64_t draws;          /* RNG draws consumed by the case's worker stream */
     int32_t  status;         /* EB200_CASE_* */
-    int32_t  pad;
+    int32_t  reason;         /* why a case was flagged: 1 scratch, 4 block runs, 5 output cap, 8 fuse tables, 11 output arena, ... */
     int64_t  thread_seed[3]; /* the case's erlamsa_rnd:gen_predictable_seed() */
 } eb200_meta;
 
@@ -136,6 +136,11 @@ int  eb200_fuzz_batch(eb200_ctx* ctx, const eb200_opts* opts,
  * (len - wlen + 1) with wlen = min(len, stride). Asynchronous on `stream`. */
 int eb200_sample_donors(eb200_ctx* ctx, const uint8_t* d_data, const uint64_t* d_off, uint64_t n_blobs, uint64_t n_donors, uint32_t stride,
                         uint8_t* d_pool, uint32_t* d_len, void* stream);
+/* Pinned host memory on the GPU's NUMA node (first-touched while the calling thread is bound to that node's CPUs): what
+ * eb200_fuzz_batch_into needs to overlap its copies at full PCIe rate. The NIF keeps its staging rings here. */
+void* eb200_host_alloc(eb200_ctx* ctx, uint64_t bytes);
+void  eb200_host_free(eb200_ctx* ctx, void* p);
+int   eb200_numa_node(eb200_ctx* ctx);    /* NUMA node of the GPU from sysfs, -1 when unknown */
 void eb200_free(void* p);
 /* profiling aid: with EB200_CASE_TIMES=1 in the environment at eb200_init, microseconds the general per-case program spent on
  * each case of the last launch (0 for cases decided by the front warps). Returns the number of entries copied. */
