@@ -25,7 +25,8 @@ class Opts(C.Structure):
                 ("gen_direct_pri", C.c_int32), ("gen_random_pri", C.c_int32),
                 ("ssrf_host", C.c_char * 64), ("ssrf_port", C.c_int32), ("rng_mode", C.c_int32),
                 ("first_case", C.c_uint64), ("max_case_out", C.c_uint64), ("scratch_bytes", C.c_uint64),
-                ("donor_pool", C.c_void_p), ("donor_len", C.c_void_p), ("n_donors", C.c_uint64), ("donor_stride", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("donor_pool", C.c_void_p), ("donor_len", C.c_void_p), ("n_donors", C.c_uint64), ("donor_stride", C.c_uint32), ("reserved0", C.c_uint32),
+                ("gen_file_pri", C.c_int32), ("gen_stdin_pri", C.c_int32)]
 
 
 class Meta(C.Structure):

@@ -91,6 +91,9 @@ EB_DEV void split_big(CaseCtx& c) {
     for (int i = np - 1; i >= 0; i--) runs_insert_front(ws, pieces[i]);
 }
 
+// Philox counter slots: (round << 8) | who, who = mutator id, or one of these
+constexpr uint32_t SLOT_SCHED = 0xFF, SLOT_PATTERN = 0xFE;
+
 // ------------------------------------------------------------------ scheduler: one mux_fuzzers round
 EB_DEV double adjust_priority(double pri, double delta) {   // :1238-1242
     if (delta == 0.0) return pri;
@@ -107,6 +110,8 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
     else if (ws->nruns > 1) { c.has_next = 1; c.next_p = ws->runs[1].p; c.next_n = ws->runs[1].len; }
     else { c.has_next = 0; c.next_p = nullptr; c.next_n = 0; }
     int nr = ws->nrows;
+    const uint32_t rnd = ++ws->round;
+    g.set_slot((rnd << 8) | SLOT_SCHED);
     // weighted_permutations/1 :1244-1250: key_i = rand(trunc(Score*Pri)), stable sort by key descending
     for (int i = 0; i < nr; i++) ws->keys[i] = (uint32_t)g.rand((uint64_t)trunc(ws->rows[i].score * (double)ws->rows[i].pri));
     for (int i = 0; i < nr; i++) {
@@ -123,6 +128,7 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
         if (!big) {
             MutRow row = ws->rows[ws->order[t]];
             temp_reset(c);
+            g.set_slot((rnd << 8) | (uint32_t)row.fn);
             unsigned long long t_m0 = 0;
             if (c.ar.mut_ns) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_m0));
             if (FULL) mut_apply(c, row, p, n, r); else mut_apply_light(c, row, p, n, r);
@@ -177,9 +183,49 @@ EB_DEV const uint8_t* random_block_dev(CaseCtx& c, uint32_t n) {   // random_blo
     random_block_fill(c, buf, n);
     return buf;
 }
-EB_DEV void generate(CaseCtx& c, const uint8_t* blob, uint32_t blen) {
+// finish/1 :43-51 after `len` bytes of stream
+EB_DEV void finish_tail(CaseCtx& c, uint64_t len) {
+    WarpState* ws = c.ws; Rng& g = c.rng;
+    uint64_t x = g.rand(len + 1);
+    if (x != len) return;
+    uint64_t bits = (uint64_t)g.rand_range(1, 16);
+    uint32_t nlen = (uint32_t)g.rand(1ull << bits);
+    if (nlen) { const uint8_t* t = random_block_dev(c, nlen); if (t) { Blk tb; tb.p = t; tb.len = nlen; tb.cnt = 1; runs_push_back(ws, tb); } }
+}
+// file / stdin generators (reference src/erlamsa_gen.erl:59-121): port_stream/2 returns an UNFORCED stream, so the blocks
+// (stream_port/5: full blocks of the wanted size, a new rand_block_size after each, the short rest last) and the finish/1
+// tail come into being at the pattern's first uncons/2 -- after the pattern's own first draws (SURVEY.md appendix A, W1'')
+EB_DEV void force_stream(CaseCtx& c) {
     WarpState* ws = c.ws; Rng& g = c.rng; const BatchParams* bp = c.bp;
-    ws->nruns = 0; ws->vhead = 0;
+    if (!ws->lazy) return;
+    ws->lazy = 0;
+    const uint8_t* p = ws->lz_p; uint32_t n = ws->lz_n, pos = 0;
+    uint64_t r0 = g.rand((uint64_t)bp->rbs_bound);
+    uint32_t wanted = (uint32_t)(r0 > (uint64_t)bp->rbs_min ? r0 : (uint64_t)bp->rbs_min);
+    while (n - pos >= wanted && ws->status == CASE_OK) {
+        Blk b; b.p = p + pos; b.len = wanted; b.cnt = 1;
+        // consecutive blocks of one size share a run
+        if (ws->nruns > 0 && ws->runs[ws->nruns - 1].len == wanted && ws->runs[ws->nruns - 1].p + (uint64_t)wanted * ws->runs[ws->nruns - 1].cnt == b.p) ws->runs[ws->nruns - 1].cnt++;
+        else runs_push_back(ws, b);
+        pos += wanted;
+        uint64_t r = g.rand((uint64_t)bp->rbs_bound);
+        wanted = (uint32_t)(r > (uint64_t)bp->rbs_min ? r : (uint64_t)bp->rbs_min);
+    }
+    if (ws->status != CASE_OK) return;
+    if (pos < n) { Blk b; b.p = p + pos; b.len = n - pos; b.cnt = 1; runs_push_back(ws, b); }
+    finish_tail(c, n);
+}
+EB_DEV void generate(CaseCtx& c, const uint8_t* blob, uint32_t blen, const uint8_t* data, const uint64_t* off) {
+    WarpState* ws = c.ws; Rng& g = c.rng; const BatchParams* bp = c.bp;
+    ws->nruns = 0; ws->vhead = 0; ws->lazy = 0;
+    if (bp->generator == 2 || bp->generator == 3) {
+        if (bp->generator == 2) {   // file_streamer :106-121: the case picks its file, P = erand(N)
+            uint64_t pi = g.erand(bp->n_blobs) - 1;
+            blob = data + off[pi]; blen = (uint32_t)(off[pi + 1] - off[pi]);
+        }
+        ws->lazy = 1; ws->lz_p = blob; ws->lz_n = blen;
+        return;
+    }
     if (bp->generator == 0) {   // direct_generator + finish
         (void)g.rand((uint64_t)bp->rbs_bound);
         Blk b; b.p = blob; b.len = blen; b.cnt = 1; runs_push_back(ws, b);
@@ -283,13 +329,15 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
     for (int guard = 0; guard < 100000 && ws->status == CASE_OK; guard++) {
         // ---- pattern dispatch
         uint64_t ip = 0;
-        if (pat == P_NU) { split_big(c); emit_all(c); return; }
-        if (pat == P_CO) { if (g.erand(2) == 1) { split_big(c); emit_all(c); return; } pat = P_OD; }
+        if (pat == P_NU) { force_stream(c); split_big(c); emit_all(c); return; }
+        if (pat == P_CO) { if (g.erand(2) == 1) { force_stream(c); split_big(c); emit_all(c); return; } pat = P_OD; }
         if (pat == P_OD || pat == P_ND || pat == P_BU) {
             cont = pat == P_OD ? CONT_OD : pat == P_ND ? CONT_ND : CONT_BU;
             // mutate_once/4 :267-278
-            if (active_is_single_empty(ws)) { ws->vhead = 0; ws->nruns = 0; return; }
+            if (!ws->lazy && active_is_single_empty(ws)) { ws->vhead = 0; ws->nruns = 0; return; }
             ip = g.rand(INITIAL_IP);
+            force_stream(c);
+            if (ws->status != CASE_OK) return;
             if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
             split_big(c);
         } else if (!FULL) { ws->status = CASE_UNSUPPORTED; return;
@@ -297,6 +345,8 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             // make_complex_pat + mutate_once_skipper :148-161,352-361
             next = (int)g.rand_elem_idx(P_COUNT);
             ip = g.rand(INITIAL_IP);
+            force_stream(c);
+            if (ws->status != CASE_OK) return;
             if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
             realize_virtual(c);
             if (ws->status != CASE_OK) return;
@@ -311,6 +361,8 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             // make_complex_pat + mutate_once_sizer :83-111 / mutate_once_csum :117-144
             next = (int)g.rand_elem_idx(P_COUNT);
             ip = g.rand(INITIAL_IP);
+            force_stream(c);
+            if (ws->status != CASE_OK) return;
             if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
             realize_virtual(c);
             if (ws->status != CASE_OK) return;
@@ -345,6 +397,8 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             // mutate_once_archiver :167-214 on data that is not a ZIP archive: all blocks are glued into one
             next = (int)g.rand_elem_idx(P_COUNT);
             ip = g.rand(INITIAL_IP);
+            force_stream(c);
+            if (ws->status != CASE_OK) return;
             if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
             realize_virtual(c);
             if (ws->status != CASE_OK) return;
@@ -365,6 +419,8 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             // mutate_once_compressed :217-260 on data that is neither gzip nor zlib: plain mutate_once_loop
             next = (int)g.rand_elem_idx(P_COUNT);
             ip = g.rand(INITIAL_IP);
+            force_stream(c);
+            if (ws->status != CASE_OK) return;
             if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
             realize_virtual(c);
             if (ws->status != CASE_OK) return;
@@ -382,6 +438,7 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
         }
         mux_fuzzers<FULL>(c);
         if (ws->status != CASE_OK) return;
+        g.set_slot((ws->round << 8) | SLOT_PATTERN);
         // ---- continuation
         if (cont == CONT_OD) { emit_all(c); return; }
         if (cont == CONT_ND) {
@@ -394,6 +451,7 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
                 if (!(pr || nb < 2)) break;
                 mux_fuzzers<FULL>(c);
                 if (ws->status != CASE_OK) return;
+                g.set_slot((ws->round << 8) | SLOT_PATTERN);
             }
             emit_all(c); return;
         }
@@ -412,7 +470,7 @@ struct DecideArgs {
 // case_list: a follow-up launch over the cases a previous launch had to flag for lack of arena space re-runs exactly
 // those case numbers (same seeds, same slots; what outgrows the slot goes to the overflow region as before)
 struct FusedArgs { int fused; uint8_t* out; uint64_t out_capacity; const uint64_t* slot_off; uint64_t* out_off; uint64_t ovf_base; unsigned long long* ovf_used; uint64_t data_bytes;
-                   const uint32_t* case_list; uint64_t n_list; unsigned long long* case_counter; int deciders; int fronts; int front_depth; };
+                   const uint32_t* case_list; uint64_t n_list; unsigned long long* case_counter; int deciders; int fronts; int front_depth; int tma_workers; };
 
 // slot sizes for the single-pass mode: input length + slack, 16-byte aligned (the common mutations change a
 // case by a few bytes; anything bigger spills to the overflow region)
@@ -448,6 +506,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         c.rng.mode = bp.rng_mode; c.rng.key = bp.philox_key; c.rng.ctr_hi = I;
         c.rng.seed(ts0, ts1, ts2);
         ws->donor = (uint64_t)(ts0 * 31 + ts1 * 17 + ts2);
+        ws->round = 0; c.rng.set_slot(SLOT_PATTERN);
         // fresh per-case state (CurMuta is not carried between cases, reference src/erlamsa_main.erl:223-235)
         ws->status = CASE_OK; ws->reason = 0; ws->n_used = 0; ws->n_failed = 0; ws->noseg = 0; ws->olen = 0;
         ws->st_n[0] = ws->st_n[1] = 0; ws->fo_has = 0; ws->nwrap = 0; ws->rrun_n = 0; ws->ntseg = 0; ws->tlen = 0; ws->nvseg = 0; ws->vlen = 0; ws->vchunked = 0;
@@ -455,7 +514,7 @@ EB_DEV void decide_one_case(WarpState* ws, const BatchParams& bp, const DecideAr
         ws->nrows = bp.n_rows;
         for (int i = 0; i < bp.n_rows; i++) { MutRow r; r.score = (double)bp.row_score[i]; r.pri = bp.row_pri[i]; r.name = bp.row_id[i]; r.fn = bp.row_id[i]; r.pad = 0; ws->rows[i] = r; }
         __syncwarp();
-        generate(c, blob, blen);
+        generate(c, blob, blen, data, off);
         int pat = -1;
         if (ws->status == CASE_OK) {
             // mux_patterns :438-443 + choose_pri (reference src/erlamsa_utils.erl:155-160)

@@ -59,10 +59,11 @@ struct eb200_ctx {
     int apply_variant = 0;
     int threads = CASE_THREADS;   // eb_case_kernel: threads per CTA (EB200_THREADS) ...
     int deciders = 0;             // ... of which this many warps run the general per-case program (EB200_DECIDERS; 0 = chosen per batch),
+    int tma_workers = 0;          // workers that copy through shared memory with cp.async.bulk (EB200_TMA_WORKERS; A/B, profiles/variants_r2.txt)
     int front_depth = 32;         // fronts post while fewer than this many jobs are waiting in the ring (EB200_FRONT_DEPTH)
     int fronts = -1;              // this many decide 32 byte-mutator cases at a time, lane per case (EB200_FRONTS; -1 = chosen per batch), the rest are copy/scan workers
     DevBuf case_status, retry_list, case_usec;
-    int chunk_mb = 64, h2d_ahead = 2;      // host pipeline: bytes of input per chunk (EB200_CHUNK_MB), uploads queued ahead of the compute (EB200_H2D_AHEAD)
+    int chunk_mb = 256, h2d_ahead = 2;      // host pipeline: bytes of input per chunk (EB200_CHUNK_MB), uploads queued ahead of the compute (EB200_H2D_AHEAD)
     int numa_node = -1;                    // of the GPU (sysfs), -1 unknown
     bool want_case_times = false; uint64_t case_times_n = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // host-path pipeline (created on first use)
@@ -91,7 +92,7 @@ static bool batch_is_light(const BatchParams& bp) {
     return true;
 }
 // shared memory of eb_case_kernel: job queue + parent-stream power table + one WarpState per deciding warp
-static size_t case_smem(int deciders) { return case_smem_layout(deciders, nullptr, nullptr, nullptr); }
+static size_t case_smem(int deciders, int tma_workers = 0) { return case_smem_layout(deciders, nullptr, nullptr, nullptr, nullptr, tma_workers, nullptr); }
 // counters block (device, 8 x u64): [0] scratch_used [1] segs_used [2] overflow bits [3] ovf_used [4..6] flagged [7] next case
 enum { CNT_SCRATCH = 0, CNT_SEGS = 1, CNT_OVERFLOW = 2, CNT_OVF_USED = 3, CNT_FLAGGED = 4, CNT_NEXT_CASE = 7 };
 
@@ -152,6 +153,8 @@ static int compute_batch_params(const eb200_opts* o, uint64_t n_blobs, uint64_t 
     std::vector<std::pair<int, int>> gs;                                 // make_generator for paths == [direct]
     if (o->gen_random_pri >= 0) gs.push_back({o->gen_random_pri, 1});
     if (o->gen_direct_pri >= 0) gs.push_back({o->gen_direct_pri, 0});
+    if (o->gen_file_pri >= 0) gs.push_back({o->gen_file_pri, 2});
+    if (o->gen_stdin_pri >= 0) { if (n_cases != 1 || o->first_case > 1) return EB200_ERR_UNSUPPORTED; gs.push_back({o->gen_stdin_pri, 3}); }
     if (gs.empty()) return EB200_ERR_ARG;
     { auto sg = sort_by_priority(gs); int sum = 0; for (auto& g : sg) sum += g.first;
       int g = choose_pri(sg, (int64_t)par.rand((uint64_t)sum)); if (g < 0) return EB200_ERR_ARG; bp.generator = g; }
@@ -187,7 +190,7 @@ void eb200_default_opts(eb200_opts* o) {
     o->blockscale = 1.0;
     for (int i = 0; i < EB200_N_MUTATORS; i++) o->muta_pri[i] = kMutPri[i];
     for (int i = 0; i < EB200_N_PATTERNS; i++) o->pat_pri[i] = kPatPri[i];
-    o->gen_direct_pri = 500; o->gen_random_pri = 1;
+    o->gen_direct_pri = 500; o->gen_random_pri = 1; o->gen_file_pri = -1; o->gen_stdin_pri = -1;
     strcpy(o->ssrf_host, "localhost"); o->ssrf_port = 51234;
     o->rng_mode = EB200_RNG_AS183; o->first_case = 1;
 }
@@ -219,11 +222,12 @@ int eb200_init(int device, eb200_ctx** out) {
     if (const char* v = getenv("EB200_CASE_TIMES")) ctx->want_case_times = atoi(v) != 0;
     if (const char* v = getenv("EB200_THREADS")) { int k = atoi(v); if (k >= 64 && k <= CASE_THREADS && k % 32 == 0) ctx->threads = k; }
     if (const char* v = getenv("EB200_DECIDERS")) { int k = atoi(v); if (k >= 0 && k <= 32) ctx->deciders = k; }
+    if (const char* v = getenv("EB200_TMA_WORKERS")) { int k = atoi(v); if (k >= 0 && k <= 12) ctx->tma_workers = k; }
     if (const char* v = getenv("EB200_FRONT_DEPTH")) { int k = atoi(v); if (k >= 0 && k <= 200) ctx->front_depth = k; }
     if (const char* v = getenv("EB200_FRONTS")) { int k = atoi(v); if (k >= -1 && k <= MAX_FRONTS) ctx->fronts = k; }
     if (ctx->deciders > ctx->threads / 32) ctx->deciders = ctx->threads / 32;
-    if (cudaFuncSetAttribute(eb_case_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)case_smem(32)) != cudaSuccess ||
-        cudaFuncSetAttribute(eb_case_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)case_smem(32)) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
+    if (cudaFuncSetAttribute(eb_case_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
+        cudaFuncSetAttribute(eb_case_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
     *out = ctx; return EB200_OK;
 }
 
@@ -293,7 +297,7 @@ static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_byte
 }
 static void launch_cases(eb200_ctx* ctx, const BatchParams& bp, const LaunchPlan& lp, cudaStream_t st, const uint8_t* d_data, const uint64_t* d_off,
                          uint64_t* d_out_len, eb200_meta* d_meta, const FusedArgs& fa) {
-    size_t sm = case_smem(lp.roles.deciders);
+    size_t sm = case_smem(lp.roles.deciders, fa.tma_workers);
     if (!batch_is_light(bp)) eb_case_kernel<true><<<lp.grid, ctx->threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
     else eb_case_kernel<false><<<lp.grid, ctx->threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
 }
@@ -363,7 +367,7 @@ static cudaError_t grow_preserving(DevBuf& b, size_t want, size_t keep, cudaStre
 // launch -- the batch is never run twice.
 static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* opts, const uint8_t* d_data, const uint64_t* d_off, uint64_t data_bytes,
                      bool own_out, uint8_t* d_out, uint64_t out_capacity, uint64_t out_base, uint64_t* d_out_off, uint64_t* d_out_len, eb200_meta* d_meta,
-                     cudaStream_t st, uint64_t* total_out, uint32_t* launches) {
+                     cudaStream_t st, uint64_t* total_out, uint32_t* launches, uint64_t host_slots = 0) {
     uint64_t n = bp.n_cases;
     CK(ctx->sz16.ensure(n * 8));
     CK(ctx->case_status.ensure(n + 64));
@@ -382,9 +386,11 @@ static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* op
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[2], st));
     *launches += 4;
-    uint64_t slots = 0;
-    CK(cudaMemcpyAsync(&slots, (uint64_t*)ctx->slot_off.p + n, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    uint64_t slots = host_slots;      // the pipelined host path sums the slot sizes itself (it has the offsets): one sync less per chunk
+    if (!slots) {
+        CK(cudaMemcpyAsync(&slots, (uint64_t*)ctx->slot_off.p + n, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     if (own_out) {
         uint64_t want = out_base + slots + std::max<uint64_t>(64ull << 20, slots / 8) + 64;
         if (ctx->out.cap < want) {
@@ -405,7 +411,7 @@ static int run_fused(eb200_ctx* ctx, const BatchParams& bp, const eb200_opts* op
         FusedArgs fa; memset(&fa, 0, sizeof(fa));
         fa.fused = 1; fa.out = d_out; fa.out_capacity = out_capacity; fa.slot_off = (const uint64_t*)ctx->slot_off.p; fa.out_off = d_out_off;
         fa.ovf_base = slots; fa.ovf_used = cnt + CNT_OVF_USED; fa.data_bytes = data_bytes;
-        fa.case_counter = cnt + CNT_NEXT_CASE; fa.deciders = lp.roles.deciders; fa.fronts = lp.roles.fronts; fa.front_depth = ctx->front_depth;
+        fa.case_counter = cnt + CNT_NEXT_CASE; fa.deciders = lp.roles.deciders; fa.fronts = lp.roles.fronts; fa.front_depth = ctx->front_depth; fa.tma_workers = ctx->tma_workers;
         if (attempt) { fa.case_list = (const uint32_t*)ctx->retry_list.p; fa.n_list = n_list; }
         if (attempt == 0) CK(cudaEventRecord(ctx->ev[0], st));
         launch_cases(ctx, bp, lp, st, d_data, d_off, d_out_len, d_meta, fa);
@@ -581,8 +587,10 @@ static int fuzz_batch_host_pipelined(eb200_ctx* ctx, const eb200_opts* opts, con
             uint64_t* d_off_j = (uint64_t*)ctx->out_off.p + k0 + j;          // nc + 1 entries per chunk
             uint64_t total = 0;
             if (ctx->fused) {
+                uint64_t cslots = 0;
+                for (uint64_t k = k0; k < k1; k++) { uint64_t len = off[b0 + k + 1] - off[b0 + k]; uint64_t slack = std::min<uint64_t>(std::max<uint64_t>(len / 16, 256), 65536); cslots += align16(len + slack); }
                 rc = run_fused(ctx, bp, &o, (const uint8_t*)ctx->data.p, (const uint64_t*)ctx->off.p, data_bytes, true, nullptr, 0, base, d_off_j,
-                               (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches);
+                               (uint64_t*)ctx->out_len.p + k0, meta ? (eb200_meta*)ctx->meta.p + k0 : nullptr, ctx->s_comp, &total, &launches, cslots);
                 if (rc) goto drain;
                 if (base + total > user_cap) { rc = EB200_ERR_NOMEM; goto drain; }
             } else {

@@ -145,7 +145,8 @@ __device__ __noinline__ bool fast_num_lane(Rng& g, JobQ* q, FrontState* fs, cons
 // One lane, one case. Returns true when the case is fully decided here: out = blob[0,pos) ++ lit[0,ll) ++ blob[pos+skip, n).
 // Draw order = decide_one_case -> generate -> run_case_machine(P_OD) -> mux_fuzzers -> mut_byte / mut_num, single-block case.
 __device__ __forceinline__ bool fast_decide_lane(const BatchParams& bp, Rng& g, JobQ* q, FrontState* fs, uint32_t blen, const uint8_t* blob, uint8_t* slot, uint64_t cap, FastOut& fo, uint8_t** num_start) {
-    if (bp.generator != 0 || blen == 0 || blen > ABSMAX_BINARY_BLOCK) return false;
+    if (bp.generator != 0 || blen == 0 || blen > ABSMAX_BINARY_BLOCK) return false;     // random / file / stdin generators: general path
+    g.set_slot(SLOT_PATTERN);
     (void)g.rand((uint64_t)bp.rbs_bound);                                   // direct_generator: unused rand_block_size
     if (g.rand((uint64_t)blen + 1) == blen) return false;                    // finish/1 appends a random tail: general path
     int pat = -1;
@@ -156,6 +157,7 @@ __device__ __forceinline__ bool fast_decide_lane(const BatchParams& bp, Rng& g, 
     (void)g.rand(ip);                                                        // mutate_once_loop: one draw, then the only block is it
     // weighted_permutations: key_i = rand(trunc(Score_i * Pri_i)) in table order; the stable descending sort puts the
     // first row with the largest key in front
+    g.set_slot((1u << 8) | SLOT_SCHED);
     int best = -1; uint64_t bestk = 0;
     for (int i = 0; i < bp.n_rows; i++) {
         uint64_t k = g.rand((uint64_t)trunc((double)bp.row_score[i] * (double)bp.row_pri[i]));
@@ -163,6 +165,7 @@ __device__ __forceinline__ bool fast_decide_lane(const BatchParams& bp, Rng& g, 
     }
     if (best < 0) return false;
     int id = bp.row_id[best];
+    g.set_slot((1u << 8) | (uint32_t)id);
     if (id == M_NUM) { if (cap < (uint64_t)blen + NUM_PAD + 112) return false; return fast_num_lane(g, q, fs, blob, blen, slot + NUM_PAD, fo, num_start); }
     if (!fast_byte_mut(id)) return false;
     // mut_byte (sed_byte_* / sed_utf8_widen)
@@ -253,7 +256,7 @@ __device__ __noinline__ void front_loop(const BatchParams& bp, const DecideArgs&
 // fronts = 0 and deciders = all warps gives the round-1 arrangement (every warp does its own byte work inline) for A/B runs.
 // FULL / LIGHT: see mut_is_light().
 constexpr int MAX_FRONTS = 4;
-static inline __host__ __device__ size_t case_smem_layout(int deciders, size_t* pw_off, size_t* slow_off, size_t* ws_off, size_t* fs_off = nullptr) {
+static inline __host__ __device__ size_t case_smem_layout(int deciders, size_t* pw_off, size_t* slow_off, size_t* ws_off, size_t* fs_off = nullptr, int tma_workers = 0, size_t* tma_off = nullptr) {
     size_t o = sizeof(JobQ);
     if (pw_off) *pw_off = o;
     o += 3 * PW_BITS * 4; o = (o + 15) & ~(size_t)15;
@@ -262,7 +265,9 @@ static inline __host__ __device__ size_t case_smem_layout(int deciders, size_t* 
     if (fs_off) *fs_off = o;
     o += sizeof(FrontState) * MAX_FRONTS; o = (o + 15) & ~(size_t)15;
     if (ws_off) *ws_off = o;
-    return o + sizeof(WarpState) * (size_t)deciders;
+    o += sizeof(WarpState) * (size_t)deciders; o = (o + 127) & ~(size_t)127;
+    if (tma_off) *tma_off = o;
+    return o + sizeof(TmaStage) * (size_t)tma_workers;
 }
 template <bool FULL>
 __global__ void __launch_bounds__(CASE_THREADS, 1)
@@ -274,8 +279,8 @@ eb_case_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ of
     if (deciders > nwarps) deciders = nwarps;
     if (fronts + deciders >= nwarps) fronts = 0;       // fronts only make sense with workers behind them
     if (fronts > MAX_FRONTS) fronts = MAX_FRONTS;
-    size_t pw_off, slow_off, ws_off, fs_off;
-    case_smem_layout(deciders, &pw_off, &slow_off, &ws_off, &fs_off);
+    size_t pw_off, slow_off, ws_off, fs_off, tma_off;
+    case_smem_layout(deciders, &pw_off, &slow_off, &ws_off, &fs_off, fa.tma_workers, &tma_off);
     JobQ* q = reinterpret_cast<JobQ*>(smem_raw);
     uint32_t* pw = reinterpret_cast<uint32_t*>(smem_raw + pw_off);                 // [3][PW_BITS]: a^(3 * 2^j) mod p
     SlowRing* slow = reinterpret_cast<SlowRing*>(smem_raw + slow_off);
@@ -294,7 +299,11 @@ eb_case_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ of
     a.fused = fa.fused; a.out = fa.out; a.out_capacity = fa.out_capacity; a.slot_off = fa.slot_off; a.out_off = fa.out_off;
     a.ovf_base = fa.ovf_base; a.ovf_used = fa.ovf_used; a.data_bytes = fa.data_bytes;
     if (warp < fronts) { front_loop(bp, a, fa, q, slow, pw, reinterpret_cast<FrontState*>(smem_raw + fs_off) + warp); return; }
-    if (warp >= fronts + deciders) { worker_loop(q); return; }
+    if (warp >= fronts + deciders) {
+        int wi = warp - fronts - deciders;       // the first tma_workers workers stage through shared memory with bulk-async copies
+        worker_loop(q, wi < fa.tma_workers ? reinterpret_cast<TmaStage*>(smem_raw + tma_off) + wi : nullptr);
+        return;
+    }
     const bool have_workers = fronts + deciders < nwarps;
     JobQ* qq = have_workers ? q : nullptr;
     WarpState* ws = wsbase + (warp - fronts);

@@ -170,15 +170,75 @@ __device__ __forceinline__ void job_countcopy(const Job& j) {
     }
 }
 
-// the worker warps' whole program
-__device__ __noinline__ void worker_loop(JobQ* q) {
+// ---- bulk-async (TMA) variant of the streaming copy, for A/B runs (EB200_TMA_WORKERS; profiles/variants_r2.txt):
+// a range whose source and destination share their 16-byte phase goes global -> shared -> global with cp.async.bulk
+// (SASS: UBLKCP), 8 KiB tiles, two staging buffers per worker, completion through an mbarrier (loads) and bulk groups
+// (stores); one elected lane issues everything, no payload byte touches a register. Other ranges take the register path.
+constexpr uint32_t TMA_TILE = 8192;
+struct TmaStage { uint8_t buf[2][TMA_TILE]; uint64_t mbar[2]; uint32_t phase[2]; uint32_t inited; uint32_t pad; };
+__device__ __forceinline__ void tma_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tma_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+}
+__device__ __noinline__ void tma_copy(TmaStage* st, uint8_t* dst, const uint8_t* src, uint64_t n) {
+    if ((((uintptr_t)dst ^ (uintptr_t)src) & 15u) != 0 || n < 2 * TMA_TILE) { warp_copy_stream<true>(dst, src, n); return; }
+    const int l = lane_id();
+    uint64_t head = (16 - ((uintptr_t)dst & 15u)) & 15u;
+    if ((uint64_t)l < head) dst[l] = src[l];
+    dst += head; src += head; n -= head;
+    uint64_t body = n & ~15ull, ntiles = (body + TMA_TILE - 1) / TMA_TILE;
+    if (l == 0) {
+        uint32_t b0 = (uint32_t)__cvta_generic_to_shared(&st->buf[0][0]), b1 = (uint32_t)__cvta_generic_to_shared(&st->buf[1][0]);
+        uint32_t m0 = (uint32_t)__cvta_generic_to_shared(&st->mbar[0]), m1 = (uint32_t)__cvta_generic_to_shared(&st->mbar[1]);
+        auto tile_bytes = [&](uint64_t t) { uint64_t o = t * TMA_TILE; return (uint32_t)(body - o < TMA_TILE ? body - o : TMA_TILE); };
+        tma_load(b0, src, tile_bytes(0), m0);
+        for (uint64_t t = 0; t < ntiles; t++) {
+            uint32_t cur = (uint32_t)(t & 1);
+            if (t + 1 < ntiles) {
+                // the other buffer was the source of store t-1: its bytes must have left shared memory before it is refilled
+                if (t >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                tma_load(cur ? b0 : b1, src + (t + 1) * TMA_TILE, tile_bytes(t + 1), cur ? m0 : m1);
+            }
+            mbar_wait_parity(cur ? m1 : m0, st->phase[cur]); st->phase[cur] ^= 1u;
+            tma_store(dst + t * TMA_TILE, cur ? b1 : b0, tile_bytes(t));
+        }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+    uint64_t tail = n - body;
+    if ((uint64_t)l < tail) dst[body + l] = src[body + l];
+}
+__device__ __forceinline__ void job_edit_tma(TmaStage* st, const Job& j) {
+    uint8_t* dst = (uint8_t*)(uintptr_t)j.a; const uint8_t* src = (const uint8_t*)(uintptr_t)j.b;
+    uint32_t n = j.len, pos = j.res, ll = (j.kind >> 8) & 255u, skip = j.kind >> 16;
+    tma_copy(st, dst, src, pos);
+    tma_copy(st, dst + pos + ll, src + pos + skip, n - pos - skip);
+}
+
+// the worker warps' whole program (st != nullptr: this worker owns a bulk-async staging area)
+__device__ __noinline__ void worker_loop(JobQ* q, TmaStage* st) {
     Job j;
+    if (st && lane_id() == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&st->mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&st->mbar[1])) : "memory");
+        st->phase[0] = st->phase[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     while (jobq_get(q, j)) {
         switch (j.kind & 255u) {
-        case JOB_EDIT: job_edit(j); break;
+        case JOB_EDIT: if (st) job_edit_tma(st, j); else job_edit(j); break;
         case JOB_SELECT_DIGIT: job_select(j); break;
         case JOB_COUNTCOPY_DIGIT: job_countcopy(j); break;
-        case JOB_COPY_NC: warp_copy_stream<true>((uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); break;
+        case JOB_COPY_NC: if (st) tma_copy(st, (uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); else warp_copy_stream<true>((uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); break;
         case JOB_COPY: warp_copy_stream<false>((uint8_t*)(uintptr_t)j.a, (const uint8_t*)(uintptr_t)j.b, j.len); break;
         case JOB_COUNT_DIGIT: job_count<PRED_DIGIT, true>(j); break;
         default: job_count<PRED_NEWLINE, false>(j); break;

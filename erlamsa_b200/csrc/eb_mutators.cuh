@@ -91,6 +91,10 @@ EB_DEV void mut_bytes(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutResul
             uint8_t* buf = scratch_alloc(c, (uint64_t)m * 9);
             if (!buf) { r.kind = RES_SAME; r.delta = 0; return; }
             uint64_t* K = (uint64_t*)buf; uint8_t* V = buf + (uint64_t)m * 8;
+            if (g.mode != 0) {   // Philox: key i is draw i of this mutator's slot -- 32 keys per step
+                for (uint32_t i = lane_id(); i < l; i += 32) { K[i] = (uint64_t)__double_as_longlong(g.uniform_philox_at(g.local + i)); V[i] = p[s + i]; }
+                g.philox_skip(l);
+            } else
             for (uint32_t i = 0; i < l; i++) { double u = g.uniform(); if (lane_id() == 0) { K[i] = (uint64_t)__double_as_longlong(u); V[i] = p[s + i]; } }
             for (uint32_t i = l + lane_id(); i < m; i += 32) { K[i] = ~0ull; V[i] = 0xff; }
             __syncwarp();
@@ -102,6 +106,20 @@ EB_DEV void mut_bytes(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutResul
         uint8_t* buf = scratch_alloc(c, l);
         if (!buf) { r.kind = RES_SAME; r.delta = 0; return; }
         uint64_t prob = g.erand(100);
+        if (g.mode != 0) {   // Philox: byte i owns draws 2i (does the mask apply) and 2i + 1 (which bit / byte) of this slot
+            for (uint32_t i = lane_id(); i < l; i += 32) {
+                uint64_t nn = (uint64_t)trunc(g.uniform_philox_at(g.local + 2 * i) * 100.0);
+                bool oc = prob == 1 ? nn != 0 : nn < prob;                      // rand_occurs_fixed/2, quirk included
+                uint32_t h = p[s + i];
+                if (oc) {
+                    double u = g.uniform_philox_at(g.local + 2 * i + 1);
+                    uint32_t bit = 1u << (uint32_t)trunc(u * 8.0);
+                    if (kind == 0) h &= ~bit; else if (kind == 1) h |= bit; else if (kind == 2) h ^= bit; else h = (uint32_t)trunc(u * 256.0);
+                }
+                buf[i] = (uint8_t)h;
+            }
+            g.philox_skip(2 * l);
+        } else {
         bool occ = g.rand_occurs_fixed(prob, 100);
         for (uint32_t i = 0; i < l; i++) {
             bool nxt = g.rand_occurs_fixed(prob, 100);
@@ -114,6 +132,7 @@ EB_DEV void mut_bytes(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutResul
             }
             if (lane_id() == 0) buf[i] = (uint8_t)h;
             occ = nxt;
+        }
         }
         __syncwarp();
         t_push(ws, seg_copy(buf, l));

@@ -6,8 +6,10 @@
 //    draw-for-draw "exact" mode. Each component is x_k = x_0 * a^k mod p, so the stream can be
 //    entered at any draw index with three modular exponentiations (used to derive per-case seeds
 //    without replaying the parent stream, reference src/erlamsa_main.erl:179).
-//  * Philox4x32-10 keyed by (option seed, global case id), counter = draw index: every draw is an
-//    independent function of its index -- no serial state, distribution-equivalent decisions.
+//  * Philox4x32-10 keyed by the option seed; counter = (index inside the slot, SLOT, global case id), where a slot is
+//    (mutation round, who draws: scheduler / mutator id / pattern): every decision has its own counter range, so a mutator
+//    that fails or draws more does not shift anybody else's draws, and per-byte draws (sp / snand / srnd) are computed by
+//    32 lanes at once (uniform_philox_at). Distribution-equivalent, not bit-equal, to the reference stream.
 //
 // All helpers mirror erlamsa_rnd's API one to one (names and N = 0 "no draw" rules included),
 // reference src/erlamsa_rnd.erl:65-242.
@@ -52,13 +54,24 @@ struct Rng {
     uint64_t draws;          // draw index (also the Philox counter)
     int32_t mode;            // 0 AS183, 1 Philox
     uint64_t key, ctr_hi;    // Philox: key = option seed hash, ctr_hi = global case id
+    uint32_t slot, local;    // Philox: current slot and the next index inside it
+    // Philox only: start drawing from slot s (no-op for AS183, whose stream is one sequence by definition)
+    EB_HD void set_slot(uint32_t s) { if (mode != 0) { slot = s; local = 0; } }
+    // Philox only: draw number `idx` of the current slot, without advancing anything (lane-parallel loops)
+    EB_HD double uniform_philox_at(uint32_t idx) const {
+        uint32_t o[4];
+        philox4x32_10(idx, slot, (uint32_t)ctr_hi, (uint32_t)(ctr_hi >> 32), (uint32_t)key, (uint32_t)(key >> 32), o);
+        uint64_t v = ((uint64_t)o[0] << 32) | o[1];
+        return (double)(v >> 11) * (1.0 / 9007199254740992.0);
+    }
+    EB_HD void philox_skip(uint32_t n) { local += n; draws += n; }
 
     // erlamsa_rnd:seed/1 -> random:seed/3
     EB_HD void seed(int64_t s1, int64_t s2, int64_t s3) {
         a1 = (int32_t)((s1 < 0 ? -s1 : s1) % 30268) + 1;
         a2 = (int32_t)((s2 < 0 ? -s2 : s2) % 30306) + 1;
         a3 = (int32_t)((s3 < 0 ? -s3 : s3) % 30322) + 1;
-        draws = 0;
+        draws = 0; slot = 0; local = 0;
     }
     // skip k draws of the AS183 stream in O(log k)
     EB_HD void jump(uint64_t k) {
@@ -83,8 +96,8 @@ struct Rng {
     }
     EB_HD double uniform_philox() {
         uint32_t o[4];
-        philox4x32_10((uint32_t)draws, (uint32_t)(draws >> 32), (uint32_t)ctr_hi, (uint32_t)(ctr_hi >> 32), (uint32_t)key, (uint32_t)(key >> 32), o);
-        draws++;
+        philox4x32_10(local, slot, (uint32_t)ctr_hi, (uint32_t)(ctr_hi >> 32), (uint32_t)key, (uint32_t)(key >> 32), o);
+        draws++; local++;
         uint64_t v = ((uint64_t)o[0] << 32) | o[1];
         return (double)(v >> 11) * (1.0 / 9007199254740992.0);
     }

@@ -15,7 +15,7 @@
 
 namespace eb {
 
-constexpr int MAX_RUNS = 24;
+constexpr int MAX_RUNS = 64;
 constexpr int MAX_VSEG = 16;
 constexpr int MAX_OSEG = 48;
 
@@ -48,6 +48,9 @@ struct WarpState {
     struct Wrap { uint32_t kind; uint32_t bits; uint32_t big; uint32_t tail_n; uint64_t field_pos; uint64_t mark; const uint8_t* tail_p; } wrap[8];
     int nwrap;
     const uint8_t* fo_p; uint32_t fo_n; int fo_has;
+    // file / stdin generators: the block list does not exist until the pattern's first uncons (eb_decide.cuh force_stream)
+    int lazy; const uint8_t* lz_p; uint32_t lz_n;
+    uint32_t round;          // mux_fuzzers rounds so far in this case (Philox counter slots, eb_rng.cuh)
     uint64_t donor;          // this case's donor index (thread seed hash, see mut_fuse)
     uint16_t sc[SC_MAX];
     uint32_t qpend;          // countdown of this warp's outstanding scan jobs (eb_jobs.cuh)

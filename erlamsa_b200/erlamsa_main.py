@@ -1,13 +1,21 @@
-"""Python mirror of the reference's driver entry, erlamsa_main:fuzzer/1 (reference
-src/erlamsa_main.erl:124-247), for paths == [direct] / output == return, backed by the CUDA engine.
+"""Python mirror of the reference's driver entry, erlamsa_main:fuzzer/1 (reference src/erlamsa_main.erl:124-247), backed by the
+CUDA engine, for the generators and outputs that are part of the hot path's surroundings:
 
-    fuzzer(#{paths => [direct], input => Bin, seed => {A,B,C}, n => N, mutations => [...], patterns => [...]})
-        -> [binary()]            (empty outputs are not recorded, record_result/2 :120-122)
+    paths  => [direct] with input => Bin | [Bin]   direct generator (src/erlamsa_gen.erl:152-164); a LIST is a corpus: case I
+                                                     mutates element (I-1) rem length -- the batched generalisation
+    paths  => ["file1", "dir/file2", ...]           file generator (:104-121): every case picks one of the files (erand), which is
+                                                     cut lazily into random-size blocks (rand_block_size :55-56)
+    paths  => ["-"]                                 stdin generator (:92-102), n == 1 only (the reference pre-reads stdin in the
+                                                     parent process for n > 1, which is not modelled)
+    output => return                                -> [binary()], empty results dropped like record_result/2 (:120-122)
+    output => "out/fuzz-%n.bin"                     file writer (src/erlamsa_out.erl:103-123): %n = case number; returns []
+                                                     like the reference does for non-direct outputs
 
-`fuzz/1` is the spelling BASELINE.json's north star uses for the same entry. `input` may also be a
-LIST of binaries (a corpus): case I then mutates element (I-1) rem length -- the batched
-generalisation the engine exists for; n defaults to the corpus size.
+`fuzz/1` is the spelling BASELINE.json's north star uses for the same entry.
 """
+import os
+import sys
+
 from .engine import Engine
 
 _engine = None
@@ -20,24 +28,57 @@ def _get_engine():
     return _engine
 
 
+def _file_name(template, n):
+    """build_name/3 (src/erlamsa_out.erl:103-107): every %n becomes the case number"""
+    return template.replace("%n", str(n))
+
+
 def fuzzer(opts):
     opts = dict(opts)
-    paths = opts.get("paths", ["-"])
-    if list(paths) != ["direct"]:
-        raise NotImplementedError("only paths => [direct] is served by the batch engine; "
-                                  "stdin/file/network front-ends stay in Erlang (SURVEY.md 8b)")
-    if opts.get("output", "return") != "return":
-        raise NotImplementedError("only output => return")
-    inp = opts.get("input")
-    if inp is None:
-        raise ValueError("direct generator needs `input`")
-    blobs = [bytes(inp)] if isinstance(inp, (bytes, bytearray, memoryview)) else [bytes(b) for b in inp]
-    n = int(opts.get("n", len(blobs) if len(blobs) > 1 else 1))
-    skip = int(opts.get("skip", 0))
+    paths = list(opts.get("paths", ["-"]))
+    output = opts.get("output", "-")
+    if output != "return" and not isinstance(output, str):
+        raise NotImplementedError("network / exec outputs stay in Erlang (SURVEY.md section 2)")
     o = dict(opts)
+    skip = int(opts.get("skip", 0))
+    if paths == ["direct"]:
+        inp = opts.get("input")
+        if inp is None:
+            raise ValueError("direct generator needs `input`")
+        blobs = [bytes(inp)] if isinstance(inp, (bytes, bytearray, memoryview)) else [bytes(b) for b in inp]
+        n = int(opts.get("n", len(blobs) if len(blobs) > 1 else 1))
+    elif paths == ["-"]:
+        n = int(opts.get("n", 1))
+        if n != 1:
+            raise NotImplementedError("stdin with n > 1: the reference pre-reads stdin in the parent process (src/erlamsa_gen.erl:98-101)")
+        blobs = [opts["stdin_data"] if "stdin_data" in opts else sys.stdin.buffer.read()]
+        o.setdefault("generators", {"stdin": 100000, "random": 1})       # what make_generator keeps of the defaults for ["-"]
+    else:
+        blobs = []
+        for p in paths:
+            with open(p, "rb") as f:
+                blobs.append(f.read())
+        n = int(opts.get("n", 1))
+        if "generators" not in o:                                         # defaults for file paths; `jump` has no device implementation
+            o["generators"] = {"file": 1000, "random": 1}
+    for k in ("paths", "output", "input", "n", "skip", "stdin_data"):
+        o.pop(k, None)
     o["first_case"] = skip + 1
     outs, _meta = _get_engine().fuzz_batch(blobs, o, n_cases=max(n - skip, 0))
-    return [x for x in outs if x != b""]
+    if output == "return":
+        return [x for x in outs if x != b""] if paths == ["direct"] else []
+    if output == "-":
+        for x in outs:
+            sys.stdout.buffer.write(x)
+        return []
+    for k, x in enumerate(outs):                                          # file_writer/1: one file per case, numbered from skip + 1
+        name = _file_name(output, skip + 1 + k)
+        d = os.path.dirname(name)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        with open(name, "wb") as f:
+            f.write(x)
+    return []
 
 
 fuzz = fuzzer

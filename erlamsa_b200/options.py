@@ -88,6 +88,11 @@ def make_opts(opts=None):
         g = dict(opts["generators"])
         o.gen_direct_pri = int(g.get("direct", -1))
         o.gen_random_pri = int(g.get("random", -1))
+        o.gen_file_pri = int(g.get("file", -1))
+        o.gen_stdin_pri = int(g.get("stdin", -1))
+        unknown = set(g) - {"direct", "random", "file", "stdin"}
+        if unknown:
+            raise ValueError("generator(s) without a device implementation: %s" % ", ".join(sorted(unknown)))
     o.ssrf_host = str(opts.get("ssrf_host", "localhost")).encode()[:63]
     o.ssrf_port = int(opts.get("ssrf_port", 51234))
     o.rng_mode = {"as183": 0, "philox": 1}[opts.get("rng", "as183")]

@@ -82,6 +82,12 @@ typedef struct eb200_opts {
     uint64_t n_donors;
     uint32_t donor_stride;
     uint32_t reserved0;
+    /* option `generators` for paths that are files / stdin (reference src/erlamsa_gen.erl:59-121, :232-236): `file` (1000) makes every
+     * case pick its blob with erand(n_blobs) and cuts it lazily into random-size blocks (256..4095 x blockscale); `stdin` (100000) is
+     * the same over blob (I-1) mod n_blobs and is only the reference's behaviour for n == 1 (with n > 1 the reference pre-reads stdin
+     * in the parent process: EB200_ERR_UNSUPPORTED). -1 = not selected (default). `jump` is not implemented. */
+    int32_t  gen_file_pri;
+    int32_t  gen_stdin_pri;
 } eb200_opts;
 
 typedef struct eb200_meta {

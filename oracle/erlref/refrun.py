@@ -85,3 +85,34 @@ class Reference(object):
             i = first_case + k
             out.append(self.case(blobs[(i - 1) % len(blobs)], i, seed, mutations, patterns, **kw))
         return out
+
+
+    def case_paths(self, files, case_no, seed, mutations=None, patterns=None, stdin=None, generators=None, **kw):
+        """test case `case_no` of fuzzer(#{paths => Files | ["-"], output => return, ...}): the file / stdin generators.
+        files: list of byte strings (virtual files f0, f1, ...); stdin: bytes (paths = ["-"], only meaningful with case_no == 1).
+        Non-direct paths do not record results (src/erlamsa_main.erl:143), so the written bytes are read back from the
+        erlamsa_logger:log_data call the driver makes for every case (:199)."""
+        rt = self.rt
+        rt.vfs = {"f%d" % i: b for i, b in enumerate(files or [])}
+        paths = ["-"] if stdin is not None else ["f%d" % i for i in range(len(files))]
+        rt.stdin.data = stdin or b""
+        rt.stdin.pos = 0
+        opts = self.opts_map(b"", seed, mutations, patterns, n=case_no, skip=case_no - 1, generators=generators, **kw)
+        del opts["input"]
+        opts["paths"] = from_py([from_py([ord(c) for c in p]) for p in paths])
+        opts["maxrunningtime"] = 600000
+        rt.logged_data = []
+        try:
+            rt.steps = 0
+            rt.budget = self.budget
+            rt.child_draws = []
+            rt.last_crash = None
+            rt.call("erlamsa_main", "fuzzer", opts)
+        except BudgetExceeded:
+            return RefResult(b"", 0, "budget")
+        except rt.Unsupported as e:
+            return RefResult(b"", 0, "unsupported", str(e))
+        if rt.last_crash is not None:
+            return RefResult(b"", rt.child_draws[-1] if rt.child_draws else 0, "died", str(rt.last_crash))
+        out = rt.logged_data[-1] if rt.logged_data else b""
+        return RefResult(out, rt.child_draws[-1] if rt.child_draws else 0, "ok")

@@ -52,6 +52,8 @@ struct Opts {
     int pat_pri[P_COUNT];    // -1: not selected
     int gen_direct_pri = 500;   // src/erlamsa_gen.erl:246-253 (-1: not selected)
     int gen_random_pri = 1;
+    int gen_file_pri = -1;      // paths = files (src/erlamsa_gen.erl:104-121): case picks blob erand(N), lazily split into random-size blocks
+    int gen_stdin_pri = -1;     // paths = ["-"] with n == 1 (:92-102): the blob is the stdin data, split lazily like a file
     std::string ssrf_host = "localhost";   // get_ssrf_ep/0 default, src/erlamsa_mutations.erl:697-702
     int ssrf_port = 51234;
     // cross-seed donor pool for sed_fuse_old (BASELINE config C5; not a reference option, see fuse_old in mutations.hpp)

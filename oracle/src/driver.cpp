@@ -27,6 +27,11 @@ struct CaseRunner {
     const std::vector<std::pair<int, int>>& sorted_pats;   // {pri, PatId} after sort_by_priority
     int pat_sum;
     using Cont = std::function<Blocks(const Blocks&)>;
+    // file / stdin generators hand the pattern an UNFORCED stream (port_stream/2 returns a fun, src/erlamsa_gen.erl:59-61): the
+    // blocks -- one rand_block_size draw each -- and the finish/1 tail come into being at the pattern's first uncons/2, i.e.
+    // after the pattern's own first draws (SURVEY.md appendix A, W1'')
+    std::function<Blocks()> lazy;
+    Blocks force(const Blocks& ll) { if (!lazy) return ll; auto f = lazy; lazy = nullptr; return f(); }
 
     // split/1 :45-60 -- oversize head blocks are cut up (with draws)
     void split_big(Bin& th, Blocks& rest) {
@@ -57,9 +62,10 @@ struct CaseRunner {
         }
     }
     // mutate_once/4 :267-278
-    Blocks mutate_once(const Blocks& ll, const Cont& cont) {
-        if (ll.size() == 1 && ll[0].empty()) return Blocks();   // {Mutator, Meta}: nothing is written
+    Blocks mutate_once(const Blocks& ll0, const Cont& cont) {
+        if (!lazy && ll0.size() == 1 && ll0[0].empty()) return Blocks();   // {Mutator, Meta}: nothing is written
         uint64_t ip = rng.rand(INITIAL_IP);
+        Blocks ll = force(ll0);
         if (ll.empty()) return cont(Blocks());
         Bin th = ll[0]; Blocks rest(ll.begin() + 1, ll.end());
         split_big(th, rest);
@@ -115,14 +121,15 @@ struct CaseRunner {
         case P_ND: return mutate_once(ll, cont_nd());
         case P_BU: return mutate_once(ll, cont_bu());
         case P_CO: if (rng.erand(2) == 1) return run_pattern(P_NU, ll); return run_pattern(P_OD, ll);
-        case P_NU: { Blocks o = ll; if (!o.empty()) { Bin th = o[0]; Blocks rest(o.begin() + 1, o.end()); split_big(th, rest); o.clear(); o.push_back(th); o.insert(o.end(), rest.begin(), rest.end()); } return o; }
+        case P_NU: { Blocks o = force(ll); if (!o.empty()) { Bin th = o[0]; Blocks rest(o.begin() + 1, o.end()); split_big(th, rest); o.clear(); o.push_back(th); o.insert(o.end(), rest.begin(), rest.end()); } return o; }
         default: break;
         }
         // make_complex_pat :352-357: the continuation is drawn uniformly from all ten patterns
         int next = (int)rng.rand_elem_idx(P_COUNT);
         uint64_t ip = rng.rand(INITIAL_IP);
-        if (ll.empty()) throw CaseDied("complex pattern on an empty block list");
-        Bin bin = ll[0]; Blocks rest(ll.begin() + 1, ll.end());
+        Blocks llf = force(ll);
+        if (llf.empty()) throw CaseDied("complex pattern on an empty block list");
+        Bin bin = llf[0]; Blocks rest(llf.begin() + 1, llf.end());
         if (pat == P_SK) {   // mutate_once_skipper :148-161
             uint64_t len = rng.rand((uint64_t)std::trunc((double)bin.size() / 2.0));
             Bin head = bin.substr(0, len), th = bin.substr(len);
@@ -171,7 +178,8 @@ struct CaseRunner {
 struct Fuzzer {
     Opts opts; Rng parent; Mutations muts; std::vector<MutNode> fs0;
     std::vector<std::pair<int, int>> sorted_pats; int pat_sum = 0;
-    int generator = 0;   // 0 direct, 1 random
+    int generator = 0;   // 0 direct, 1 random, 2 file, 3 stdin (n == 1)
+    const uint8_t* corpus_data = nullptr; const uint64_t* corpus_off = nullptr; uint64_t corpus_n = 0;   // for the file generator's path choice
 
     explicit Fuzzer(const Opts& o) : opts(o), muts(parent, opts) {
         parent.seed(opts.seed[0], opts.seed[1], opts.seed[2]);   // :134
@@ -181,6 +189,8 @@ struct Fuzzer {
         std::vector<std::pair<int, int>> gs;                       // {pri, kind}; option order: random, ..., direct
         if (opts.gen_random_pri >= 0) gs.push_back({opts.gen_random_pri, 1});
         if (opts.gen_direct_pri >= 0) gs.push_back({opts.gen_direct_pri, 0});
+        if (opts.gen_file_pri >= 0) gs.push_back({opts.gen_file_pri, 2});
+        if (opts.gen_stdin_pri >= 0) gs.push_back({opts.gen_stdin_pri, 3});
         if (gs.empty()) throw Unsupported("no generators");
         generator = choose_pri(sort_by_priority(gs), parent, true);
         // make_pattern :409-422: foldl prepends -> reversed table order, then sort_by_priority
@@ -211,6 +221,16 @@ struct Fuzzer {
     uint64_t rand_block_size(Rng& rng) {   // :55-56
         return std::max<uint64_t>(rng.rand((uint64_t)erl_round(MAX_BLOCK_SIZE * opts.blockscale)), (uint64_t)erl_round(MIN_BLOCK_SIZE * opts.blockscale));
     }
+    // stream_port/5 :65-88 over an in-memory file: full blocks of the wanted size (a new size is drawn after each), the short
+    // rest as the last block, then finish/1 of the total length
+    Blocks stream_blocks(Rng& rng, const Bin& input) {
+        Blocks ll; uint64_t pos = 0, n = input.size();
+        uint64_t wanted = rand_block_size(rng);
+        while (n - pos >= wanted) { ll.push_back(input.substr(pos, wanted)); pos += wanted; wanted = rand_block_size(rng); }
+        if (pos < n) ll.push_back(input.substr(pos));
+        finish(rng, n, ll);
+        return ll;
+    }
     Blocks generate(Rng& rng, const Bin& input) {
         Blocks ll;
         if (generator == 0) {   // direct_generator :161-164 (split_binary's first clause never matches)
@@ -239,8 +259,18 @@ struct Fuzzer {
         m.thread_seed[0] = ts[0]; m.thread_seed[1] = ts[1]; m.thread_seed[2] = ts[2];
         Bin out;
         try {
-            Blocks ll = generate(rng, input);
+            Blocks ll;
             CaseRunner cr{rng, opts, m, fs0, meta, sorted_pats, pat_sum};
+            if (generator == 2 || generator == 3) {
+                Bin in = input;
+                if (generator == 2) {      // file_streamer :106-121: P = erand(N) picks the path
+                    if (!corpus_data || !corpus_n) throw Unsupported("file generator without a corpus");
+                    uint64_t p = rng.erand(corpus_n) - 1;
+                    in = Bin((const char*)corpus_data + corpus_off[p], corpus_off[p + 1] - corpus_off[p]);
+                }
+                Rng* rp = &rng;
+                cr.lazy = [this, rp, in]() { return stream_blocks(*rp, in); };
+            } else ll = generate(rng, input);
             int pat = choose_pri(sorted_pats, rng, false);
             meta.pattern = pat;
             Blocks res = cr.run_pattern(pat, ll);
@@ -269,6 +299,7 @@ struct eo_opts_c {
     int32_t ssrf_port;
     uint64_t max_case_out;
     const uint8_t* donor_pool; const uint32_t* donor_len; uint64_t n_donors; uint32_t donor_stride; uint32_t pad;
+    int32_t gen_file_pri, gen_stdin_pri;
 };
 struct eo_meta_c {
     int32_t pattern, generator, n_used, n_failed;
@@ -286,6 +317,7 @@ static eo::Opts conv(const eo_opts_c* c) {
     o.gen_direct_pri = c->gen_direct_pri; o.gen_random_pri = c->gen_random_pri;
     o.ssrf_host = std::string(c->ssrf_host, strnlen(c->ssrf_host, 64)); o.ssrf_port = c->ssrf_port;
     if (c->max_case_out) o.max_case_out = c->max_case_out;
+    o.gen_file_pri = c->gen_file_pri; o.gen_stdin_pri = c->gen_stdin_pri;
     o.donor_pool = c->donor_pool; o.donor_len = c->donor_len; o.n_donors = c->n_donors; o.donor_stride = c->donor_stride;
     return o;
 }
@@ -302,7 +334,7 @@ void eo_default_opts(eo_opts_c* c) {
     c->blockscale = 1.0;
     for (int i = 0; i < eo::M_COUNT; i++) c->muta_pri[i] = o.muta_pri[i];
     for (int i = 0; i < eo::P_COUNT; i++) c->pat_pri[i] = o.pat_pri[i];
-    c->gen_direct_pri = 500; c->gen_random_pri = 1;
+    c->gen_direct_pri = 500; c->gen_random_pri = 1; c->gen_file_pri = -1; c->gen_stdin_pri = -1;
     strcpy(c->ssrf_host, "localhost"); c->ssrf_port = 51234;
 }
 
@@ -317,6 +349,7 @@ static void* run_thread(void* p) {
     RunArgs* a = (RunArgs*)p;
     try {
         eo::Fuzzer f(conv(a->opts));
+        f.corpus_data = a->data; f.corpus_off = a->off; f.corpus_n = a->n_blobs;
         eo::Meta skip;
         for (uint64_t i = 1; i < a->first_case; i++) { int64_t ts[3]; f.parent.gen_predictable_seed(ts); }
         a->out_off[0] = 0;

@@ -1,5 +1,5 @@
 """A/B timing of engine configurations on the C3 workload (not a test; run on the GPU box).
-usage: python tests/perf_variants.py "deciders:threads[:fronts],..." [cases]
+usage: python tests/perf_variants.py "deciders:threads[:fronts[:depth[:tma_workers]]],..." [cases]
 Every configuration is (EB200_DECIDERS, EB200_THREADS) of eb_case_kernel: how many of the CTA's warps decide cases, the
 rest being copy/scan workers (deciders == threads/32 is the round-1 arrangement: every warp does its own byte work)."""
 import os
@@ -24,7 +24,8 @@ muts = {c: 1 for c in os.environ.get("PERF_MUTS", "bd,bei,bed,bf,bi,ber,br,num")
 for cfg in configs:
     dec, thr = cfg[0], cfg[1]
     fr = cfg[2] if len(cfg) > 2 else 1
-    os.environ["EB200_FRONT_DEPTH"] = str(cfg[3] if len(cfg) > 3 else 8)
+    os.environ["EB200_FRONT_DEPTH"] = str(cfg[3] if len(cfg) > 3 else 32)
+    os.environ["EB200_TMA_WORKERS"] = str(cfg[4] if len(cfg) > 4 else 0)
     os.environ["EB200_DECIDERS"] = str(dec)
     os.environ["EB200_THREADS"] = str(thr)
     os.environ["EB200_FRONTS"] = str(fr)
@@ -39,6 +40,6 @@ for cfg in configs:
     res = res[2:]
     avg = [sum(r[k] for r in res) / len(res) for k in range(4)]
     gbs = (2 * n_cases * size) / ((avg[2] or avg[0]) * 1e-3) / 1e9
-    print("depth %s fronts %d deciders %d threads %d: kernel %.3f  scan %.3f  apply %.3f ms (%.0f GB/s = %.2f of 6572)  total %.3f  launches %d"
-          % (os.environ["EB200_FRONT_DEPTH"], fr, dec, thr, avg[0], avg[1], avg[2], gbs, gbs / 6572.2, avg[3], st.kernels_launched), flush=True)
+    print("tma %s depth %s fronts %d deciders %d threads %d: kernel %.3f  scan %.3f  apply %.3f ms (%.0f GB/s = %.2f of 6572)  total %.3f  launches %d"
+          % (os.environ["EB200_TMA_WORKERS"], os.environ["EB200_FRONT_DEPTH"], fr, dec, thr, avg[0], avg[1], avg[2], gbs, gbs / 6572.2, avg[3], st.kernels_launched), flush=True)
     eng.close()

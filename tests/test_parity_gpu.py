@@ -271,6 +271,29 @@ def test_philox_mode_is_distribution_equivalent(engine, oracle):
         assert chi2 < 3.0 * dof + 25, "%s histograms differ: chi2 %.1f on %d dof\n%r\n%r" % (name, chi2, dof, dict(a), dict(b))
 
 
+def test_philox_mode_whole_table_distribution(engine, oracle):
+    """the same check over the WHOLE default table (all 41 mutators, all patterns): which mutator gets applied first, which
+    pattern runs and how many rounds a case takes must be distributed as under the reference stream"""
+    import collections
+    blobs = corpus.mixed_corpus(0xE21A0C41, 48, 300, kinds=("num", "lines", "bin")) + corpus.text_corpus(0xE21A0C42, 16, 300)
+    n = 6000
+    ref, rmeta = oracle.fuzzer(blobs, seed=(1, 2, 3), n_cases=n, max_case_out=1 << 18)
+    got, gmeta = engine.fuzz_batch(blobs, {"seed": (1, 2, 3), "rng": "philox", "max_case_out": 1 << 18}, n_cases=n)
+    keep_r = [m for m in rmeta if m.status == 0]
+    keep_g = [m for m in gmeta if m.status == 0]
+    assert len(keep_g) > 0.9 * n and len(keep_r) > 0.9 * n
+
+    def hists(meta):
+        return (collections.Counter(m.pattern for m in meta), collections.Counter(m.used[0] for m in meta), collections.Counter(min(m.n_used, 5) for m in meta))
+
+    for name, a, b in zip(("pattern", "first mutator", "rounds"), hists(keep_r), hists(keep_g)):
+        keys = sorted(set(a) | set(b))
+        sa, sb = sum(a.values()), sum(b.values())
+        chi2 = sum((a[k] / sa - b[k] / sb) ** 2 / max(a[k] / sa + b[k] / sb, 1e-9) for k in keys) * min(sa, sb)
+        dof = max(len(keys) - 1, 1)
+        assert chi2 < 3.0 * dof + 30, "%s histograms differ: chi2 %.1f on %d dof\n%r\n%r" % (name, chi2, dof, dict(a), dict(b))
+
+
 def test_philox_mode_runs_and_differs(engine):
     blobs = corpus.mixed_corpus(0xE21A0400, 200)
     a, _ = engine.fuzz_batch(blobs, {"mutations": {"bd": 1, "bf": 1, "num": 1}, "patterns": {"od": 1}, "seed": (1, 2, 3), "rng": "philox"})

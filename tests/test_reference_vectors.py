@@ -110,3 +110,60 @@ def test_otp_run_matches_committed_vectors():
         if st != "ok" or digest(out) != v["digests"][k]:
             bad.append((name, k, st))
     assert n > 0 and not bad, bad[:10]
+
+
+# ---------------------------------------------------------------- file / stdin generators (reference_vectors_paths.json)
+PATHS_PATH = os.path.join(HERE, "golden", "reference_vectors_paths.json")
+PVEC = json.load(open(PATHS_PATH))["vectors"] if os.path.exists(PATHS_PATH) else []
+
+
+def _paths_opts(v):
+    gens = v["generators"]
+    if v["stdin"] is not None:
+        gens = gens or {"stdin": 100000, "random": 1}       # what make_generator keeps of the defaults for paths = ["-"]
+        blobs = [bytes.fromhex(v["stdin"])]
+    else:
+        blobs = [bytes.fromhex(b) for b in v["files"]]
+    return blobs, gens
+
+
+@pytest.mark.parametrize("v", PVEC, ids=[v["name"] for v in PVEC])
+def test_oracle_matches_reference_file_and_stdin_generators(v, oracle):
+    blobs, gens = _paths_opts(v)
+    kw = dict(v["extra"])
+    bad = []
+    for idx, i in enumerate(v["cases"]):
+        outs, meta = oracle.fuzzer(blobs, mutations=v["mutations"], patterns=v["patterns"], seed=tuple(v["seed"]), generators=gens, n_cases=1, first_case=i,
+                                   max_case_out=1 << 26, **kw)
+        if v["status"][idx] == "ok" and (meta[0].status != 0 or digest(outs[0]) != v["digests"][idx] or meta[0].draws != v["draws"][idx]):
+            bad.append((i, meta[0].status, len(outs[0]), v["digests"][idx][0], meta[0].draws, v["draws"][idx]))
+    assert not bad, bad[:8]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("v", PVEC, ids=[v["name"] for v in PVEC])
+def test_engine_matches_reference_file_and_stdin_generators(v, engine):
+    blobs, gens = _paths_opts(v)
+    bad, flagged = [], {}
+    for idx, i in enumerate(v["cases"]):
+        opts = {"seed": tuple(v["seed"]), "first_case": i, "max_case_out": 1 << 26, "generators": gens}
+        if v["mutations"] is not None:
+            opts["mutations"] = v["mutations"]
+        if v["patterns"] is not None:
+            opts["patterns"] = v["patterns"]
+        opts.update(v["extra"])
+        if v["stdin"] is not None:
+            opts["first_case"] = 1
+        outs, meta = engine.fuzz_batch(blobs, opts, n_cases=1)
+        if meta[0].status not in (0, 2):
+            flagged[str(i)] = [meta[0].status, meta[0].pad]
+            continue
+        if v["status"][idx] == "ok" and (meta[0].status != 0 or digest(outs[0]) != v["digests"][idx] or meta[0].draws != v["draws"][idx]):
+            bad.append((i, meta[0].status, len(outs[0]), v["digests"][idx][0], meta[0].draws, v["draws"][idx]))
+    if os.environ.get("EB200_DUMP_FLAGS"):
+        p = os.path.join(os.path.dirname(HERE), "gpurun_out", "flags_seen.json")
+        seen = json.load(open(p)) if os.path.exists(p) else {}
+        seen[v["name"]] = flagged
+        json.dump(seen, open(p, "w"), indent=0, sort_keys=True)
+    assert not bad, "engine differs from the reference at %r" % bad[:8]
+    assert flagged == EXPECTED_FLAGS.get(v["name"], {}), "flagged set changed: %r" % flagged
