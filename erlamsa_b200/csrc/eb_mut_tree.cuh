@@ -43,15 +43,42 @@ EB_DEV uint32_t tree_parse(CaseCtx& c, const uint8_t* p, uint32_t n, TNode** out
     *out = nodes;
     if (!nodes || !stack) return 0;
     uint32_t sp = 0, nn = 0; int topclose = -1;
-    for (uint32_t i = 0; i < n; i++) {
-        uint32_t h = p[i];
-        if ((int)h == topclose) {   // the innermost open node closes (checked before "is it an opener", :807-808)
-            nodes[stack[sp - 1] & 0xffffffu].e = i + 1; sp--;
-            topclose = sp ? (int)(stack[sp - 1] >> 24) : -1;
-            continue;
+    // Only the ten delimiter bytes ( ) [ ] < > { } " ' can open or close a node; everything else leaves the automaton where
+    // it is. Each 512-byte window is classified 32 lanes wide (one 16-bit mask per lane), the automaton then visits the
+    // candidates only -- a dependent memory access per byte was 80-110 ms per 256 KiB call (gpurun_out/tc_c4.log).
+    {
+        const uint32_t lead = (uint32_t)((uintptr_t)p & 15u); const uint8_t* base = p - lead; const uint32_t span = lead + n;
+        for (uint32_t w0 = 0; w0 < span; w0 += 512) {
+            uint32_t wofs = w0 + (uint32_t)lane_id() * 16u;
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (wofs < span && wofs + 16 > lead) r = *reinterpret_cast<const uint4*>(base + wofs);
+            uint32_t words[4] = {r.x, r.y, r.z, r.w};
+            uint32_t m = 0;
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                uint32_t ch = (words[q >> 2] >> ((q & 3) * 8)) & 255u;
+                bool d = ch == '(' || ch == ')' || ch == '[' || ch == ']' || ch == '<' || ch == '>' || ch == '{' || ch == '}' || ch == '"' || ch == 39;
+                if (d && wofs + q >= lead && wofs + q < span) m |= 1u << q;
+            }
+            uint32_t lanes = __ballot_sync(0xffffffffu, m != 0);
+            while (lanes) {
+                int L = __ffs(lanes) - 1; lanes &= lanes - 1;
+                uint32_t mm = __shfl_sync(0xffffffffu, m, L);
+                uint32_t w4[4] = {__shfl_sync(0xffffffffu, r.x, L), __shfl_sync(0xffffffffu, r.y, L), __shfl_sync(0xffffffffu, r.z, L), __shfl_sync(0xffffffffu, r.w, L)};
+                while (mm) {
+                    int q = __ffs(mm) - 1; mm &= mm - 1;
+                    uint32_t i = w0 + (uint32_t)L * 16u + (uint32_t)q - lead;
+                    uint32_t h = (w4[q >> 2] >> ((q & 3) * 8)) & 255u;
+                    if ((int)h == topclose) {   // the innermost open node closes (checked before "is it an opener", :807-808)
+                        nodes[stack[sp - 1] & 0xffffffu].e = i + 1; sp--;
+                        topclose = sp ? (int)(stack[sp - 1] >> 24) : -1;
+                        continue;
+                    }
+                    int cl = usual_close(h);
+                    if (cl >= 0) { TNode t; t.s = i; t.e = 0; nodes[nn] = t; stack[sp++] = nn | ((uint32_t)cl << 24); nn++; topclose = cl; }
+                }
+            }
         }
-        int cl = usual_close(h);
-        if (cl >= 0) { TNode t; t.s = i; t.e = 0; nodes[nn] = t; stack[sp++] = nn | ((uint32_t)cl << 24); nn++; topclose = cl; }
     }
     uint32_t k = 0;   // drop the openers that never closed
     for (uint32_t j = 0; j < nn; j++) { TNode t = nodes[j]; if (t.e) { nodes[k] = t; k++; } }
