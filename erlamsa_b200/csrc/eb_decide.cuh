@@ -338,7 +338,14 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             ip = g.rand(INITIAL_IP);
             force_stream(c);
             if (ws->status != CASE_OK) return;
-            if (active_count(ws) == 0) { ws->status = CASE_DIED; return; }
+            if (active_count(ws) == 0) {
+                // an empty block list (an empty file without a finish/1 tail): mutate_once/4 hands [] to the continuation (:274-277).
+                // od writes nothing; nd flips its coin and may come back here; bu would call the mutator on [] and then on the
+                // binary it returns, which has no clause: the worker dies
+                if (cont == CONT_OD) return;
+                if (cont == CONT_ND) { if (g.rand_occurs_fixed(4, 5)) { pat = P_ND; continue; } return; }
+                ws->status = CASE_DIED; return;
+            }
             split_big(c);
         } else if (!FULL) { ws->status = CASE_UNSUPPORTED; return;
         } else if (pat == P_SK) {

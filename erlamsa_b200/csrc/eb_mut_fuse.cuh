@@ -93,6 +93,7 @@ EB_DEV uint32_t fuse_classify(FuseSide& sd, const uint32_t* src, uint32_t k, uin
 
 // ---- one small node per lane (see fuse_device, path 1)
 constexpr uint32_t FUSE_K = 24;
+constexpr uint32_t FUSE_NONE = 0xffffffffu;
 struct SmallSide {
     uint32_t pos[FUSE_K];      // suffix positions in list order
     uint8_t ch[FUSE_K];        // first byte of each live suffix
@@ -160,12 +161,42 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
     int cur = 0; uint32_t ncur = 1;
     { FNode r0; r0.fo = 0; r0.fc = na; r0.to = 0; r0.tc = nb; ND[0][0] = r0; }
     int64_t fuel = 100000;
+    bool compact = false;
     for (;;) {
         bool stop = fuel < 0;
         if (!stop) stop = g.rand(8) == 0;
         uint32_t nnext = 0;
+        if (!stop && compact) {
+            // ---- every node of this level holds at most one suffix per side (and so will all their descendants): the level is
+            // two flat arrays, PA[k] / PB[k] = the node's source / target position (NONE = no suffix), kept in the F / T ping-pong
+            // buffers; a step reads 32 nodes with two coalesced loads and two byte gathers, nothing depends on the previous step
+            // but the output offset. Same rules as the general path written out for one-element lists.
+            const int nx = cur ^ 1;
+            const uint32_t* PA = F[cur]; const uint32_t* PB = T[cur]; uint32_t* QA = F[nx]; uint32_t* QB = T[nx];
+            const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
+            for (uint32_t e = ncur; e > 0;) {
+                uint32_t take = e < 32 ? e : 32;
+                bool act = (uint32_t)l < take;
+                uint32_t pa = FUSE_NONE, pb = FUSE_NONE;
+                if (act) { pa = PA[e - 1 - (uint32_t)l]; pb = PB[e - 1 - (uint32_t)l]; }
+                bool ha = pa != FUSE_NONE && pa < na, hb = pb != FUSE_NONE && pb < nb;
+                uint32_t cha = ha ? a[pa] : 0x100u, chb = hb ? b[pb] : 0x200u;
+                bool a_drop = ha && pa + 1 == na, b_drop = hb && pb + 1 == nb;
+                bool child = false; uint32_t ca = FUSE_NONE, cb = FUSE_NONE;
+                if (a_drop) { child = true; ca = na; cb = nb; }                                   // {_Char, []} -> [[[]], []] (:91-93)
+                else if (ha && cha == chb) { child = true; ca = pa + 1; cb = b_drop ? FUSE_NONE : pb + 1; }
+                uint32_t cm = __ballot_sync(0xffffffffu, child);
+                if (child) { uint32_t at = nnext + (uint32_t)__popc(cm & ltm); QA[at] = ca; QB[at] = cb; }
+                nnext += (uint32_t)__popc(cm);
+                e -= take;
+            }
+            __syncwarp();
+            if (nnext == 0) stop = true;
+            else { fuel -= (int64_t)nnext; cur = nx; ncur = nnext; continue; }
+        }
         if (!stop) {
             const int nx = cur ^ 1; uint32_t fo = 0, to = 0;
+            uint32_t maxsz = 0;                                              // largest suffix list among the children of this level
             // nodes are stored in emission order; the reference's list is that order reversed
             uint32_t e = ncur;
             const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
@@ -202,6 +233,7 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
                     }
                     uint32_t ftot = __shfl_sync(0xffffffffu, fpre, 31), ttot = __shfl_sync(0xffffffffu, tpre, 31), ctot = __shfl_sync(0xffffffffu, cpre, 31);
                     if ((uint64_t)fo + ftot > fcap || (uint64_t)to + ttot > tcap || (uint64_t)nnext + ctot > ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
+                    uint32_t lane_max = 0;
                     if (act) {
                         uint32_t f0 = fo + fpre - fadd, t0 = to + tpre - tadd, c0 = nnext + cpre - cadd;
                         small_side_write(A, F[nx] + f0);
@@ -218,8 +250,10 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
                             if (bi < 0) continue;                                   // notfound
                             ch_n.fo = f0 + A.cstart[ci]; ch_n.fc = A.csize[ci]; ch_n.to = t0 + B.cstart[bi]; ch_n.tc = B.csize[bi];
                             ND[nx][c0++] = ch_n;
+                            uint32_t mx = ch_n.fc > ch_n.tc ? ch_n.fc : ch_n.tc; if (mx > lane_max) lane_max = mx;
                         }
                     }
+                    maxsz = max(maxsz, __reduce_max_sync(0xffffffffu, lane_max));
                     fo += ftot; to += ttot; nnext += ctot; e -= runlen;
                     __syncwarp();
                     continue;
@@ -246,15 +280,38 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
                         ch_n.fo = sa.start[ch]; ch_n.fc = sizeA[ch]; ch_n.to = sb.start[ch]; ch_n.tc = sizeB[ch];
                         if (l == 0) ND[nx][nnext] = ch_n;
                         nnext++;
+                        maxsz = max(maxsz, max(ch_n.fc, ch_n.tc));
                     }
                 }
                 fo += fa; to += tb;
                 __syncwarp();
             }
             if (nnext == 0) stop = true;
-            else { fuel -= (int64_t)nnext; cur = nx; ncur = nnext; continue; }
+            else {
+                fuel -= (int64_t)nnext; cur = nx; ncur = nnext;
+                if (maxsz <= 1) {      // from here on every node is at most 1 x 1: flatten the level into position arrays
+                    const int l2 = lane_id(); const int ot = cur ^ 1;
+                    for (uint32_t k = (uint32_t)l2; k < ncur; k += 32) {
+                        FNode nd = ND[cur][k];
+                        F[ot][k] = nd.fc ? F[cur][nd.fo] : FUSE_NONE;
+                        T[ot][k] = nd.tc ? T[cur][nd.to] : FUSE_NONE;
+                    }
+                    __syncwarp();
+                    cur = ot; compact = true;
+                }
+                continue;
+            }
         }
         // any_position_pair(Nodes)
+        if (compact) {
+            uint32_t r = (uint32_t)g.rand_elem_idx(ncur);
+            uint32_t pa = F[cur][ncur - 1 - r], pb = T[cur][ncur - 1 - r];
+            int64_t fi = g.rand_elem_idx(pa != FUSE_NONE ? 1 : 0);
+            from = fi < 0 ? na : pa;
+            int64_t ti = g.rand_elem_idx(pb != FUSE_NONE ? 1 : 0);
+            to = ti < 0 ? nb : pb;
+            return true;
+        }
         uint32_t r = (uint32_t)g.rand_elem_idx(ncur);
         FNode nd = ND[cur][ncur - 1 - r];
         int64_t fi = g.rand_elem_idx(nd.fc);

@@ -393,8 +393,7 @@ enum { JA_NUM = 0, JA_STR, JA_TRUE, JA_FALSE, JA_NULL, JA_JUNK, JA_OARR, JA_CARR
 struct JAtom { uint32_t kind, a, b, match; };
 enum { JV_NUMBER = 0, JV_STRING, JV_TRUE, JV_FALSE, JV_NULL, JV_JUNK, JV_CONTAINER };
 enum { JC_ARRAY = 0, JC_ELEMENTS, JC_OBJECT, JC_MEMBERS, JC_PAIR, JC_PAIR_DELIM, JC_VALUE, JC_ARRAY_END, JC_OBJECT_END, JC_PAIR_START, JC_PAIR_END };
-EB_DEV JsScan js_tokenize(const uint8_t* SP, uint32_t n, uint8_t* stk, uint32_t cap, JAtom* atoms, uint32_t acap) {
-    ByteWin bw; bw.init(SP, n); WinRef S{&bw};          // bytes out of a register window (eb_warp.cuh), not one memory access each
+EB_DEV JsScan js_tokenize(const uint8_t* S, uint32_t n, uint8_t* stk, uint32_t cap, JAtom* atoms, uint32_t acap) {
     JsScan o; o.status = 0; o.ntop = 0; o.kind = 0; o.a = o.b = 0; o.natoms = 0; o.irregular = 0;
     uint32_t sp = 0, i = 0;
     auto ATOM = [&](uint32_t kind, uint32_t a, uint32_t b) {
@@ -462,7 +461,7 @@ EB_DEV JsScan js_tokenize(const uint8_t* SP, uint32_t n, uint8_t* stk, uint32_t 
         if (i + 5 <= n && S[i] == 'f' && S[i + 1] == 'a' && S[i + 2] == 'l' && S[i + 3] == 's' && S[i + 4] == 'e') { ATOM(JA_FALSE, i, i + 5); if (!push_value(JV_FALSE, i, i + 5)) { o.status = 1; return o; } i += 5; continue; }
         if (i + 4 <= n && S[i] == 'n' && S[i + 1] == 'u' && S[i + 2] == 'l' && S[i + 3] == 'l') { ATOM(JA_NULL, i, i + 4); if (!push_value(JV_NULL, i, i + 4)) { o.status = 1; return o; } i += 4; continue; }
         if (ch == '"') {
-            uint32_t q = find_byte(SP, i + 1, n, '"');
+            uint32_t q = find_byte(S, i + 1, n, '"');
             if (q >= n) { ATOM(JA_JUNK, i + 1, n); if (!push_value(JV_JUNK, i + 1, n)) { o.status = 1; return o; } i = n; continue; }
             ATOM(JA_STR, i + 1, q);
             if (!push_value(JV_STRING, i + 1, q)) { o.status = 1; return o; }

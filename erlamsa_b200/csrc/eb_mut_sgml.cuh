@@ -26,7 +26,6 @@ constexpr uint32_t SF_XMLNS = 4u;           // xmlns_modify/2 fired for this tag
 
 struct SgDoc {
     const uint8_t* S; uint32_t n;
-    ByteWin W;
     STok* tok; uint32_t ntok, tok_cap;
     SPar* par; uint32_t npar, par_cap;
     uint32_t N, NT;
@@ -39,7 +38,7 @@ __device__ __forceinline__ uint32_t sg_lower(uint32_t c) { return ((c >= 'A' && 
 // tz/2 (:82-148) from state {tag,""} at S[i..]: 0 = token written to *t (params appended to d.par), 1 = throw(incorrect_sgml),
 // 2 = function_clause (unterminated comment), 3 = device table full
 EB_DEV int sg_scan_tag(SgDoc& d, uint32_t i, STok* t, uint32_t* next) {
-    const uint8_t* SP = d.S; const uint32_t n = d.n; WinRef S{&d.W};
+    const uint8_t* S = d.S; const uint32_t n = d.n;
     enum { TAGN, BANG, COMMENT, QUE, ETAG, ENDTAG, ENDTAG_GT, ATTR, EATT, VAL, SQVAL, DQVAL, UQVAL };
     int st = TAGN;
     uint32_t tag0 = i, tag1 = i, a0 = 0, a1 = 0, v0 = 0;
@@ -48,7 +47,7 @@ EB_DEV int sg_scan_tag(SgDoc& d, uint32_t i, STok* t, uint32_t* next) {
     auto st2 = [&](uint32_t q, uint32_t c0, uint32_t c1) { return q + 2 <= n && S[q] == c0 && S[q + 1] == c1; };
     auto add_par = [&](uint32_t vs, uint32_t ve, uint32_t quote) -> bool {
         if (par_base + np >= d.par_cap) return false;
-        SPar pr; pr.np = SP + a0; pr.nl = a1 - a0; pr.vp = SP + vs; pr.vl = ve - vs; pr.q = quote; pr.choice = 0;
+        SPar pr; pr.np = S + a0; pr.nl = a1 - a0; pr.vp = S + vs; pr.vl = ve - vs; pr.q = quote; pr.choice = 0;
         d.par[par_base + np] = pr; np++; return true;
     };
     auto done = [&](uint32_t kind, const uint8_t* ptr, uint32_t len, uint32_t nx) {
@@ -64,23 +63,23 @@ EB_DEV int sg_scan_tag(SgDoc& d, uint32_t i, STok* t, uint32_t* next) {
                 if (S[i] == '?') { st = QUE; i = ws(i + 1); tag0 = i; continue; }
                 if (S[i] == '/') { st = ENDTAG; i = ws(i + 1); tag0 = tag1 = i; continue; }
             }
-            if (st2(i, '/', '>')) return done(ST_SC, SP + tag0, tag1 - tag0, i + 2);
+            if (st2(i, '/', '>')) return done(ST_SC, S + tag0, tag1 - tag0, i + 2);
             if (i < n && sg_ev(S[i])) { st = ATTR; a0 = a1 = 0; i = ws(i); continue; }
             if (i < n) { i++; tag1 = i; continue; }
             return 1;
-        case BANG: { uint32_t q = find_byte(SP, i, n, '>'); if (q >= n) return 1; return done(ST_BANG, SP + tag0, q - tag0, q + 1); }
-        case COMMENT: { uint32_t q = i; for (;;) { q = find_byte(SP, q, n, '-'); if (q >= n) return 2; if (q + 3 <= n && S[q + 1] == '-' && S[q + 2] == '>') return done(ST_COMMENT, SP + tag0, q - tag0, q + 3); q++; } }
-        case QUE: { uint32_t q = i; for (;;) { q = find_byte(SP, q, n, '?'); if (q >= n) return 1; if (q + 2 <= n && S[q + 1] == '>') return done(ST_QUE, SP + tag0, q - tag0, q + 2); q++; } }
+        case BANG: { uint32_t q = find_byte(S, i, n, '>'); if (q >= n) return 1; return done(ST_BANG, S + tag0, q - tag0, q + 1); }
+        case COMMENT: { uint32_t q = i; for (;;) { q = find_byte(S, q, n, '-'); if (q >= n) return 2; if (q + 3 <= n && S[q + 1] == '-' && S[q + 2] == '>') return done(ST_COMMENT, S + tag0, q - tag0, q + 3); q++; } }
+        case QUE: { uint32_t q = i; for (;;) { q = find_byte(S, q, n, '?'); if (q >= n) return 1; if (q + 2 <= n && S[q + 1] == '>') return done(ST_QUE, S + tag0, q - tag0, q + 2); q++; } }
         case ETAG:
-            if (st2(i, '/', '>')) return done(ST_SC, SP + tag0, tag1 - tag0, i + 2);
-            if (i < n && S[i] == '>') return done(ST_OPEN, SP + tag0, tag1 - tag0, i + 1);
+            if (st2(i, '/', '>')) return done(ST_SC, S + tag0, tag1 - tag0, i + 2);
+            if (i < n && S[i] == '>') return done(ST_OPEN, S + tag0, tag1 - tag0, i + 1);
             return 1;
         case ENDTAG:
             if (i < n && sg_ev(S[i])) { st = ENDTAG_GT; i = ws(i); continue; }
             if (i < n) { i++; tag1 = i; continue; }
             return 1;
         case ENDTAG_GT:
-            if (i < n && S[i] == '>') return done(ST_CLOSE, SP + tag0, tag1 - tag0, i + 1);
+            if (i < n && S[i] == '>') return done(ST_CLOSE, S + tag0, tag1 - tag0, i + 1);
             return 1;
         case ATTR:
             if (a1 == a0 && ((i < n && sg_ev(S[i])) || st2(i, '/', '>'))) { st = ETAG; continue; }
@@ -95,8 +94,8 @@ EB_DEV int sg_scan_tag(SgDoc& d, uint32_t i, STok* t, uint32_t* next) {
             if (i < n && S[i] == '\'') { st = SQVAL; i++; v0 = i; continue; }
             if (i < n && S[i] == '"') { st = DQVAL; i++; v0 = i; continue; }
             st = UQVAL; v0 = i; continue;
-        case SQVAL: { uint32_t q = find_byte(SP, i, n, '\''); if (q >= n) return 1; if (!add_par(v0, q, '\'')) return 3; a0 = a1 = 0; st = ATTR; i = ws(q + 1); continue; }
-        case DQVAL: { uint32_t q = find_byte(SP, i, n, '"'); if (q >= n) return 1; if (!add_par(v0, q, '"')) return 3; a0 = a1 = 0; st = ATTR; i = ws(q + 1); continue; }
+        case SQVAL: { uint32_t q = find_byte(S, i, n, '\''); if (q >= n) return 1; if (!add_par(v0, q, '\'')) return 3; a0 = a1 = 0; st = ATTR; i = ws(q + 1); continue; }
+        case DQVAL: { uint32_t q = find_byte(S, i, n, '"'); if (q >= n) return 1; if (!add_par(v0, q, '"')) return 3; a0 = a1 = 0; st = ATTR; i = ws(q + 1); continue; }
         default:   // UQVAL
             if ((i < n && sg_ev(S[i])) || st2(i, '/', '>')) { if (!add_par(v0, i, 0)) return 3; a0 = a1 = 0; st = ATTR; i = ws(i); continue; }
             if (i < n) { i++; continue; }
@@ -107,8 +106,8 @@ EB_DEV int sg_scan_tag(SgDoc& d, uint32_t i, STok* t, uint32_t* next) {
 
 // tokenize/1 (:65-96). 0 ok, 1 throw, 2 error, 3 tables full / text with more skipped gaps than the device keeps
 EB_DEV int sg_tokenize(CaseCtx& c, SgDoc& d) {
-    const uint8_t* SP = d.S; const uint32_t n = d.n; WinRef S{&d.W};
-    uint32_t lt = find_byte(SP, 0, n, '<');
+    const uint8_t* S = d.S; const uint32_t n = d.n;
+    uint32_t lt = find_byte(S, 0, n, '<');
     if (lt >= n) return 1;
     auto ws = [&](uint32_t q) { while (q < n && sg_ws(S[q])) q++; return q; };
     STok cur; uint32_t p = 0;
@@ -119,7 +118,7 @@ EB_DEV int sg_tokenize(CaseCtx& c, SgDoc& d) {
         uint32_t piece0[8], piece1[8]; int np = 0; uint32_t pstart = p;
         STok t2; uint32_t nx = 0; bool eof = false;
         for (;;) {
-            uint32_t q = find_byte(SP, p, n, '<');
+            uint32_t q = find_byte(S, p, n, '<');
             if (q >= n) { eof = true; break; }
             uint32_t e = ws(q + 1);
             const uint32_t par_mark = d.npar;
@@ -137,14 +136,14 @@ EB_DEV int sg_tokenize(CaseCtx& c, SgDoc& d) {
         if (d.ntok + 2 >= d.tok_cap) return 3;
         d.tok[d.ntok++] = cur;
         STok tx; tx.kind = eof ? ST_EOFTEXT : ST_TEXT; tx.par0 = 0; tx.npar = 0; tx.match = SG_NOMATCH; tx.flags = 0;
-        if (np == 0) { tx.ptr = SP + pstart; tx.len = tend - pstart; }
+        if (np == 0) { tx.ptr = S + pstart; tx.len = tend - pstart; }
         else {
             uint32_t tot = tend - pstart; for (int j = 0; j < np; j++) tot += piece1[j] - piece0[j];
             uint8_t* buf = scratch_alloc(c, tot);
             if (!buf) return 3;
             uint32_t o = 0;
-            for (int j = 0; j < np; j++) { warp_copy(buf + o, SP + piece0[j], piece1[j] - piece0[j]); o += piece1[j] - piece0[j]; }
-            warp_copy(buf + o, SP + pstart, tend - pstart);
+            for (int j = 0; j < np; j++) { warp_copy(buf + o, S + piece0[j], piece1[j] - piece0[j]); o += piece1[j] - piece0[j]; }
+            warp_copy(buf + o, S + pstart, tend - pstart);
             __syncwarp();
             tx.ptr = buf; tx.len = tot;
         }
@@ -322,7 +321,7 @@ EB_DEV void mut_sgm(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     r.rechunk = 0; r.consumed_next = 0; r.kind = RES_SAME; r.delta = -1;
     if (mem_binarish(p, n)) return;                                      // parse/2 :185-186
-    SgDoc d; d.S = p; d.n = n; d.ntok = 0; d.npar = 0; d.N = d.NT = 0; d.W.init(p, n);
+    SgDoc d; d.S = p; d.n = n; d.ntok = 0; d.npar = 0; d.N = d.NT = 0;
     // table sizes for ordinary markup (a tag every four bytes or denser is not)
     d.tok_cap = n / 4 + 64; d.par_cap = n / 4 + 16;                      // beyond that ("<><><>...") the case is flagged
     d.tok = (STok*)temp_alloc(c, (uint64_t)d.tok_cap * sizeof(STok));

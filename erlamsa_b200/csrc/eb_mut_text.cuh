@@ -21,41 +21,34 @@ EB_DEV bool texty(uint32_t b) {   // :46-52
 }
 
 // lex/1 :75-143. tab == nullptr: count only. Returns the number of chunks; *stringy = any non-byte chunk.
-EB_DEV uint32_t lex_device(const uint8_t* dp, uint32_t n, ChunkEnt* tab, bool* stringy) {
+EB_DEV uint32_t lex_device(const uint8_t* d, uint32_t n, ChunkEnt* tab, bool* stringy) {
     uint32_t cnt = 0; bool str = false;
     uint32_t p = 0; bool have_raw = false; uint32_t raw_start = 0;
-    ByteWin d; d.init(dp, n);          // bytes come out of a register window, not one memory access each
     auto emit = [&](uint32_t type, uint32_t start) {
         if (tab && lane_id() == 0) { tab[cnt].start = start; tab[cnt].type = type; }
         cnt++; if (type != CH_BYTE) str = true;
     };
-    // texty_enough/2 :54-64 asks for six texty bytes ahead at every position outside a text chunk; `bad` remembers the
-    // first non-texty byte found ahead, so a run of raw bytes costs one look per byte instead of up to six
-    uint32_t bad = 0; bool bad_valid = false;
     while (p < n) {
         // texty_enough/2 :54-64 (MIN_TEXTY = 6; a short all-texty tail also counts)
         bool te = true;
-        if (bad_valid && bad >= p && bad < p + 6) te = false;
-        else {
-            for (uint32_t k = 0; k < 6; k++) { if (p + k >= n) break; if (!texty(d.get(p + k))) { te = false; bad = p + k; bad_valid = true; break; } }
-        }
+        for (uint32_t k = 0; k < 6; k++) { if (p + k >= n) break; if (!texty(d[p + k])) { te = false; break; } }
         if (!te) { if (!have_raw) { have_raw = true; raw_start = p; } p++; continue; }
         if (have_raw) { emit(CH_BYTE, raw_start); have_raw = false; }
         // step_text :95-107
         uint32_t seen_start = p;
         for (;;) {
             if (p >= n) { emit(CH_TEXT, seen_start); break; }
-            uint32_t h = d.get(p);
+            uint32_t h = d[p];
             if (h == 34 || h == 39) {
                 // step_delimited :114-143
                 uint32_t q = p; p++;
                 bool closed = false;
                 for (;;) {
                     if (p >= n) break;
-                    uint32_t c = d.get(p);
+                    uint32_t c = d[p];
                     if (c == h) { closed = true; break; }
                     if (c == 92 && p + 1 >= n) { p++; continue; }
-                    if (c == 92) { if (texty(d.get(p + 1))) p += 2; else p++; continue; }
+                    if (c == 92) { if (texty(d[p + 1])) p += 2; else p++; continue; }
                     if (texty(c)) { p++; continue; }
                     break;
                 }

@@ -56,7 +56,9 @@ struct Rng {
     uint64_t key, ctr_hi;    // Philox: key = option seed hash, ctr_hi = global case id
     uint32_t slot, local;    // Philox: current slot and the next index inside it
     // Philox only: start drawing from slot s (no-op for AS183, whose stream is one sequence by definition)
-    EB_HD void set_slot(uint32_t s) { if (mode != 0) { slot = s; local = 0; } }
+    // (re-entering the slot that is already current continues its sequence: a loop that comes back to the same slot -- `bu` over
+    //  an emptied block list -- must not see the same draw again and again)
+    EB_HD void set_slot(uint32_t s) { if (mode != 0 && slot != s) { slot = s; local = 0; } }
     // Philox only: draw number `idx` of the current slot, without advancing anything (lane-parallel loops)
     EB_HD double uniform_philox_at(uint32_t idx) const {
         uint32_t o[4];

@@ -159,41 +159,6 @@ __device__ __noinline__ void warp_fill(uint8_t* dst, uint8_t b, uint64_t n) {
     for (uint64_t i = lane_id(); i < n; i += 32) dst[i] = b;
 }
 
-// ------------------------------------------------------------------ sequential byte access for warp-uniform automata
-// The string lexer, the bracket matcher and the SGML / JSON tokenizers are sequential automata executed warp-uniformly.
-// Read through plain `p[i]` they paid a dependent memory access per byte (ab / js / sgm / ts1 / tr: 80-110 ms per
-// 256 KiB call in round 2's first profile, gpurun_out/tc_c4.log). A ByteWin keeps a 512-byte window of the block in
-// registers -- one coalesced 16-byte load per lane per window -- and hands out bytes by shuffle: ~10 instructions and
-// no memory access per byte. Indices must be warp-uniform (they are: the automaton state is). Random access outside the
-// window just moves it.
-struct ByteWin {
-    const uint8_t* d; uint32_t n;
-    uint32_t w0;          // window start (multiple of 512 relative to the 16-byte aligned base), 0xffffffff = none
-    uint32_t lead;        // d - aligned base
-    uint4 r;
-    __device__ __forceinline__ void init(const uint8_t* p, uint32_t len) { d = p; n = len; lead = (uint32_t)((uintptr_t)p & 15u); w0 = 0xffffffffu; r = make_uint4(0, 0, 0, 0); }
-    __device__ __forceinline__ void load(uint32_t a) {      // a = aligned coordinate (lead + index)
-        w0 = a & ~511u;
-        uint32_t wofs = w0 + (uint32_t)lane_id() * 16u;
-        const uint8_t* base = d - lead;
-        // words wholly outside [lead, lead + n) are not touched
-        if (wofs < lead + n && wofs + 16 > lead) r = *reinterpret_cast<const uint4*>(base + wofs); else r = make_uint4(0, 0, 0, 0);
-    }
-    // byte i of the block (i < n, warp-uniform)
-    __device__ __forceinline__ uint32_t get(uint32_t i) {
-        uint32_t a = lead + i;
-        if ((a & ~511u) != w0) load(a);
-        uint32_t o = a & 511u;
-        uint32_t sel = (o >> 2) & 3u;
-        uint32_t word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
-        word = __shfl_sync(0xffffffffu, word, (int)(o >> 4));
-        return (word >> ((o & 3u) * 8u)) & 255u;
-    }
-};
-
-// `S[i]` on a WinRef reads byte i out of a ByteWin instead of memory (drop-in for `const uint8_t* S` in the tokenizers)
-struct WinRef { ByteWin* w; __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return w->get(i); } };
-
 // ------------------------------------------------------------------ byte scans
 // A scan walks [p, p+n) in 512-byte warp chunks laid out on 16-byte ALIGNED coordinates
 // (chunk 0 starts at p rounded down to 16). Each lane owns one aligned 16-byte word and reduces
