@@ -246,7 +246,7 @@ void eb200_shutdown(eb200_ctx* ctx) {
 // cannot help keep the warps on the general program. Measured on C3 (profiles/variants_r2.txt): fronts 3 / deciders 2
 // 2.55 ms, 2/2 2.65, 4/2 2.58, 1/2 3.10; without fronts 5.3 ms (32 deciders, inline copies) .. 9.6 ms (8 deciders).
 struct Roles { int fronts, deciders; };
-static Roles choose_roles(const eb200_ctx* ctx, const BatchParams& bp, bool fused) {
+static Roles choose_roles(const eb200_ctx* ctx, const BatchParams& bp, bool fused, uint64_t mean_len) {
     Roles r;
     double pod = 0, psum = 0, mfast = 0, msum = 0;
     for (int i = 0; i < bp.n_pats; i++) { psum += bp.pat_pri[i]; if (bp.pat_id[i] == P_OD) pod += bp.pat_pri[i]; }
@@ -256,6 +256,8 @@ static Roles choose_roles(const eb200_ctx* ctx, const BatchParams& bp, bool fuse
     if (share >= 0.5) { r.fronts = 3; r.deciders = 2; }
     else if (share >= 0.02) { r.fronts = 1; r.deciders = warps >= 32 ? 20 : warps / 2; }
     else { r.fronts = 0; r.deciders = warps >= 32 ? 24 : warps / 2; }
+    // blocks below the job thresholds (16 KiB) are copied and scanned inline by their decider: workers would only sit idle
+    if (share < 0.5 && mean_len < JOB_MIN_COPY) { r.deciders = warps - r.fronts - (r.fronts ? 2 : 0); }
     if (ctx->fronts >= 0) r.fronts = ctx->fronts;
     if (ctx->deciders > 0) r.deciders = ctx->deciders;
     if (r.deciders > warps) r.deciders = warps;
@@ -265,7 +267,7 @@ static Roles choose_roles(const eb200_ctx* ctx, const BatchParams& bp, bool fuse
 // arenas + launch geometry shared by both modes
 struct LaunchPlan { Arenas ar; int grid; Roles roles; };
 static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_bytes, uint64_t n_launch, bool fused, LaunchPlan& lp) {
-    lp.roles = choose_roles(ctx, bp, fused);
+    lp.roles = choose_roles(ctx, bp, fused, bp.n_blobs ? data_bytes / bp.n_blobs : 0);
     const int deciders = lp.roles.deciders;
     unsigned long long* cnt = (unsigned long long*)ctx->counters.p;
     Arenas& ar = lp.ar;
