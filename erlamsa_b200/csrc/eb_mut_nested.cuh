@@ -2,8 +2,8 @@
 //   uri  (reference src/erlamsa_mutations.erl:734-784)  SSRF / path-traversal rewrite of every text chunk holding "://"
 //   b64  (reference :657-690)                            base64-decodable text chunks get one full scheduler round
 //   sgm  (reference src/erlamsa_sgml.erl)                eb_mut_sgml.cuh (all twelve mutations; inner text only at top level)
-//   js   (reference src/erlamsa_json.erl:722-731)        tokenizer exact; a lone scalar token is mutated on the device,
-//                                                        a document with containers flags the case
+//   js   (reference src/erlamsa_json.erl:722-731)        eb_mut_json.cuh (atom-stream formulation: scalars, arrays and objects on the
+//                                                        device; only a key followed by another value in key position flags the case)
 // A flagged case (CASE_UNSUPPORTED) is reported to the caller and its output is the unchanged input: nothing is
 // computed on the host on its behalf.
 //
@@ -328,7 +328,7 @@ EB_DEV uint32_t b64_encode_dev(const uint8_t* in, uint32_t m, uint8_t* out) {   
 }
 
 // At LVL == MAX_NEST the attempt cannot open another round: it is exact as long as no chunk decodes (the usual
-// outcome on decoded bytes) and flags the case when a second level of nesting would be needed.
+// outcome on decoded bytes) and flags the case when one more level of nesting (a third) would be needed.
 template <int LVL>
 EB_DEV void mut_b64(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     WarpState* ws = c.ws; Rng& g = c.rng;

@@ -1,7 +1,7 @@
 """N > 1 host logic on CPU (gloo, world_size 2): the case loop is cut into per-rank windows (erlamsa_b200.sharding),
 each rank runs only its window, and the gathered result equals the single-process run -- the property that makes the
 multi-GPU path collective-free. The per-rank compute here is the oracle (no GPU in this container); on the GPU box the
-same windows drive the CUDA engine (tests/test_multigpu.py, bench.py)."""
+same windows drive the CUDA engine (bench.py --gpus N; tests/test_parity_gpu.py checks window independence on one GPU)."""
 import hashlib
 import os
 import socket
