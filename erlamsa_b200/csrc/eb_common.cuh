@@ -103,7 +103,7 @@ struct Arenas {
     uint8_t* temp; uint64_t temp_per_warp;
     unsigned long long* flagged;   // [3]: cases that ended unsupported / died / over a cap
     uint8_t* case_status;          // [n_cases]: status | reason << 4 (the host re-runs arena-overflow cases from it)
-    unsigned long long* mut_ns;    // [2 * M_COUNT] or null: nanoseconds and calls per mutator (same profiling aid)
+    unsigned long long* mut_ns;    // [2 * (M_COUNT + 8)] or null: nanoseconds and calls per mutator, then per fuse phase (same profiling aid)
     uint32_t* case_usec;           // [n_cases] or null: wall time of the general per-case program (EB200_CASE_TIMES=1, profiling aid)
 };
 

@@ -279,7 +279,7 @@ static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_byte
     ar.flagged = cnt + CNT_FLAGGED;
     ar.case_status = (uint8_t*)ctx->case_status.p;
     ar.case_usec = nullptr; ar.mut_ns = nullptr;
-    if (ctx->want_case_times) { CK(ctx->case_usec.ensure(bp.n_cases * 4 + 128 + 2 * M_COUNT * 8)); ar.case_usec = (uint32_t*)ctx->case_usec.p; ar.mut_ns = (unsigned long long*)((uint8_t*)ctx->case_usec.p + ((bp.n_cases * 4 + 63) & ~63ull)); ctx->case_times_n = bp.n_cases; if (!fused || n_launch == bp.n_cases) CK(cudaMemset(ar.case_usec, 0, bp.n_cases * 4 + 128 + 2 * M_COUNT * 8)); }
+    if (ctx->want_case_times) { CK(ctx->case_usec.ensure(bp.n_cases * 4 + 128 + 2 * (M_COUNT + 8) * 8)); ar.case_usec = (uint32_t*)ctx->case_usec.p; ar.mut_ns = (unsigned long long*)((uint8_t*)ctx->case_usec.p + ((bp.n_cases * 4 + 63) & ~63ull)); ctx->case_times_n = bp.n_cases; if (!fused || n_launch == bp.n_cases) CK(cudaMemset(ar.case_usec, 0, bp.n_cases * 4 + 128 + 2 * (M_COUNT + 8) * 8)); }
     uint64_t want_ctas = (n_launch + deciders - 1) / deciders;
     lp.grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms);
     if (lp.grid < 1) lp.grid = 1;
@@ -780,12 +780,13 @@ uint64_t eb200_debug_case_times(eb200_ctx* ctx, uint32_t* out, uint64_t n) {
     if (cudaMemcpy(out, ctx->case_usec.p, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
 }
-// ... and per mutator: out[2 * i] = nanoseconds inside mutator i (table order), out[2 * i + 1] = calls; 2 * 41 entries
+// ... and per mutator: out[2 * i] = nanoseconds inside mutator i (table order), out[2 * i + 1] = calls; 41 pairs, then 8 pairs for the
+// phases of the fuse search (table-classified / register-classified / lane-per-node / one-suffix / flat levels; eb_mut_fuse.cuh): 98 entries
 int eb200_debug_mutator_times(eb200_ctx* ctx, uint64_t* out) {
     if (!ctx || !ctx->want_case_times || !ctx->case_usec.p) return 0;
     cudaSetDevice(ctx->device);
     const uint8_t* src = (const uint8_t*)ctx->case_usec.p + ((ctx->case_times_n * 4 + 63) & ~63ull);
-    return cudaMemcpy(out, src, 2 * M_COUNT * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? M_COUNT : 0;
+    return cudaMemcpy(out, src, 2 * (M_COUNT + 8) * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? M_COUNT : 0;
 }
 
 const char* eb200_mutator_code(int i) { return (i >= 0 && i < EB200_N_MUTATORS) ? kMutCodes[i] : nullptr; }

@@ -91,57 +91,264 @@ EB_DEV uint32_t fuse_classify(FuseSide& sd, const uint32_t* src, uint32_t k, uin
     return run - base;
 }
 
-// ---- one small node per lane (see fuse_device, path 1)
-constexpr uint32_t FUSE_K = 24;
 constexpr uint32_t FUSE_NONE = 0xffffffffu;
-struct SmallSide {
-    uint32_t pos[FUSE_K];      // suffix positions in list order
-    uint8_t ch[FUSE_K];        // first byte of each live suffix
-    uint8_t live[FUSE_K];      // 0: the [] suffix (contributes nothing), 1: placed, 2: the dropped special
-    uint32_t n;
-    uint8_t cbyte[FUSE_K];     // classes in ascending byte order (a class whose only member was dropped has size 0)
-    uint8_t csize[FUSE_K];
-    uint8_t cstart[FUSE_K];    // start of the class inside this node's output
-    uint32_t ncls, nplaced;
-};
-__device__ __forceinline__ void small_side_load(SmallSide& s, const uint32_t* src, uint32_t k, const uint8_t* data, uint32_t len) {
-    s.n = k;
-    int special = -1;
-    for (uint32_t i = 0; i < k; i++) {
-        uint32_t p = src[i]; s.pos[i] = p;
-        bool lv = p < len;
-        s.live[i] = lv ? 1 : 0; s.ch[i] = lv ? data[p] : 0;
-        if (lv && p + 1 == len && special < 0) special = (int)i;
-    }
+
+// The same classification with the hot table in SHARED memory: for lists shorter than 65 535 suffixes the per-class counter is a
+// 16-bit word in the warp's scan scratch (WarpState::sc, idle while a fuse runs), so the read-modify-write that every 32-suffix
+// step of the count and placement passes depends on is a shared-memory access instead of an L2 round trip. Lane l owns the
+// classes 8l .. 8l+7: it turns its eight counters into class starts (one warp scan), publishes start and size to the global
+// tables the children walk reads, and keeps which of its classes exist in `mybits`.
+EB_DEV uint32_t fuse_classify_sm(const uint8_t* s, uint32_t len, const uint32_t* src, uint32_t k, uint32_t* dst, uint32_t base,
+                                 uint16_t* tbl, uint32_t* gstart, uint32_t* gsize, uint32_t& mybits) {
+    const int l = lane_id(); const uint32_t lt = (1u << l) - 1u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tbl[8 * l + i] = 0;
     // the suffix holding only the block's last byte is dropped when it is the FIRST of its class ([[]] -> [], :68-70)
-    if (special >= 0) {
-        bool before = false;
-        for (int i = 0; i < special; i++) before |= s.live[i] && s.ch[i] == s.ch[special];
-        if (!before) s.live[special] = 2;
+    uint32_t sq = 0xffffffffu, sch = 0x100u;
+    for (uint32_t q0 = 0; q0 < k; q0 += 32) {
+        uint32_t q = q0 + l; uint32_t p = q < k ? src[q] : 0xffffffffu;
+        uint32_t hit = __ballot_sync(0xffffffffu, q < k && p + 1 == len);
+        if (hit) { sq = q0 + (uint32_t)__ffs(hit) - 1; sch = s[len - 1]; break; }
+    }
+    bool special_dropped = false;
+    if (sq != 0xffffffffu) {
+        uint32_t before = 0;
+        for (uint32_t q0 = 0; q0 < sq; q0 += 32) {
+            uint32_t q = q0 + l; uint32_t p = q < sq ? src[q] : 0xffffffffu;
+            before |= __ballot_sync(0xffffffffu, q < sq && p < len && s[p] == sch);
+            if (before) break;
+        }
+        special_dropped = before == 0;
+    }
+    __syncwarp();
+    for (uint32_t q0 = 0; q0 < k; q0 += 32) {                          // count
+        uint32_t q = q0 + l; uint32_t p = q < k ? src[q] : 0xffffffffu;
+        bool counted = q < k && p < len && !(special_dropped && q == sq);   // the [] suffix contributes nothing (:68)
+        uint32_t ch = counted ? s[p] : 0u;
+        uint32_t peers = __match_any_sync(0xffffffffu, counted ? ch : 0x100u + (uint32_t)l);
+        if (counted && (peers & lt) == 0) tbl[ch] = (uint16_t)(tbl[ch] + (uint32_t)__popc(peers));
+        __syncwarp();
+    }
+    uint32_t cn[8]; uint32_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { cn[i] = tbl[8 * l + i]; mine += cn[i]; }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += x; }
+    uint32_t rel = incl - mine; mybits = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {                                       // class starts, ascending byte
+        uint32_t ch = 8u * (uint32_t)l + (uint32_t)i;
+        bool exists = cn[i] != 0 || (special_dropped && sch == ch);
+        if (exists) { mybits |= 1u << i; gstart[ch] = base + rel; gsize[ch] = cn[i]; }
+        rel += cn[i];
+        tbl[ch] = (uint16_t)rel;                                        // one past the class's last slot
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    for (uint32_t q0 = 0; q0 < k; q0 += 32) {                          // place: first arrival lands last in its class
+        uint32_t q = q0 + l; uint32_t p = q < k ? src[q] : 0xffffffffu;
+        bool placed = q < k && p < len && !(special_dropped && q == sq);
+        uint32_t ch = placed ? s[p] : 0u;
+        uint32_t peers = __match_any_sync(0xffffffffu, placed ? ch : 0x100u + (uint32_t)l);
+        uint32_t end = placed ? tbl[ch] : 0u;
+        __syncwarp();
+        if (placed) {
+            dst[base + end - 1 - (uint32_t)__popc(peers & lt)] = p + 1;
+            if ((peers & lt) == 0) tbl[ch] = (uint16_t)(end - (uint32_t)__popc(peers));
+        }
+        __syncwarp();
+    }
+    return total;
+}
+
+// profiling aid (EB200_CASE_TIMES=1): nanoseconds per phase of fuse_device, slots after the per-mutator table
+enum { FPH_BIG = 0, FPH_MID, FPH_SMALL, FPH_TINY, FPH_COMPACT, FPH_COUNT };
+struct FuseClock {
+    unsigned long long* tab; unsigned long long t0;
+    __device__ __forceinline__ void start() { if (tab) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0)); }
+    __device__ __forceinline__ void stop(int ph) {
+        if (!tab) return;
+        unsigned long long t1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (lane_id() == 0) { atomicAdd(&tab[2 * ph], t1 - t0); atomicAdd(&tab[2 * ph + 1], 1ull); }
+    }
+};
+
+// ---- one node of at most FUSE_MID suffixes per side, whole warp, first bytes held in registers (see fuse_device, path 2a).
+// Slot r of lane l holds list element r * 32 + l (arrival order). Encoding of a first byte: 0..255 live; 0x1ff the [] suffix
+// (contributes nothing); byte | 0x400 the suffix holding only the block's last byte when it is the FIRST of its class -- the
+// class exists, the element is not placed ([[]] -> [], :68-70). Classes of A are taken in ascending byte order by a min
+// reduction; inside a class the LAST arrival comes first (char_suffixes prepends). No tables, no memory traffic but the
+// two position lists and their first bytes.
+constexpr uint32_t FUSE_MID = 256;
+constexpr int FUSE_MID_SLOTS = 8;
+struct FuseOut { uint32_t* F; uint32_t* T; FNode* ND; uint32_t fcap, tcap, ncap; };
+// positions of one list and where its special suffix (position len - 1; positions of a list are distinct, so at most one) sits
+__device__ __forceinline__ void fuse_mid_pos(const uint32_t* src, uint32_t k, uint32_t len, uint32_t (&pos)[FUSE_MID_SLOTS], int& rs, uint32_t& ls) {
+    const int l = lane_id();
+#pragma unroll
+    for (int r = 0; r < FUSE_MID_SLOTS; r++) { uint32_t q = (uint32_t)r * 32 + (uint32_t)l; pos[r] = q < k ? src[q] : FUSE_NONE; }
+    rs = -1; ls = 0;
+#pragma unroll
+    for (int r = 0; r < FUSE_MID_SLOTS; r++) {
+        uint32_t sp = __ballot_sync(0xffffffffu, pos[r] + 1 == len);
+        if (sp && rs < 0) { rs = r; ls = (uint32_t)__ffs(sp) - 1; }
     }
 }
-__device__ __forceinline__ void small_side_classes(SmallSide& s) {
-    s.ncls = 0; s.nplaced = 0;
+__device__ __forceinline__ void fuse_mid_drop(uint32_t (&cls)[FUSE_MID_SLOTS], int rs, uint32_t ls) {
+    if (rs < 0) return;
+    const int l = lane_id();
+    uint32_t mine = 0x1ffu;
+#pragma unroll
+    for (int r = 0; r < FUSE_MID_SLOTS; r++) if (r == rs) mine = cls[r];
+    uint32_t cs = __shfl_sync(0xffffffffu, mine, (int)ls);
+    uint32_t before = 0;
+#pragma unroll
+    for (int r = 0; r < FUSE_MID_SLOTS; r++) {
+        uint32_t m = __ballot_sync(0xffffffffu, cls[r] == cs);
+        if (r < rs) before |= m; else if (r == rs) before |= m & ((1u << ls) - 1u);
+    }
+    if (!before && (uint32_t)l == ls) {
+#pragma unroll
+        for (int r = 0; r < FUSE_MID_SLOTS; r++) if (r == rs) cls[r] = cs | 0x400u;
+    }
+}
+__device__ __forceinline__ bool fuse_mid(const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb, const uint32_t* srcA, uint32_t kA, const uint32_t* srcB, uint32_t kB,
+                                         const FuseOut& o, uint32_t& fo, uint32_t& to, uint32_t& nnext, uint32_t& maxsz) {
+    const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
+    uint32_t ca[FUSE_MID_SLOTS], cb[FUSE_MID_SLOTS];
+    {
+        uint32_t pa[FUSE_MID_SLOTS], pb[FUSE_MID_SLOTS]; int rsa, rsb; uint32_t lsa, lsb;
+        fuse_mid_pos(srcA, kA, na, pa, rsa, lsa);                          // both position lists first, then both byte gathers:
+        fuse_mid_pos(srcB, kB, nb, pb, rsb, lsb);                          // two memory round trips for the node, not four
+#pragma unroll
+        for (int r = 0; r < FUSE_MID_SLOTS; r++) ca[r] = pa[r] < na ? (uint32_t)a[pa[r]] : 0x1ffu;
+#pragma unroll
+        for (int r = 0; r < FUSE_MID_SLOTS; r++) cb[r] = pb[r] < nb ? (uint32_t)b[pb[r]] : 0x1ffu;
+        fuse_mid_drop(ca, rsa, lsa);
+        fuse_mid_drop(cb, rsb, lsb);
+    }
+    const int nsa = (int)((kA + 31) >> 5), nsb = (int)((kB + 31) >> 5);
     int last = -1;
     for (;;) {
-        int best = 256;
-        for (uint32_t i = 0; i < s.n; i++) if (s.live[i] && (int)s.ch[i] > last && (int)s.ch[i] < best) best = s.ch[i];
-        if (best == 256) break;
-        uint32_t cnt = 0;
-        for (uint32_t i = 0; i < s.n; i++) cnt += (s.live[i] == 1 && s.ch[i] == best) ? 1u : 0u;
-        s.cbyte[s.ncls] = (uint8_t)best; s.csize[s.ncls] = (uint8_t)cnt; s.cstart[s.ncls] = (uint8_t)s.nplaced;
-        s.ncls++; s.nplaced += cnt; last = best;
+        uint32_t m = 0x1ffu;
+#pragma unroll
+        for (int r = 0; r < FUSE_MID_SLOTS; r++) { uint32_t v = ca[r] & 0x3ffu; if (r < nsa && (int)v > last && v < m) m = v; }
+        const uint32_t ch = __reduce_min_sync(0xffffffffu, m);
+        if (ch == 0x1ffu) break;
+        last = (int)ch;
+        uint32_t na_l = 0, nb_l = 0, eb_l = 0;
+#pragma unroll
+        for (int r = 0; r < FUSE_MID_SLOTS; r++) { if (r < nsa) na_l += ca[r] == ch ? 1u : 0u; }
+#pragma unroll
+        for (int r = 0; r < FUSE_MID_SLOTS; r++) { if (r < nsb) { nb_l += cb[r] == ch ? 1u : 0u; eb_l |= (cb[r] & 0x3ffu) == ch ? 1u : 0u; } }
+        const uint32_t totA = __reduce_add_sync(0xffffffffu, na_l);
+        if (totA == 0) {                 // {_Char, []} -> [[[]], []]: the two empty suffixes, whatever B holds (:91-93)
+            if (fo + 1 > o.fcap || to + 1 > o.tcap || nnext >= o.ncap) return false;
+            if (l == 0) { o.F[fo] = na; o.T[to] = nb; FNode q; q.fo = fo; q.fc = 1; q.to = to; q.tc = 1; o.ND[nnext] = q; }
+            fo++; to++; nnext++;
+            maxsz = max(maxsz, 1u);
+            continue;
+        }
+        if (!__any_sync(0xffffffffu, eb_l != 0)) continue;                  // notfound
+        const uint32_t totB = __reduce_add_sync(0xffffffffu, nb_l);
+        if ((uint64_t)fo + totA > o.fcap || (uint64_t)to + totB > o.tcap || nnext >= o.ncap) return false;
+        uint32_t run = 0;
+#pragma unroll
+        for (int r = 0; r < FUSE_MID_SLOTS; r++) {
+            if (r < nsa) {
+                bool e = ca[r] == ch; uint32_t mb = __ballot_sync(0xffffffffu, e);
+                if (e) o.F[fo + totA - 1 - (run + (uint32_t)__popc(mb & ltm))] = srcA[(uint32_t)r * 32 + (uint32_t)l] + 1;
+                run += (uint32_t)__popc(mb);
+            }
+        }
+        run = 0;
+#pragma unroll
+        for (int r = 0; r < FUSE_MID_SLOTS; r++) {
+            if (r < nsb) {
+                bool e = cb[r] == ch; uint32_t mb = __ballot_sync(0xffffffffu, e);
+                if (e) o.T[to + totB - 1 - (run + (uint32_t)__popc(mb & ltm))] = srcB[(uint32_t)r * 32 + (uint32_t)l] + 1;
+                run += (uint32_t)__popc(mb);
+            }
+        }
+        if (l == 0) { FNode q; q.fo = fo; q.fc = totA; q.to = to; q.tc = totB; o.ND[nnext] = q; }
+        nnext++; fo += totA; to += totB;
+        maxsz = max(maxsz, max(totA, totB));
     }
+    __syncwarp();
+    return true;
 }
-__device__ __forceinline__ int small_side_find(const SmallSide& s, uint32_t byte) {
-    for (uint32_t i = 0; i < s.ncls; i++) if (s.cbyte[i] == byte) return (int)i;
-    return -1;
-}
-// classes ascending, inside a class the LAST arrival first (char_suffixes prepends)
-__device__ __forceinline__ void small_side_write(const SmallSide& s, uint32_t* dst) {
-    uint32_t w = 0;
-    for (uint32_t ci = 0; ci < s.ncls; ci++)
-        for (int i = (int)s.n - 1; i >= 0; i--) if (s.live[i] == 1 && s.ch[i] == s.cbyte[ci]) dst[w++] = s.pos[i] + 1;
+
+// ---- several consecutive nodes whose lists together hold at most 32 suffixes per side (see fuse_device, path 1): lane j holds the
+// j-th source suffix and the j-th target suffix of the run, lists back to back in the order the nodes are processed. A child is a
+// (node, first byte) group: key = node << 9 | byte. match.any gives every lane its group, its size and its arrival rank; one
+// all-pairs sweep over the 32 lanes (shuffles, no memory) gives how many placed suffixes / target suffixes / children sort before
+// the group. Same rules as everywhere: classes ascending inside a node, the last arrival first inside a class, the suffix holding
+// only the block's last byte dropped when it is the first of its class, a class left empty by that turned into [[[]], []].
+// G = number of nodes taken (>= 1), ia / ib = inclusive prefix sums of the nodes' list lengths (lane i = i-th node).
+__device__ __forceinline__ bool fuse_packed(const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb, const uint32_t* Fc, const uint32_t* Tc,
+                                            const FNode& nd, uint32_t ia, uint32_t ib, uint32_t G,
+                                            const FuseOut& o, uint32_t& fo, uint32_t& to, uint32_t& nnext, uint32_t& maxsz) {
+    const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u; const uint32_t j = (uint32_t)l;
+    const uint32_t totA = __shfl_sync(0xffffffffu, ia, (int)G - 1), totB = __shfl_sync(0xffffffffu, ib, (int)G - 1);
+    // which node does suffix j belong to: the first node whose inclusive sum exceeds j
+    int loa = 0, hia = (int)G - 1, lob = 0, hib = (int)G - 1;
+#pragma unroll
+    for (int it = 0; it < 5; it++) {
+        int ma = (loa + hia) >> 1, mb = (lob + hib) >> 1;
+        uint32_t va = __shfl_sync(0xffffffffu, ia, ma), vb = __shfl_sync(0xffffffffu, ib, mb);
+        if (loa < hia) { if (va > j) hia = ma; else loa = ma + 1; }
+        if (lob < hib) { if (vb > j) hib = mb; else lob = mb + 1; }
+    }
+    const uint32_t exa = __shfl_sync(0xffffffffu, ia - nd.fc, loa), foa = __shfl_sync(0xffffffffu, nd.fo, loa);
+    const uint32_t exb = __shfl_sync(0xffffffffu, ib - nd.tc, lob), tob = __shfl_sync(0xffffffffu, nd.to, lob);
+    uint32_t pa = FUSE_NONE, pb = FUSE_NONE;
+    if (j < totA) pa = Fc[foa + (j - exa)];
+    if (j < totB) pb = Tc[tob + (j - exb)];
+    const bool la = pa < na, lb = pb < nb;                                   // NONE and the [] suffix contribute nothing
+    const uint32_t ka = la ? ((uint32_t)loa << 9) | (uint32_t)a[pa] : 0x80000000u | j;
+    const uint32_t kb = lb ? ((uint32_t)lob << 9) | (uint32_t)b[pb] : 0xc0000000u | j;
+    const uint32_t ga = __match_any_sync(0xffffffffu, ka), gb = __match_any_sync(0xffffffffu, kb);
+    const bool firsta = la && (ga & ltm) == 0, firstb = lb && (gb & ltm) == 0;
+    const bool placeda = la && !(firsta && pa + 1 == na), placedb = lb && !(firstb && pb + 1 == nb);
+    const uint32_t pma = __ballot_sync(0xffffffffu, placeda), pmb = __ballot_sync(0xffffffffu, placedb), lvb = __ballot_sync(0xffffffffu, lb);
+    const uint32_t sza = (uint32_t)__popc(ga & pma), rka = (uint32_t)__popc(ga & pma & ltm);
+    const uint32_t szb = (uint32_t)__popc(gb & pmb), rkb = (uint32_t)__popc(gb & pmb & ltm);
+    uint32_t lessAA = 0, lessBA = 0, eqBA = 0, existsBA = 0, lessBB = 0;
+#pragma unroll 8
+    for (int t = 0; t < 32; t++) {
+        uint32_t xa = __shfl_sync(0xffffffffu, ka, t), xb = __shfl_sync(0xffffffffu, kb, t);
+        uint32_t pla = (pma >> t) & 1u, plb = (pmb >> t) & 1u;
+        lessAA += (xa < ka) ? pla : 0u;
+        lessBA += (xb < ka) ? plb : 0u;
+        eqBA += (xb == ka) ? plb : 0u;
+        existsBA |= (xb == ka) ? ((lvb >> t) & 1u) : 0u;
+        lessBB += (xb < kb) ? plb : 0u;
+    }
+    const uint32_t nplA = (uint32_t)__popc(pma), nplB = (uint32_t)__popc(pmb);
+    const bool quirk = firsta && sza == 0;
+    const bool emit = firsta && (sza == 0 || existsBA);
+    const uint32_t em = __ballot_sync(0xffffffffu, emit), qm = __ballot_sync(0xffffffffu, quirk);
+    const uint32_t nq = (uint32_t)__popc(qm), nch = (uint32_t)__popc(em);
+    if ((uint64_t)fo + nplA + nq > o.fcap || (uint64_t)to + nplB + nq > o.tcap || (uint64_t)nnext + nch > o.ncap) return false;
+    uint32_t cidx = 0;                                                       // children with a smaller key come first
+    for (uint32_t mm = em; mm;) { int t = __ffs(mm) - 1; mm &= mm - 1; uint32_t xk = __shfl_sync(0xffffffffu, ka, t); cidx += (xk < ka) ? 1u : 0u; }
+    if (placeda) o.F[fo + lessAA + sza - 1 - rka] = pa + 1;
+    if (placedb) o.T[to + lessBB + szb - 1 - rkb] = pb + 1;
+    uint32_t big = 0;
+    if (emit) {
+        FNode q;
+        if (quirk) {
+            uint32_t qi = (uint32_t)__popc(qm & ltm);
+            o.F[fo + nplA + qi] = na; o.T[to + nplB + qi] = nb;
+            q.fo = fo + nplA + qi; q.fc = 1; q.to = to + nplB + qi; q.tc = 1; big = 1;
+        } else { q.fo = fo + lessAA; q.fc = sza; q.to = to + lessBA; q.tc = eqBA; big = max(sza, eqBA); }
+        o.ND[nnext + cidx] = q;
+    }
+    maxsz = max(maxsz, __reduce_max_sync(0xffffffffu, big));
+    fo += nplA + nq; to += nplB + nq; nnext += nch;
+    __syncwarp();
+    return true;
 }
 
 // find_jump_points/2 :103-128 + any_position_pair/1 :73-77
@@ -162,6 +369,7 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
     { FNode r0; r0.fo = 0; r0.fc = na; r0.to = 0; r0.tc = nb; ND[0][0] = r0; }
     int64_t fuel = 100000;
     bool compact = false;
+    FuseClock clk; clk.tab = c.ar.mut_ns ? c.ar.mut_ns + 2 * M_COUNT : nullptr; clk.t0 = 0;
     for (;;) {
         bool stop = fuel < 0;
         if (!stop) stop = g.rand(8) == 0;
@@ -172,6 +380,7 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
             // buffers; a step reads 32 nodes with two coalesced loads and two byte gathers, nothing depends on the previous step
             // but the output offset. Same rules as the general path written out for one-element lists.
             const int nx = cur ^ 1;
+            clk.start();
             const uint32_t* PA = F[cur]; const uint32_t* PB = T[cur]; uint32_t* QA = F[nx]; uint32_t* QB = T[nx];
             const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
             for (uint32_t e = ncur; e > 0;) {
@@ -191,6 +400,7 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
                 e -= take;
             }
             __syncwarp();
+            clk.stop(FPH_COMPACT);
             if (nnext == 0) stop = true;
             else { fuel -= (int64_t)nnext; cur = nx; ncur = nnext; continue; }
         }
@@ -200,67 +410,110 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
             // nodes are stored in emission order; the reference's list is that order reversed
             uint32_t e = ncur;
             const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
+            FuseOut o; o.F = F[nx]; o.T = T[nx]; o.ND = ND[nx]; o.fcap = (uint32_t)fcap; o.tcap = (uint32_t)tcap; o.ncap = (uint32_t)ncap;
             while (e > 0) {
-                // (1) a run of SMALL nodes (at most FUSE_K suffixes on each side -- what a level degenerates to after the
-                //     first split or two): one node per LANE, the same classification rules written out serially per lane
-                //     (classes ascending by byte, newest first inside a class, the [[]] -> [] drop, the {Char, []} quirk).
-                //     Measured before this path existed: ft on a 4 KiB random block 24 ms, nearly all of it in the ~256
-                //     sixteen-by-sixteen nodes of the second level taken one node per warp step (profiles/tc_c2_r2a.txt).
-                bool valid = (uint32_t)l < e;
-                FNode nd; nd.fo = nd.to = 0; nd.fc = nd.tc = FUSE_K + 1;
+                // Lane i looks at the i-th node from the top of the list. What the level looks like after the first split or two
+                // (profiles/tc_c2_r2d.txt, tc_c5_r2d.txt): nine nodes in ten hold one suffix per side, most of the rest a handful,
+                // a few dozen hold 25-250 (a phrase or a period repeated in the block), and the root and its first children thousands.
+                const bool valid = (uint32_t)l < e;
+                FNode nd; nd.fo = nd.to = 0; nd.fc = nd.tc = 64;
                 if (valid) nd = ND[cur][e - 1 - (uint32_t)l];
-                uint32_t sm = __ballot_sync(0xffffffffu, valid && nd.fc <= FUSE_K && nd.tc <= FUSE_K);
-                uint32_t runlen = sm == 0xffffffffu ? 32u : (uint32_t)__ffs(~sm) - 1u;
-                if (runlen > 0) {
-                    bool act = (uint32_t)l < runlen;
-                    SmallSide A, B;
-                    uint32_t nquirk = 0, nchild = 0;
-                    if (act) {
-                        small_side_load(A, F[cur] + nd.fo, nd.fc, a, na);
-                        small_side_load(B, T[cur] + nd.to, nd.tc, b, nb);
-                        small_side_classes(A); small_side_classes(B);
-                        for (uint32_t ci = 0; ci < A.ncls; ci++) {
-                            if (A.csize[ci] == 0) { nquirk++; nchild++; }
-                            else if (small_side_find(B, A.cbyte[ci]) >= 0) nchild++;
-                        }
+                // (0) a run of TINY nodes (at most one suffix per side): the rules written out for one-element lists, one node per
+                //     lane, a handful of instructions.
+                const uint32_t tm = __ballot_sync(0xffffffffu, valid && nd.fc <= 1 && nd.tc <= 1);
+                const uint32_t tinyrun = tm == 0xffffffffu ? 32u : (uint32_t)__ffs(~tm) - 1u;
+                if (tinyrun >= 16 || (tinyrun > 0 && tinyrun == e)) {
+                    clk.start();
+                    bool act = (uint32_t)l < tinyrun;
+                    uint32_t pa = FUSE_NONE, pb = FUSE_NONE;
+                    if (act && nd.fc) pa = F[cur][nd.fo];
+                    if (act && nd.tc) pb = T[cur][nd.to];
+                    bool ha = pa < na, hb = pb < nb;                       // NONE and the [] suffix contribute nothing
+                    uint32_t cha = ha ? a[pa] : 0x100u, chb = hb ? b[pb] : 0x200u;
+                    bool child = false; uint32_t ca = 0, cb = 0, tcn = 1;
+                    if (ha && pa + 1 == na) { child = true; ca = na; cb = nb; }                    // {_Char, []} -> [[[]], []] (:91-93)
+                    else if (cha == chb) { child = true; ca = pa + 1; cb = pb + 1; if (pb + 1 == nb) tcn = 0; }
+                    uint32_t cm = __ballot_sync(0xffffffffu, child);
+                    uint32_t cn = (uint32_t)__popc(cm);
+                    if ((uint64_t)fo + cn > fcap || (uint64_t)to + cn > tcap || (uint64_t)nnext + cn > ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
+                    if (child) {
+                        uint32_t at = (uint32_t)__popc(cm & ltm);
+                        F[nx][fo + at] = ca; T[nx][to + at] = cb;
+                        FNode q; q.fo = fo + at; q.fc = 1; q.to = to + at; q.tc = tcn; ND[nx][nnext + at] = q;
                     }
-                    uint32_t fadd = act ? A.nplaced + nquirk : 0u, tadd = act ? B.nplaced + nquirk : 0u, cadd = act ? nchild : 0u;
-                    uint32_t fpre = fadd, tpre = tadd, cpre = cadd;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        uint32_t x = __shfl_up_sync(0xffffffffu, fpre, o), y = __shfl_up_sync(0xffffffffu, tpre, o), z = __shfl_up_sync(0xffffffffu, cpre, o);
-                        if (l >= o) { fpre += x; tpre += y; cpre += z; }
-                    }
-                    uint32_t ftot = __shfl_sync(0xffffffffu, fpre, 31), ttot = __shfl_sync(0xffffffffu, tpre, 31), ctot = __shfl_sync(0xffffffffu, cpre, 31);
-                    if ((uint64_t)fo + ftot > fcap || (uint64_t)to + ttot > tcap || (uint64_t)nnext + ctot > ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
-                    uint32_t lane_max = 0;
-                    if (act) {
-                        uint32_t f0 = fo + fpre - fadd, t0 = to + tpre - tadd, c0 = nnext + cpre - cadd;
-                        small_side_write(A, F[nx] + f0);
-                        small_side_write(B, T[nx] + t0);
-                        uint32_t fq = f0 + A.nplaced, tq = t0 + B.nplaced;
-                        for (uint32_t ci = 0; ci < A.ncls; ci++) {
-                            FNode ch_n;
-                            if (A.csize[ci] == 0) {        // {_Char, []} -> [[[]], []]: the two empty suffixes, whatever B holds (:91-93)
-                                F[nx][fq] = na; T[nx][tq] = nb;
-                                ch_n.fo = fq; ch_n.fc = 1; ch_n.to = tq; ch_n.tc = 1; fq++; tq++;
-                                ND[nx][c0++] = ch_n; continue;
-                            }
-                            int bi = small_side_find(B, A.cbyte[ci]);
-                            if (bi < 0) continue;                                   // notfound
-                            ch_n.fo = f0 + A.cstart[ci]; ch_n.fc = A.csize[ci]; ch_n.to = t0 + B.cstart[bi]; ch_n.tc = B.csize[bi];
-                            ND[nx][c0++] = ch_n;
-                            uint32_t mx = ch_n.fc > ch_n.tc ? ch_n.fc : ch_n.tc; if (mx > lane_max) lane_max = mx;
-                        }
-                    }
-                    maxsz = max(maxsz, __reduce_max_sync(0xffffffffu, lane_max));
-                    fo += ftot; to += ttot; nnext += ctot; e -= runlen;
+                    if (cn) maxsz = max(maxsz, 1u);
+                    fo += cn; to += cn; nnext += cn; e -= tinyrun;
                     __syncwarp();
+                    clk.stop(FPH_TINY);
                     continue;
                 }
-                // (2) a node with longer lists: warp-parallel classification, children walked class by class
+                // (1) as many consecutive nodes as fit 32 suffixes per side together: one suffix per lane and side (fuse_packed)
+                uint32_t ia = min(nd.fc, 64u), ib = min(nd.tc, 64u);
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    uint32_t x = __shfl_up_sync(0xffffffffu, ia, o2), y = __shfl_up_sync(0xffffffffu, ib, o2);
+                    if (l >= o2) { ia += x; ib += y; }
+                }
+                const uint32_t okm = __ballot_sync(0xffffffffu, valid && ia <= 32 && ib <= 32);
+                const uint32_t G = okm == 0xffffffffu ? 32u : (uint32_t)__ffs(~okm) - 1u;
+                if (G > 0) {
+                    clk.start();
+                    if (!fuse_packed(a, na, b, nb, F[cur], T[cur], nd, ia, ib, G, o, fo, to, nnext, maxsz)) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
+                    e -= G;
+                    clk.stop(FPH_SMALL);
+                    continue;
+                }
                 e--;
                 nd = ND[cur][e];
+                clk.start();
+                // (2a) one node of up to FUSE_MID suffixes per side: first bytes in registers, classes by min reduction (fuse_mid)
+                if (nd.fc <= FUSE_MID && nd.tc <= FUSE_MID) {
+                    if (!fuse_mid(a, na, b, nb, F[cur] + nd.fo, nd.fc, T[cur] + nd.to, nd.tc, o, fo, to, nnext, maxsz)) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
+                    clk.stop(FPH_MID);
+                    continue;
+                }
+                // (2b) a node with longer lists, counters in shared memory: warp-parallel classification, then the children taken
+                //      eight classes per lane
+                if (nd.fc < 65535u && nd.tc < 65535u) {
+                    uint32_t ma, mb;
+                    const uint32_t fa2 = fuse_classify_sm(a, na, F[cur] + nd.fo, nd.fc, F[nx], fo, c.ws->sc, sa.start, sizeA, ma);
+                    const uint32_t tb2 = fuse_classify_sm(b, nb, T[cur] + nd.to, nd.tc, T[nx], to, c.ws->sc, sb.start, sizeB, mb);
+                    uint32_t szs[8]; uint32_t nch_l = 0, nq_l = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        szs[i] = 0xffffffffu;                                                     // no child
+                        if ((ma >> i) & 1u) {
+                            uint32_t sz = sizeA[8 * l + i];
+                            if (sz == 0) { szs[i] = 0; nch_l++; nq_l++; }                         // {_Char, []} -> [[[]], []] (:91-93)
+                            else if ((mb >> i) & 1u) { szs[i] = sz; nch_l++; }                    // else notfound
+                        }
+                    }
+                    uint32_t cpre = nch_l, qpre = nq_l;
+#pragma unroll
+                    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                        uint32_t x = __shfl_up_sync(0xffffffffu, cpre, o2), y = __shfl_up_sync(0xffffffffu, qpre, o2);
+                        if (l >= o2) { cpre += x; qpre += y; }
+                    }
+                    const uint32_t ctot = __shfl_sync(0xffffffffu, cpre, 31), qtot = __shfl_sync(0xffffffffu, qpre, 31);
+                    if ((uint64_t)fo + fa2 + qtot > fcap || (uint64_t)to + tb2 + qtot > tcap || (uint64_t)nnext + ctot > ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
+                    uint32_t ci = nnext + cpre - nch_l, qi = qpre - nq_l, big = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        if (szs[i] == 0xffffffffu) continue;
+                        FNode q; uint32_t ch = 8u * (uint32_t)l + (uint32_t)i;
+                        if (szs[i] == 0) {
+                            F[nx][fo + fa2 + qi] = na; T[nx][to + tb2 + qi] = nb;
+                            q.fo = fo + fa2 + qi; q.fc = 1; q.to = to + tb2 + qi; q.tc = 1; qi++; big = max(big, 1u);
+                        } else { q.fo = sa.start[ch]; q.fc = szs[i]; q.to = sb.start[ch]; q.tc = sizeB[ch]; big = max(big, max(q.fc, q.tc)); }
+                        ND[nx][ci++] = q;
+                    }
+                    maxsz = max(maxsz, __reduce_max_sync(0xffffffffu, big));
+                    fo += fa2 + qtot; to += tb2 + qtot; nnext += ctot;
+                    __syncwarp();
+                    clk.stop(FPH_BIG);
+                    continue;
+                }
+                // (2c) lists of 65 535 suffixes and more: the same through counters in global memory
                 uint32_t fa = fuse_classify(sa, F[cur] + nd.fo, nd.fc, F[nx], fo, sizeA);
                 uint32_t tb = fuse_classify(sb, T[cur] + nd.to, nd.tc, T[nx], to, sizeB);
                 for (int w = 0; w < 8; w++) {
@@ -285,6 +538,7 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
                 }
                 fo += fa; to += tb;
                 __syncwarp();
+                clk.stop(FPH_BIG);
             }
             if (nnext == 0) stop = true;
             else {

@@ -87,17 +87,6 @@ EB_DEV void emit_pieces(CaseCtx& c, const uint8_t* p, uint32_t n, const Piece* p
     t_push(ws, seg_copy(buf, (uint32_t)total));
 }
 
-// chunk table of the string lexer in temp memory (entry L is the end sentinel)
-EB_DEV ChunkEnt* lex_table(CaseCtx& c, const uint8_t* p, uint32_t n, uint32_t& L, bool& stringy) {
-    L = lex_device(p, n, nullptr, &stringy);
-    ChunkEnt* tab = (ChunkEnt*)temp_alloc(c, (uint64_t)(L + 1) * sizeof(ChunkEnt));
-    if (!tab) return nullptr;
-    lex_device(p, n, tab, &stringy);
-    if (lane_id() == 0) { tab[L].start = n; tab[L].type = CH_BYTE; }
-    __syncwarp();
-    return tab;
-}
-
 // ------------------------------------------------------------------ nested scheduler round
 struct InnerRes { int kind; uint32_t len; };   // kind 0: unchanged input, 1: ws->tseg (first len bytes), 2: ws->rrun (first len bytes)
 struct InnerSaved { StSlot st[2][10]; int st_n[2]; const uint8_t* fo_p; uint32_t fo_n; int fo_has; int has_next; const uint8_t* next_p; uint32_t next_n; };
@@ -215,8 +204,8 @@ EB_DEV void mut_uri(CaseCtx& c, MutRow& row, const uint8_t* p, uint32_t n, MutRe
     row.fn = M_B64;                                                      // the successor it returns is base64_mutator/2 (:784)
     uint32_t L; bool stringy = false;
     ChunkEnt* tab = lex_table(c, p, n, L, stringy);
-    if (!tab) { r.delta = 0; return; }
     if (!stringy) return;
+    if (!tab) { r.delta = 0; return; }
     Piece* pc = (Piece*)temp_alloc(c, sizeof(Piece) * MAX_PIECES);
     if (!pc) { r.delta = 0; return; }
     int np = 0; double d = -1;
@@ -338,8 +327,8 @@ EB_DEV void mut_b64(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     (void)g.rand_elem_idx(1);
     uint32_t L; bool stringy = false;
     ChunkEnt* tab = lex_table(c, p, n, L, stringy);
-    if (!tab) { r.delta = 0; return; }
     if (!stringy) return;
+    if (!tab) { r.delta = 0; return; }
     Piece* pc = (Piece*)temp_alloc(c, sizeof(Piece) * MAX_PIECES);
     MutRow* rows = (MutRow*)temp_alloc(c, sizeof(MutRow) * M_COUNT);
     if (!pc || !rows) { r.delta = 0; return; }

@@ -2,9 +2,10 @@
 // src/erlamsa_strlex.erl:46-156) and the text mutations built on it (reference
 // src/erlamsa_mutations.erl:436-651: `ab` construct_ascii_bad_mutator, `ad` construct_ascii_delimeter_mutator).
 //
-// The lexer is a sequential automaton (texty runs >= 6, quote pairing with backslash skipping); it is run
-// warp-uniformly over the block. Every chunk it produces is a CONTIGUOUS range of the input, so the chunk
-// list is just a table of (type, start) written to scratch; the mutation of one chunk becomes an edit script.
+// The lexer is a sequential automaton (texty runs >= 6, quote pairing with backslash skipping); its events are found
+// 32 positions at a time in bit masks built once per block (lex_masks / lex_device below). Every chunk it produces is a
+// CONTIGUOUS range of the input, so the chunk list is just a table of (type, start) in temp memory; the mutation of one
+// chunk becomes an edit script.
 #pragma once
 #include "eb_state.cuh"
 
@@ -20,55 +21,123 @@ EB_DEV bool texty(uint32_t b) {   // :46-52
     return b == 9 || b == 10 || b == 13;
 }
 
-// lex/1 :75-143. tab == nullptr: count only. Returns the number of chunks; *stringy = any non-byte chunk.
-EB_DEV uint32_t lex_device(const uint8_t* d, uint32_t n, ChunkEnt* tab, bool* stringy) {
+// ---- lex/1 :75-143, event driven.
+// The reference's automaton has three states -- outside (raw bytes until six texty bytes in a row start, texty_enough/2 :54-64),
+// text (until a quote or a non-texty byte, step_text :95-107) and delimited (until the closing quote, a non-texty byte or a
+// backslash, step_delimited :114-143) -- and in each of them nothing happens until the next byte of one small class. So the
+// block is classified ONCE, 128 bytes per warp step, into four bit masks (one bit per position), and the automaton then hops
+// from event to event with a find-next-set-bit over a 1024-position register window per mask:
+//   E   the next six positions (cut at the block's end) are all texty            -> outside: where text starts
+//   MT  not texty, or a quote                                                     -> text: where it ends / a string opens
+//   MD1 / MD2  the double / single quote, not texty, or a backslash               -> delimited
+// Between events the bytes are never looked at; the chunk list comes out exactly as the byte-by-byte walk gives it.
+struct LexMasks { const uint32_t* E; const uint32_t* MT; const uint32_t* MD1; const uint32_t* MD2; uint32_t nw; };
+
+EB_DEV bool lex_masks(CaseCtx& c, const uint8_t* d, uint32_t n, LexMasks& m) {
+    const uint32_t nw = (n + 31) >> 5;
+    uint32_t* base = (uint32_t*)temp_alloc(c, (uint64_t)(5 * (nw + 1)) * 4);
+    if (!base) return false;
+    uint32_t* T = base; uint32_t* E = base + (nw + 1); uint32_t* MT = E + (nw + 1); uint32_t* M1 = MT + (nw + 1); uint32_t* M2 = M1 + (nw + 1);
+    const int l = lane_id();
+    for (uint32_t w0 = 0; w0 < nw; w0 += 4) {
+        uint32_t b[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { uint32_t q = (w0 + (uint32_t)j) * 32 + (uint32_t)l; b[j] = q < n ? (uint32_t)d[q] : 0x100u; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t v = b[j];
+            bool inb = v < 0x100u;
+            bool t = (v >= 32 && v <= 126) || v == 9 || v == 10 || v == 13;
+            uint32_t tw = __ballot_sync(0xffffffffu, t || !inb);          // past the end counts as texty (texty_enough on a short tail)
+            uint32_t nt = __ballot_sync(0xffffffffu, inb && !t);
+            uint32_t qd = __ballot_sync(0xffffffffu, v == 34), qs = __ballot_sync(0xffffffffu, v == 39), bs = __ballot_sync(0xffffffffu, v == 92);
+            if (l == j && w0 + (uint32_t)j < nw) { uint32_t w = w0 + (uint32_t)j; T[w] = tw; MT[w] = nt | qd | qs; M1[w] = qd | nt | bs; M2[w] = qs | nt | bs; }
+        }
+    }
+    if (l == 0) { T[nw] = 0xffffffffu; E[nw] = 0; MT[nw] = 0; M1[nw] = 0; M2[nw] = 0; }
+    __syncwarp();
+    for (uint32_t w = (uint32_t)l; w < nw; w += 32) {
+        uint64_t x = (uint64_t)T[w] | ((uint64_t)T[w + 1] << 32);
+        uint64_t e = x & (x >> 1) & (x >> 2) & (x >> 3) & (x >> 4) & (x >> 5);
+        uint32_t valid = (w + 1) * 32 <= n ? 0xffffffffu : ((1u << (n & 31)) - 1u);
+        E[w] = (uint32_t)e & valid;
+    }
+    __syncwarp();
+    m.E = E; m.MT = MT; m.MD1 = M1; m.MD2 = M2; m.nw = nw;
+    return true;
+}
+
+// forward-only cursor over one mask: lane l holds word base + l
+struct LexWin {
+    const uint32_t* M; uint32_t nw; uint32_t base; uint32_t v;
+    __device__ __forceinline__ void init(const uint32_t* mask, uint32_t words) { M = mask; nw = words; base = 0xffffffffu; v = 0; }
+    // first set position >= p, or n
+    __device__ __forceinline__ uint32_t next(uint32_t p, uint32_t n) {
+        if (p >= n) return n;
+        const int l = lane_id();
+        uint32_t w = p >> 5;
+        for (;;) {
+            if (base == 0xffffffffu || w < base || w >= base + 32) { base = w; uint32_t idx = base + (uint32_t)l; v = idx < nw ? M[idx] : 0u; }
+            uint32_t x = v;
+            uint32_t idx = base + (uint32_t)l;
+            if (idx < (p >> 5)) x = 0; else if (idx == (p >> 5)) x &= 0xffffffffu << (p & 31);
+            uint32_t bal = __ballot_sync(0xffffffffu, x != 0);
+            if (bal) { int src = __ffs(bal) - 1; uint32_t xx = __shfl_sync(0xffffffffu, x, src); return (base + (uint32_t)src) * 32 + (uint32_t)__ffs(xx) - 1; }
+            w = base + 32;
+            if (w >= nw) return n;
+        }
+    }
+};
+
+// tab == nullptr: count only. Returns the number of chunks; *stringy = any non-byte chunk.
+EB_DEV uint32_t lex_device(const LexMasks& m, const uint8_t* d, uint32_t n, ChunkEnt* tab, bool* stringy) {
     uint32_t cnt = 0; bool str = false;
-    uint32_t p = 0; bool have_raw = false; uint32_t raw_start = 0;
     auto emit = [&](uint32_t type, uint32_t start) {
         if (tab && lane_id() == 0) { tab[cnt].start = start; tab[cnt].type = type; }
         cnt++; if (type != CH_BYTE) str = true;
     };
+    LexWin we, wt, w1, w2; we.init(m.E, m.nw); wt.init(m.MT, m.nw); w1.init(m.MD1, m.nw); w2.init(m.MD2, m.nw);
+    uint32_t p = 0;
     while (p < n) {
-        // texty_enough/2 :54-64 (MIN_TEXTY = 6; a short all-texty tail also counts)
-        bool te = true;
-        for (uint32_t k = 0; k < 6; k++) { if (p + k >= n) break; if (!texty(d[p + k])) { te = false; break; } }
-        if (!te) { if (!have_raw) { have_raw = true; raw_start = p; } p++; continue; }
-        if (have_raw) { emit(CH_BYTE, raw_start); have_raw = false; }
-        // step_text :95-107
-        uint32_t seen_start = p;
+        uint32_t p2 = we.next(p, n);                       // outside: raw bytes up to the start of a texty run
+        if (p2 > p) emit(CH_BYTE, p);
+        if (p2 >= n) break;
+        const uint32_t seen_start = p2;
+        uint32_t x = wt.next(p2, n);                       // step_text :95-107
+        if (x >= n) { emit(CH_TEXT, seen_start); break; }
+        uint32_t h = d[x];
+        if (h != 34 && h != 39) { emit(CH_TEXT, seen_start); p = x; continue; }       // a non-texty byte ends the text
+        const uint32_t q = x; p = x + 1;                   // step_delimited :114-143
         for (;;) {
-            if (p >= n) { emit(CH_TEXT, seen_start); break; }
-            uint32_t h = d[p];
-            if (h == 34 || h == 39) {
-                // step_delimited :114-143
-                uint32_t q = p; p++;
-                bool closed = false;
-                for (;;) {
-                    if (p >= n) break;
-                    uint32_t c = d[p];
-                    if (c == h) { closed = true; break; }
-                    if (c == 92 && p + 1 >= n) { p++; continue; }
-                    if (c == 92) { if (texty(d[p + 1])) p += 2; else p++; continue; }
-                    if (texty(c)) { p++; continue; }
-                    break;
-                }
-                if (closed) {
-                    if (q > seen_start) emit(CH_TEXT, seen_start);
-                    emit(CH_DELIM, q);
-                    p++;
-                } else {
-                    emit(CH_TEXT, seen_start);   // seen ++ quote ++ after, one contiguous text chunk
-                }
-                break;
+            uint32_t y = h == 34 ? w1.next(p, n) : w2.next(p, n);
+            if (y >= n) { emit(CH_TEXT, seen_start); p = n; break; }                  // never closed: seen ++ quote ++ after, one text chunk
+            uint32_t cc = d[y];
+            if (cc == h) { if (q > seen_start) emit(CH_TEXT, seen_start); emit(CH_DELIM, q); p = y + 1; break; }
+            if (cc == 92) {
+                if (y + 1 >= n) { p = y + 1; continue; }
+                p = texty(d[y + 1]) ? y + 2 : y + 1; continue;
             }
-            if (texty(h)) { p++; continue; }
-            emit(CH_TEXT, seen_start); break;
+            emit(CH_TEXT, seen_start); p = y; break;                                  // a non-texty byte inside the string
         }
     }
-    if (have_raw) emit(CH_BYTE, raw_start);
     *stringy = str;
     __syncwarp();
     return cnt;
+}
+
+// chunk table of the string lexer in temp memory (entry L is the end sentinel). nullptr: no memory (the case is flagged) or,
+// with stringy == false, nothing but raw bytes in the block (no table is built then)
+EB_DEV ChunkEnt* lex_table(CaseCtx& c, const uint8_t* p, uint32_t n, uint32_t& L, bool& stringy) {
+    LexMasks m; L = 0; stringy = false;
+    if (!lex_masks(c, p, n, m)) { stringy = true; return nullptr; }
+    L = lex_device(m, p, n, nullptr, &stringy);
+    if (!stringy) return nullptr;
+    ChunkEnt* tab = (ChunkEnt*)temp_alloc(c, (uint64_t)(L + 1) * sizeof(ChunkEnt));
+    if (!tab) return nullptr;
+    lex_device(m, p, n, tab, &stringy);
+    if (lane_id() == 0) { tab[L].start = n; tab[L].type = CH_BYTE; }
+    __syncwarp();
+    return tab;
 }
 
 // small literal builder in scratch (lane 0 writes)
@@ -196,14 +265,10 @@ EB_DEV void mutate_text(CaseCtx& c, int m, const uint8_t* t, uint32_t n) {
 EB_DEV void mut_ascii(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutResult& r) {
     WarpState* ws = c.ws; Rng& g = c.rng;
     r.rechunk = 0; r.consumed_next = 0;
-    bool stringy = false;
-    uint32_t L = lex_device(p, n, nullptr, &stringy);
+    bool stringy = false; uint32_t L = 0;
+    ChunkEnt* tab = lex_table(c, p, n, L, stringy);
     if (!stringy) { r.kind = RES_SAME; r.delta = -1; return; }
-    ChunkEnt* tab = (ChunkEnt*)temp_alloc(c, (uint64_t)(L + 1) * sizeof(ChunkEnt));
     if (!tab) { r.kind = RES_SAME; r.delta = 0; return; }
-    lex_device(p, n, tab, &stringy);
-    if (lane_id() == 0) { tab[L].start = n; tab[L].type = CH_BYTE; }
-    __syncwarp();
     t_reset(ws);
     bool done = false;
     for (uint32_t rr = 0; !((double)rr > (double)L / 4.0); rr++) {

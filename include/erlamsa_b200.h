@@ -151,7 +151,8 @@ void eb200_free(void* p);
 /* profiling aid: with EB200_CASE_TIMES=1 in the environment at eb200_init, microseconds the general per-case program spent on
  * each case of the last launch (0 for cases decided by the front warps). Returns the number of entries copied. */
 uint64_t eb200_debug_case_times(eb200_ctx* ctx, uint32_t* out, uint64_t n);
-/* ... and per mutator (table order): out[2*i] = nanoseconds spent inside mutator i, out[2*i+1] = calls; out holds 82 entries */
+/* ... and per mutator (table order): out[2*i] = nanoseconds spent inside mutator i, out[2*i+1] = calls; then five (ns, steps) pairs for the
+ * phases of the fuse search; out holds 98 entries */
 int eb200_debug_mutator_times(eb200_ctx* ctx, uint64_t* out);
 
 /* Same as eb200_fuzz_batch, but the outputs are written into a caller buffer (e.g. a resource binary or pinned

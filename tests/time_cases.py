@@ -1,5 +1,5 @@
 """Where does the time of a batch go? (not a test; run on the GPU box)
-usage: EB200_CASE_TIMES=1 python tests/time_cases.py c2|c4|smoke [n_cases]
+usage: EB200_CASE_TIMES=1 python tests/time_cases.py c2|c4|c5|smoke [n_cases]
 Runs one batch through the host path with per-case timing of the general program (eb200_debug_case_times) and prints the
 total by first used mutator / pattern and the slowest cases."""
 import ctypes as C
@@ -26,6 +26,11 @@ elif which == "c4":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     blobs = corpus.uniform_corpus(0xE21A0004, min(n, 64), 262144, "markup")
     opts = {"seed": (1, 2, 3), "mutations": {c: 1 for c in ("ab", "ad", "tr2", "td", "ts1", "ts2", "tr", "sgm", "js")}, "patterns": {"od": 1}}
+elif which == "c5":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+    r5 = corpus.rng(0xE21A0005)
+    blobs = [corpus.structured_text(r5, 4096).ljust(4096, b" ")[:4096] for _ in range(256)]
+    opts = {"seed": (1, 2, 3), "mutations": {"ft": 1, "fn": 1, "fo": 1}, "patterns": {"od": 1}}
 else:
     n = 256
     blobs = corpus.mixed_corpus(0x5A0CE, 256, max_len=3000)
@@ -60,11 +65,15 @@ for k in sorted(range(n), key=lambda k: -us[k])[:25]:
     print("  case %6d  %9.2f ms  pat %-3s used %-40s fails %3d in %7d out %8d status %d/%d draws %d" % (
         k, us[k] / 1e3, PC[m.pattern] if 0 <= m.pattern < len(PC) else "?", ",".join(MC[u] for u in m.used if u >= 0), m.n_failed,
         len(blobs[k % len(blobs)]), len(outs[k]), m.status, m.pad, m.draws))
-mt = (C.c_uint64 * 82)()
+mt = (C.c_uint64 * 98)()
 N.lib().eb200_debug_mutator_times.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
 if N.lib().eb200_debug_mutator_times(eng._ctx, mt):
     print("time inside each mutator (all attempts, successful or not):")
     for i in sorted(range(41), key=lambda i: -mt[2 * i]):
         if mt[2 * i + 1]:
             print("  %-6s total %10.1f ms  calls %7d  mean %9.1f us" % (MC[i], mt[2 * i] / 1e6, mt[2 * i + 1], mt[2 * i] / 1e3 / mt[2 * i + 1]))
+    print("fuse search by phase:")
+    for j, name in enumerate(("tables (> 256 per side)", "registers (25..256)", "lane per node (2..24)", "one suffix per side", "flat levels")):
+        if mt[82 + 2 * j + 1]:
+            print("  %-26s total %10.1f ms  steps %8d  mean %9.2f us" % (name, mt[82 + 2 * j] / 1e6, mt[82 + 2 * j + 1], mt[82 + 2 * j] / 1e3 / mt[82 + 2 * j + 1]))
 # time by mutator TRIED is not recorded; failures dominate when `used` is short and n_failed large
