@@ -11,6 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.environ.get("EB200_LIB") or os.path.join(PKG_DIR, "liberlamsa_b200.so")   # EB200_LIB: A/B builds of the same engine
 SRC = os.path.join(PKG_DIR, "csrc", "eb_engine.cu")
+SRC_WIDE = os.path.join(PKG_DIR, "csrc", "eb_wide.cu")   # the general kernel once more, for 512 threads / 128 registers
 
 N_MUTATORS = 41
 N_PATTERNS = 10
@@ -49,7 +50,7 @@ def build(force=False):
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    subprocess.check_call([nvcc] + NVCC_FLAGS + [SRC, "-o", LIB_PATH])
+    subprocess.check_call([nvcc] + NVCC_FLAGS + [SRC, SRC_WIDE, "-o", LIB_PATH])
     return LIB_PATH
 
 

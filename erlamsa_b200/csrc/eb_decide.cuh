@@ -490,7 +490,10 @@ __global__ void __launch_bounds__(256) eb_slot_sizes(const uint64_t* __restrict_
     sz16[k] = align16(len + slack);
 }
 
-constexpr int CASE_THREADS = 1024;
+#ifndef EB_CASE_THREADS
+#define EB_CASE_THREADS 1024
+#endif
+constexpr int CASE_THREADS = EB_CASE_THREADS;   // threads per CTA = the register budget the per-case program is compiled for (64 at 1024)
 constexpr int PW_BITS = 48;
 
 // one test case, start to finish, decided by one warp (bulk byte work goes to the CTA's workers through q)

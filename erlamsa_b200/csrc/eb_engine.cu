@@ -21,6 +21,11 @@
 #include "eb_apply.cuh"
 #include "eb_erlsort.hpp"
 
+// eb_wide.cu: eb_case_kernel<FULL> compiled for 512 threads per CTA (128 registers per thread)
+extern "C" int eb200_wide_init(void);
+extern "C" void eb200_wide_launch(int grid, int threads, size_t smem, cudaStream_t st, const uint8_t* d_data, const uint64_t* d_off,
+                                  const void* bp, const void* ar, void* cases, uint64_t* out_len, uint64_t* sz16, void* meta, const void* fa);
+
 using namespace eb;
 
 static const char* const kMutCodes[EB200_N_MUTATORS] = {
@@ -57,6 +62,7 @@ struct eb200_ctx {
     cudaEvent_t ev[6];
     bool funny_loaded = false;
     int apply_variant = 0;
+    int wide = 0;                 // general kernel at 512 threads / 128 registers: -1 chosen per launch, 0 never, 1 always (EB200_WIDE)
     int threads = CASE_THREADS;   // eb_case_kernel: threads per CTA (EB200_THREADS) ...
     int deciders = 0;             // ... of which this many warps run the general per-case program (EB200_DECIDERS; 0 = chosen per batch),
     int tma_workers = 0;          // workers that copy through shared memory with cp.async.bulk (EB200_TMA_WORKERS; A/B, profiles/variants_r2.txt)
@@ -221,13 +227,14 @@ int eb200_init(int device, eb200_ctx** out) {
     }
     if (const char* v = getenv("EB200_CASE_TIMES")) ctx->want_case_times = atoi(v) != 0;
     if (const char* v = getenv("EB200_THREADS")) { int k = atoi(v); if (k >= 64 && k <= CASE_THREADS && k % 32 == 0) ctx->threads = k; }
+    if (const char* v = getenv("EB200_WIDE")) { int k = atoi(v); if (k >= -1 && k <= 1) ctx->wide = k; }
     if (const char* v = getenv("EB200_DECIDERS")) { int k = atoi(v); if (k >= 0 && k <= 32) ctx->deciders = k; }
     if (const char* v = getenv("EB200_TMA_WORKERS")) { int k = atoi(v); if (k >= 0 && k <= 12) ctx->tma_workers = k; }
     if (const char* v = getenv("EB200_FRONT_DEPTH")) { int k = atoi(v); if (k >= 0 && k <= 200) ctx->front_depth = k; }
     if (const char* v = getenv("EB200_FRONTS")) { int k = atoi(v); if (k >= -1 && k <= MAX_FRONTS) ctx->fronts = k; }
     if (ctx->deciders > ctx->threads / 32) ctx->deciders = ctx->threads / 32;
     if (cudaFuncSetAttribute(eb_case_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
-        cudaFuncSetAttribute(eb_case_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess) { delete ctx; return EB200_ERR_CUDA; }
+        cudaFuncSetAttribute(eb_case_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess || eb200_wide_init() != 0) { delete ctx; return EB200_ERR_CUDA; }
     *out = ctx; return EB200_OK;
 }
 
@@ -246,16 +253,16 @@ void eb200_shutdown(eb200_ctx* ctx) {
 // cannot help keep the warps on the general program. Measured on C3 (profiles/variants_r2.txt): fronts 3 / deciders 2
 // 2.55 ms, 2/2 2.65, 4/2 2.58, 1/2 3.10; without fronts 5.3 ms (32 deciders, inline copies) .. 9.6 ms (8 deciders).
 struct Roles { int fronts, deciders; };
-static Roles choose_roles(const eb200_ctx* ctx, const BatchParams& bp, bool fused, uint64_t mean_len) {
+static Roles choose_roles(const eb200_ctx* ctx, const BatchParams& bp, bool fused, uint64_t mean_len, int threads) {
     Roles r;
     double pod = 0, psum = 0, mfast = 0, msum = 0;
     for (int i = 0; i < bp.n_pats; i++) { psum += bp.pat_pri[i]; if (bp.pat_id[i] == P_OD) pod += bp.pat_pri[i]; }
     for (int i = 0; i < bp.n_rows; i++) { double w = bp.row_pri[i] * 5.5; msum += w; if (fast_byte_mut(bp.row_id[i]) || bp.row_id[i] == M_NUM) mfast += w; }
     double share = (psum > 0 && msum > 0 && fused && bp.generator == 0) ? (pod / psum) * (mfast / msum) : 0.0;
-    int warps = ctx->threads / 32;
+    int warps = threads / 32;
     if (share >= 0.5) { r.fronts = 3; r.deciders = 2; }
     else if (share >= 0.02) { r.fronts = 1; r.deciders = warps >= 32 ? 20 : warps / 2; }
-    else { r.fronts = 0; r.deciders = warps >= 32 ? 24 : warps / 2; }
+    else { r.fronts = 0; r.deciders = warps >= 32 ? 24 : warps == 16 ? 12 : warps / 2; }
     // (measured on C2, 4 KiB blocks copied inline by their decider: 24 deciders 1153 ms per step, 32 deciders 1303 ms -- more warps on
     //  the general program only fight over the instruction-miss path)
     (void)mean_len;
@@ -266,9 +273,18 @@ static Roles choose_roles(const eb200_ctx* ctx, const BatchParams& bp, bool fuse
     return r;
 }
 // arenas + launch geometry shared by both modes
-struct LaunchPlan { Arenas ar; int grid; Roles roles; };
+struct LaunchPlan { Arenas ar; int grid; Roles roles; int threads; bool wide; };
 static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_bytes, uint64_t n_launch, bool fused, LaunchPlan& lp) {
-    lp.roles = choose_roles(ctx, bp, fused, bp.n_blobs ? data_bytes / bp.n_blobs : 0);
+    lp.threads = ctx->threads; lp.wide = false;
+    lp.roles = choose_roles(ctx, bp, fused, bp.n_blobs ? data_bytes / bp.n_blobs : 0, lp.threads);
+    // The general program with no front warps: when the launch has only a few cases per deciding warp, its time is the latency
+    // of the slowest cases, not throughput -- run it at 512 threads per CTA, where the program has 128 registers per thread and
+    // stops spilling to a stack that misses L1 (eb_wide.cu). Measured in profiles/variants_r2.txt section 8.
+    if (!batch_is_light(bp) && lp.roles.fronts == 0 && ctx->threads == CASE_THREADS &&
+        (ctx->wide == 1 || (ctx->wide < 0 && n_launch < (uint64_t)ctx->num_sms * lp.roles.deciders * 8))) {
+        lp.wide = true; lp.threads = 512;
+        lp.roles = choose_roles(ctx, bp, fused, bp.n_blobs ? data_bytes / bp.n_blobs : 0, lp.threads);
+    }
     const int deciders = lp.roles.deciders;
     unsigned long long* cnt = (unsigned long long*)ctx->counters.p;
     Arenas& ar = lp.ar;
@@ -301,8 +317,9 @@ static int plan_launch(eb200_ctx* ctx, const BatchParams& bp, uint64_t data_byte
 static void launch_cases(eb200_ctx* ctx, const BatchParams& bp, const LaunchPlan& lp, cudaStream_t st, const uint8_t* d_data, const uint64_t* d_off,
                          uint64_t* d_out_len, eb200_meta* d_meta, const FusedArgs& fa) {
     size_t sm = case_smem(lp.roles.deciders, fa.tma_workers);
-    if (!batch_is_light(bp)) eb_case_kernel<true><<<lp.grid, ctx->threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
-    else eb_case_kernel<false><<<lp.grid, ctx->threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
+    if (lp.wide) eb200_wide_launch(lp.grid, lp.threads, sm, st, d_data, d_off, &bp, &lp.ar, ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, d_meta, &fa);
+    else if (!batch_is_light(bp)) eb_case_kernel<true><<<lp.grid, lp.threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
+    else eb_case_kernel<false><<<lp.grid, lp.threads, sm, st>>>(d_data, d_off, bp, lp.ar, (CaseOut*)ctx->cases.p, d_out_len, (uint64_t*)ctx->sz16.p, (MetaDev*)d_meta, fa);
 }
 
 // decide + scan for a batch resident on the device (two-pass mode). On return *total_out = packed output size.
@@ -781,7 +798,7 @@ uint64_t eb200_debug_case_times(eb200_ctx* ctx, uint32_t* out, uint64_t n) {
     return n;
 }
 // ... and per mutator: out[2 * i] = nanoseconds inside mutator i (table order), out[2 * i + 1] = calls; 41 pairs, then 8 pairs for the
-// phases of the fuse search (table-classified / register-classified / lane-per-node / one-suffix / flat levels; eb_mut_fuse.cuh): 98 entries
+// phases of the fuse search (class tables / registers / packed runs / one-suffix runs / flat levels; eb_mut_fuse.cuh): 98 entries
 int eb200_debug_mutator_times(eb200_ctx* ctx, uint64_t* out) {
     if (!ctx || !ctx->want_case_times || !ctx->case_usec.p) return 0;
     cudaSetDevice(ctx->device);

@@ -18,8 +18,6 @@
 
 namespace eb {
 
-struct FNode { uint32_t fo, fc, to, tc; };
-
 struct FuseSide {
     const uint8_t* s; uint32_t len;
     uint32_t* cnt;     // [256] per-class element count; all zero between nodes
@@ -162,27 +160,14 @@ EB_DEV uint32_t fuse_classify_sm(const uint8_t* s, uint32_t len, const uint32_t*
     return total;
 }
 
-// profiling aid (EB200_CASE_TIMES=1): nanoseconds per phase of fuse_device, slots after the per-mutator table
-enum { FPH_BIG = 0, FPH_MID, FPH_SMALL, FPH_TINY, FPH_COMPACT, FPH_COUNT };
-struct FuseClock {
-    unsigned long long* tab; unsigned long long t0;
-    __device__ __forceinline__ void start() { if (tab) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0)); }
-    __device__ __forceinline__ void stop(int ph) {
-        if (!tab) return;
-        unsigned long long t1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        if (lane_id() == 0) { atomicAdd(&tab[2 * ph], t1 - t0); atomicAdd(&tab[2 * ph + 1], 1ull); }
-    }
-};
-
-// ---- one node of at most FUSE_MID suffixes per side, whole warp, first bytes held in registers (see fuse_device, path 2a).
+// ---- one node of at most FUSE_MID suffixes per side, whole warp, first bytes held in registers (fuse_mid, path 2a of fuse_step).
 // Slot r of lane l holds list element r * 32 + l (arrival order). Encoding of a first byte: 0..255 live; 0x1ff the [] suffix
 // (contributes nothing); byte | 0x400 the suffix holding only the block's last byte when it is the FIRST of its class -- the
 // class exists, the element is not placed ([[]] -> [], :68-70). Classes of A are taken in ascending byte order by a min
 // reduction; inside a class the LAST arrival comes first (char_suffixes prepends). No tables, no memory traffic but the
 // two position lists and their first bytes.
-constexpr uint32_t FUSE_MID = 256;
-constexpr int FUSE_MID_SLOTS = 8;
-struct FuseOut { uint32_t* F; uint32_t* T; FNode* ND; uint32_t fcap, tcap, ncap; };
+constexpr uint32_t FUSE_MID = 128;
+constexpr int FUSE_MID_SLOTS = 4;
 // positions of one list and where its special suffix (position len - 1; positions of a list are distinct, so at most one) sits
 __device__ __forceinline__ void fuse_mid_pos(const uint32_t* src, uint32_t k, uint32_t len, uint32_t (&pos)[FUSE_MID_SLOTS], int& rs, uint32_t& ls) {
     const int l = lane_id();
@@ -213,9 +198,19 @@ __device__ __forceinline__ void fuse_mid_drop(uint32_t (&cls)[FUSE_MID_SLOTS], i
         for (int r = 0; r < FUSE_MID_SLOTS; r++) if (r == rs) cls[r] = cs | 0x400u;
     }
 }
-__device__ __forceinline__ bool fuse_mid(const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb, const uint32_t* srcA, uint32_t kA, const uint32_t* srcB, uint32_t kB,
-                                         const FuseOut& o, uint32_t& fo, uint32_t& to, uint32_t& nnext, uint32_t& maxsz) {
+
+// Every node path below is its own function working on the search state in SHARED memory (FuseSh in the warp's WarpState):
+// the per-case program's stack does not fit the L1 next to 24 other warps', so a spilled register or a by-reference local
+// is an L2 round trip; shared memory is not. Each path reads what it needs, writes the next level's counters back.
+
+// (2a) one node of up to FUSE_MID suffixes per side
+EB_DEV bool fuse_mid(FuseSh* s, uint32_t sfo, uint32_t kA, uint32_t sto, uint32_t kB) {
     const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
+    const int cur = s->cur, nx = cur ^ 1;
+    const uint8_t* a = s->a; const uint8_t* b = s->b; const uint32_t na = s->na, nb = s->nb;
+    const uint32_t* srcA = s->F[cur] + sfo; const uint32_t* srcB = s->T[cur] + sto;
+    uint32_t* Fn = s->F[nx]; uint32_t* Tn = s->T[nx]; FNode* NDn = s->ND[nx];
+    uint32_t fo = s->fo, to = s->to, nnext = s->nnext, maxsz = s->maxsz;
     uint32_t ca[FUSE_MID_SLOTS], cb[FUSE_MID_SLOTS];
     {
         uint32_t pa[FUSE_MID_SLOTS], pb[FUSE_MID_SLOTS]; int rsa, rsb; uint32_t lsa, lsb;
@@ -244,21 +239,21 @@ __device__ __forceinline__ bool fuse_mid(const uint8_t* a, uint32_t na, const ui
         for (int r = 0; r < FUSE_MID_SLOTS; r++) { if (r < nsb) { nb_l += cb[r] == ch ? 1u : 0u; eb_l |= (cb[r] & 0x3ffu) == ch ? 1u : 0u; } }
         const uint32_t totA = __reduce_add_sync(0xffffffffu, na_l);
         if (totA == 0) {                 // {_Char, []} -> [[[]], []]: the two empty suffixes, whatever B holds (:91-93)
-            if (fo + 1 > o.fcap || to + 1 > o.tcap || nnext >= o.ncap) return false;
-            if (l == 0) { o.F[fo] = na; o.T[to] = nb; FNode q; q.fo = fo; q.fc = 1; q.to = to; q.tc = 1; o.ND[nnext] = q; }
+            if (fo + 1 > s->fcap || to + 1 > s->tcap || nnext >= s->ncap) return false;
+            if (l == 0) { Fn[fo] = na; Tn[to] = nb; FNode q; q.fo = fo; q.fc = 1; q.to = to; q.tc = 1; NDn[nnext] = q; }
             fo++; to++; nnext++;
             maxsz = max(maxsz, 1u);
             continue;
         }
         if (!__any_sync(0xffffffffu, eb_l != 0)) continue;                  // notfound
         const uint32_t totB = __reduce_add_sync(0xffffffffu, nb_l);
-        if ((uint64_t)fo + totA > o.fcap || (uint64_t)to + totB > o.tcap || nnext >= o.ncap) return false;
+        if ((uint64_t)fo + totA > s->fcap || (uint64_t)to + totB > s->tcap || nnext >= s->ncap) return false;
         uint32_t run = 0;
 #pragma unroll
         for (int r = 0; r < FUSE_MID_SLOTS; r++) {
             if (r < nsa) {
                 bool e = ca[r] == ch; uint32_t mb = __ballot_sync(0xffffffffu, e);
-                if (e) o.F[fo + totA - 1 - (run + (uint32_t)__popc(mb & ltm))] = srcA[(uint32_t)r * 32 + (uint32_t)l] + 1;
+                if (e) Fn[fo + totA - 1 - (run + (uint32_t)__popc(mb & ltm))] = srcA[(uint32_t)r * 32 + (uint32_t)l] + 1;
                 run += (uint32_t)__popc(mb);
             }
         }
@@ -267,29 +262,32 @@ __device__ __forceinline__ bool fuse_mid(const uint8_t* a, uint32_t na, const ui
         for (int r = 0; r < FUSE_MID_SLOTS; r++) {
             if (r < nsb) {
                 bool e = cb[r] == ch; uint32_t mb = __ballot_sync(0xffffffffu, e);
-                if (e) o.T[to + totB - 1 - (run + (uint32_t)__popc(mb & ltm))] = srcB[(uint32_t)r * 32 + (uint32_t)l] + 1;
+                if (e) Tn[to + totB - 1 - (run + (uint32_t)__popc(mb & ltm))] = srcB[(uint32_t)r * 32 + (uint32_t)l] + 1;
                 run += (uint32_t)__popc(mb);
             }
         }
-        if (l == 0) { FNode q; q.fo = fo; q.fc = totA; q.to = to; q.tc = totB; o.ND[nnext] = q; }
+        if (l == 0) { FNode q; q.fo = fo; q.fc = totA; q.to = to; q.tc = totB; NDn[nnext] = q; }
         nnext++; fo += totA; to += totB;
         maxsz = max(maxsz, max(totA, totB));
     }
     __syncwarp();
+    if (l == 0) { s->fo = fo; s->to = to; s->nnext = nnext; s->maxsz = maxsz; }
+    __syncwarp();
     return true;
 }
 
-// ---- several consecutive nodes whose lists together hold at most 32 suffixes per side (see fuse_device, path 1): lane j holds the
-// j-th source suffix and the j-th target suffix of the run, lists back to back in the order the nodes are processed. A child is a
-// (node, first byte) group: key = node << 9 | byte. match.any gives every lane its group, its size and its arrival rank; one
-// all-pairs sweep over the 32 lanes (shuffles, no memory) gives how many placed suffixes / target suffixes / children sort before
-// the group. Same rules as everywhere: classes ascending inside a node, the last arrival first inside a class, the suffix holding
-// only the block's last byte dropped when it is the first of its class, a class left empty by that turned into [[[]], []].
-// G = number of nodes taken (>= 1), ia / ib = inclusive prefix sums of the nodes' list lengths (lane i = i-th node).
-__device__ __forceinline__ bool fuse_packed(const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb, const uint32_t* Fc, const uint32_t* Tc,
-                                            const FNode& nd, uint32_t ia, uint32_t ib, uint32_t G,
-                                            const FuseOut& o, uint32_t& fo, uint32_t& to, uint32_t& nnext, uint32_t& maxsz) {
+// (1) several consecutive nodes whose lists together hold at most 32 suffixes per side: lane j holds the j-th source suffix and the
+// j-th target suffix of the run, lists back to back in the order the nodes are processed. A child is a (node, first byte) group:
+// key = node << 9 | byte. match.any gives every lane its group, its size and its arrival rank; one all-pairs sweep over the 32
+// lanes (shuffles, no memory) gives how many placed suffixes / target suffixes sort before the group. Same rules as everywhere:
+// classes ascending inside a node, the last arrival first inside a class, the suffix holding only the block's last byte dropped
+// when it is the first of its class, a class left empty by that turned into [[[]], []].
+// nfo/nfc/nto/ntc = this lane's node (lane i = i-th node from the top), ia / ib = inclusive prefix sums of the list lengths,
+// G = number of nodes taken (>= 1).
+EB_DEV bool fuse_packed(FuseSh* s, uint32_t nfo, uint32_t nfc, uint32_t nto, uint32_t ntc, uint32_t ia, uint32_t ib, uint32_t G) {
     const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u; const uint32_t j = (uint32_t)l;
+    const int cur = s->cur, nx = cur ^ 1;
+    const uint32_t na = s->na, nb = s->nb;
     const uint32_t totA = __shfl_sync(0xffffffffu, ia, (int)G - 1), totB = __shfl_sync(0xffffffffu, ib, (int)G - 1);
     // which node does suffix j belong to: the first node whose inclusive sum exceeds j
     int loa = 0, hia = (int)G - 1, lob = 0, hib = (int)G - 1;
@@ -300,14 +298,14 @@ __device__ __forceinline__ bool fuse_packed(const uint8_t* a, uint32_t na, const
         if (loa < hia) { if (va > j) hia = ma; else loa = ma + 1; }
         if (lob < hib) { if (vb > j) hib = mb; else lob = mb + 1; }
     }
-    const uint32_t exa = __shfl_sync(0xffffffffu, ia - nd.fc, loa), foa = __shfl_sync(0xffffffffu, nd.fo, loa);
-    const uint32_t exb = __shfl_sync(0xffffffffu, ib - nd.tc, lob), tob = __shfl_sync(0xffffffffu, nd.to, lob);
+    const uint32_t exa = __shfl_sync(0xffffffffu, ia - nfc, loa), foa = __shfl_sync(0xffffffffu, nfo, loa);
+    const uint32_t exb = __shfl_sync(0xffffffffu, ib - ntc, lob), tob = __shfl_sync(0xffffffffu, nto, lob);
     uint32_t pa = FUSE_NONE, pb = FUSE_NONE;
-    if (j < totA) pa = Fc[foa + (j - exa)];
-    if (j < totB) pb = Tc[tob + (j - exb)];
+    if (j < totA) pa = s->F[cur][foa + (j - exa)];
+    if (j < totB) pb = s->T[cur][tob + (j - exb)];
     const bool la = pa < na, lb = pb < nb;                                   // NONE and the [] suffix contribute nothing
-    const uint32_t ka = la ? ((uint32_t)loa << 9) | (uint32_t)a[pa] : 0x80000000u | j;
-    const uint32_t kb = lb ? ((uint32_t)lob << 9) | (uint32_t)b[pb] : 0xc0000000u | j;
+    const uint32_t ka = la ? ((uint32_t)loa << 9) | (uint32_t)s->a[pa] : 0x80000000u | j;
+    const uint32_t kb = lb ? ((uint32_t)lob << 9) | (uint32_t)s->b[pb] : 0xc0000000u | j;
     const uint32_t ga = __match_any_sync(0xffffffffu, ka), gb = __match_any_sync(0xffffffffu, kb);
     const bool firsta = la && (ga & ltm) == 0, firstb = lb && (gb & ltm) == 0;
     const bool placeda = la && !(firsta && pa + 1 == na), placedb = lb && !(firstb && pb + 1 == nb);
@@ -315,8 +313,9 @@ __device__ __forceinline__ bool fuse_packed(const uint8_t* a, uint32_t na, const
     const uint32_t sza = (uint32_t)__popc(ga & pma), rka = (uint32_t)__popc(ga & pma & ltm);
     const uint32_t szb = (uint32_t)__popc(gb & pmb), rkb = (uint32_t)__popc(gb & pmb & ltm);
     uint32_t lessAA = 0, lessBA = 0, eqBA = 0, existsBA = 0, lessBB = 0;
-#pragma unroll 8
-    for (int t = 0; t < 32; t++) {
+    const int span = (int)max(totA, totB);
+#pragma unroll 4
+    for (int t = 0; t < span; t++) {
         uint32_t xa = __shfl_sync(0xffffffffu, ka, t), xb = __shfl_sync(0xffffffffu, kb, t);
         uint32_t pla = (pma >> t) & 1u, plb = (pmb >> t) & 1u;
         lessAA += (xa < ka) ? pla : 0u;
@@ -330,236 +329,289 @@ __device__ __forceinline__ bool fuse_packed(const uint8_t* a, uint32_t na, const
     const bool emit = firsta && (sza == 0 || existsBA);
     const uint32_t em = __ballot_sync(0xffffffffu, emit), qm = __ballot_sync(0xffffffffu, quirk);
     const uint32_t nq = (uint32_t)__popc(qm), nch = (uint32_t)__popc(em);
-    if ((uint64_t)fo + nplA + nq > o.fcap || (uint64_t)to + nplB + nq > o.tcap || (uint64_t)nnext + nch > o.ncap) return false;
+    const uint32_t fo = s->fo, to = s->to, nnext = s->nnext;
+    if ((uint64_t)fo + nplA + nq > s->fcap || (uint64_t)to + nplB + nq > s->tcap || (uint64_t)nnext + nch > s->ncap) return false;
     uint32_t cidx = 0;                                                       // children with a smaller key come first
     for (uint32_t mm = em; mm;) { int t = __ffs(mm) - 1; mm &= mm - 1; uint32_t xk = __shfl_sync(0xffffffffu, ka, t); cidx += (xk < ka) ? 1u : 0u; }
-    if (placeda) o.F[fo + lessAA + sza - 1 - rka] = pa + 1;
-    if (placedb) o.T[to + lessBB + szb - 1 - rkb] = pb + 1;
+    uint32_t* Fn = s->F[nx]; uint32_t* Tn = s->T[nx];
+    if (placeda) Fn[fo + lessAA + sza - 1 - rka] = pa + 1;
+    if (placedb) Tn[to + lessBB + szb - 1 - rkb] = pb + 1;
     uint32_t big = 0;
     if (emit) {
         FNode q;
         if (quirk) {
             uint32_t qi = (uint32_t)__popc(qm & ltm);
-            o.F[fo + nplA + qi] = na; o.T[to + nplB + qi] = nb;
+            Fn[fo + nplA + qi] = na; Tn[to + nplB + qi] = nb;
             q.fo = fo + nplA + qi; q.fc = 1; q.to = to + nplB + qi; q.tc = 1; big = 1;
         } else { q.fo = fo + lessAA; q.fc = sza; q.to = to + lessBA; q.tc = eqBA; big = max(sza, eqBA); }
-        o.ND[nnext + cidx] = q;
+        s->ND[nx][nnext + cidx] = q;
     }
-    maxsz = max(maxsz, __reduce_max_sync(0xffffffffu, big));
-    fo += nplA + nq; to += nplB + nq; nnext += nch;
+    big = __reduce_max_sync(0xffffffffu, big);
+    __syncwarp();
+    if (l == 0) { s->fo = fo + nplA + nq; s->to = to + nplB + nq; s->nnext = nnext + nch; s->maxsz = max(s->maxsz, big); }
     __syncwarp();
     return true;
+}
+
+// (0) a run of TINY nodes (at most one suffix per side), one node per lane: the rules written out for one-element lists
+EB_DEV bool fuse_tiny(FuseSh* s, uint32_t nfo, uint32_t nfc, uint32_t nto, uint32_t ntc, uint32_t tinyrun) {
+    const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
+    const int cur = s->cur, nx = cur ^ 1;
+    const uint32_t na = s->na, nb = s->nb;
+    const bool act = (uint32_t)l < tinyrun;
+    uint32_t pa = FUSE_NONE, pb = FUSE_NONE;
+    if (act && nfc) pa = s->F[cur][nfo];
+    if (act && ntc) pb = s->T[cur][nto];
+    const bool ha = pa < na, hb = pb < nb;                       // NONE and the [] suffix contribute nothing
+    const uint32_t cha = ha ? s->a[pa] : 0x100u, chb = hb ? s->b[pb] : 0x200u;
+    bool child = false; uint32_t ca = 0, cb = 0, tcn = 1;
+    if (ha && pa + 1 == na) { child = true; ca = na; cb = nb; }                    // {_Char, []} -> [[[]], []] (:91-93)
+    else if (cha == chb) { child = true; ca = pa + 1; cb = pb + 1; if (pb + 1 == nb) tcn = 0; }
+    const uint32_t cm = __ballot_sync(0xffffffffu, child);
+    const uint32_t cn = (uint32_t)__popc(cm);
+    const uint32_t fo = s->fo, to = s->to, nnext = s->nnext;
+    if ((uint64_t)fo + cn > s->fcap || (uint64_t)to + cn > s->tcap || (uint64_t)nnext + cn > s->ncap) return false;
+    if (child) {
+        uint32_t at = (uint32_t)__popc(cm & ltm);
+        s->F[nx][fo + at] = ca; s->T[nx][to + at] = cb;
+        FNode q; q.fo = fo + at; q.fc = 1; q.to = to + at; q.tc = tcn; s->ND[nx][nnext + at] = q;
+    }
+    __syncwarp();
+    if (l == 0) { s->fo = fo + cn; s->to = to + cn; s->nnext = nnext + cn; if (cn) s->maxsz = max(s->maxsz, 1u); }
+    __syncwarp();
+    return true;
+}
+
+// (2b) a node with longer lists, counters in shared memory (fuse_classify_sm), then the children taken eight classes per lane;
+// (2c) lists of 65 535 suffixes and more: the same through counters in global memory (fuse_classify)
+EB_DEV bool fuse_tables(FuseSh* s, uint16_t* sc, uint32_t sfo, uint32_t kA, uint32_t sto, uint32_t kB) {
+    const int l = lane_id();
+    const int cur = s->cur, nx = cur ^ 1;
+    const uint32_t na = s->na, nb = s->nb;
+    uint32_t* tabs = s->tabs;
+    uint32_t* startA = tabs + 256; uint32_t* startB = tabs + 768; uint32_t* sizeA = tabs + 1024; uint32_t* sizeB = tabs + 1280;
+    uint32_t fo = s->fo, to = s->to, nnext = s->nnext, maxsz = s->maxsz;
+    if (kA < 65535u && kB < 65535u) {
+        uint32_t ma, mb;
+        const uint32_t fa2 = fuse_classify_sm(s->a, na, s->F[cur] + sfo, kA, s->F[nx], fo, sc, startA, sizeA, ma);
+        const uint32_t tb2 = fuse_classify_sm(s->b, nb, s->T[cur] + sto, kB, s->T[nx], to, sc, startB, sizeB, mb);
+        uint32_t szs[8]; uint32_t nch_l = 0, nq_l = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            szs[i] = 0xffffffffu;                                                     // no child
+            if ((ma >> i) & 1u) {
+                uint32_t sz = sizeA[8 * l + i];
+                if (sz == 0) { szs[i] = 0; nch_l++; nq_l++; }                         // {_Char, []} -> [[[]], []] (:91-93)
+                else if ((mb >> i) & 1u) { szs[i] = sz; nch_l++; }                    // else notfound
+            }
+        }
+        uint32_t cpre = nch_l, qpre = nq_l;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            uint32_t x = __shfl_up_sync(0xffffffffu, cpre, o2), y = __shfl_up_sync(0xffffffffu, qpre, o2);
+            if (l >= o2) { cpre += x; qpre += y; }
+        }
+        const uint32_t ctot = __shfl_sync(0xffffffffu, cpre, 31), qtot = __shfl_sync(0xffffffffu, qpre, 31);
+        if ((uint64_t)fo + fa2 + qtot > s->fcap || (uint64_t)to + tb2 + qtot > s->tcap || (uint64_t)nnext + ctot > s->ncap) return false;
+        uint32_t ci = nnext + cpre - nch_l, qi = qpre - nq_l, big = 0;
+        uint32_t* Fn = s->F[nx]; uint32_t* Tn = s->T[nx]; FNode* NDn = s->ND[nx];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (szs[i] == 0xffffffffu) continue;
+            FNode q; uint32_t ch = 8u * (uint32_t)l + (uint32_t)i;
+            if (szs[i] == 0) {
+                Fn[fo + fa2 + qi] = na; Tn[to + tb2 + qi] = nb;
+                q.fo = fo + fa2 + qi; q.fc = 1; q.to = to + tb2 + qi; q.tc = 1; qi++; big = max(big, 1u);
+            } else { q.fo = startA[ch]; q.fc = szs[i]; q.to = startB[ch]; q.tc = sizeB[ch]; big = max(big, max(q.fc, q.tc)); }
+            NDn[ci++] = q;
+        }
+        big = __reduce_max_sync(0xffffffffu, big);
+        __syncwarp();
+        if (l == 0) { s->fo = fo + fa2 + qtot; s->to = to + tb2 + qtot; s->nnext = nnext + ctot; s->maxsz = max(maxsz, big); }
+        __syncwarp();
+        return true;
+    }
+    FuseSide sa, sb; sa.s = s->a; sa.len = na; sa.cnt = tabs; sa.start = startA; sb.s = s->b; sb.len = nb; sb.cnt = tabs + 512; sb.start = startB;
+    uint32_t* Fn = s->F[nx]; uint32_t* Tn = s->T[nx]; FNode* NDn = s->ND[nx];
+    uint32_t fa = fuse_classify(sa, s->F[cur] + sfo, kA, Fn, fo, sizeA);
+    uint32_t tb = fuse_classify(sb, s->T[cur] + sto, kB, Tn, to, sizeB);
+    for (int w = 0; w < 8; w++) {
+        uint32_t m = sa.bits[w];
+        while (m) {
+            uint32_t bit = (uint32_t)__ffs(m) - 1; m &= m - 1; uint32_t ch = (uint32_t)w * 32 + bit;
+            FNode ch_n;
+            if (sizeA[ch] == 0) {       // {_Char, []} -> [[[]], []]: the two empty suffixes, whatever B holds (:91-93)
+                if (fo + fa + 1 > s->fcap || to + tb + 1 > s->tcap || nnext >= s->ncap) return false;
+                if (l == 0) { Fn[fo + fa] = na; Tn[to + tb] = nb; }
+                ch_n.fo = fo + fa; ch_n.fc = 1; ch_n.to = to + tb; ch_n.tc = 1; fa++; tb++;
+                if (l == 0) NDn[nnext] = ch_n;
+                nnext++; continue;
+            }
+            if (!((sb.bits[w] >> bit) & 1u)) continue;                     // notfound
+            if (nnext >= s->ncap) return false;
+            ch_n.fo = sa.start[ch]; ch_n.fc = sizeA[ch]; ch_n.to = sb.start[ch]; ch_n.tc = sizeB[ch];
+            if (l == 0) NDn[nnext] = ch_n;
+            nnext++;
+            maxsz = max(maxsz, max(ch_n.fc, ch_n.tc));
+        }
+    }
+    __syncwarp();
+    if (l == 0) { s->fo = fo + fa; s->to = to + tb; s->nnext = nnext; s->maxsz = maxsz; }
+    __syncwarp();
+    return true;
+}
+
+// one flat level (every node at most 1 x 1, and so all their descendants): two position arrays PA[k] / PB[k] = the node's source /
+// target position (NONE = no suffix), kept in the F / T ping-pong buffers; a step reads 32 nodes with two coalesced loads and
+// two byte gathers, nothing depends on the previous step but the output offset. Returns the number of children.
+EB_DEV uint32_t fuse_flat_level(FuseSh* s) {
+    const int cur = s->cur, nx = cur ^ 1;
+    const uint32_t* PA = s->F[cur]; const uint32_t* PB = s->T[cur]; uint32_t* QA = s->F[nx]; uint32_t* QB = s->T[nx];
+    const uint8_t* a = s->a; const uint8_t* b = s->b; const uint32_t na = s->na, nb = s->nb;
+    const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
+    uint32_t nnext = 0;
+    for (uint32_t e = s->ncur; e > 0;) {
+        uint32_t take = e < 32 ? e : 32;
+        bool act = (uint32_t)l < take;
+        uint32_t pa = FUSE_NONE, pb = FUSE_NONE;
+        if (act) { pa = PA[e - 1 - (uint32_t)l]; pb = PB[e - 1 - (uint32_t)l]; }
+        bool ha = pa != FUSE_NONE && pa < na, hb = pb != FUSE_NONE && pb < nb;
+        uint32_t cha = ha ? a[pa] : 0x100u, chb = hb ? b[pb] : 0x200u;
+        bool a_drop = ha && pa + 1 == na, b_drop = hb && pb + 1 == nb;
+        bool child = false; uint32_t ca = FUSE_NONE, cb = FUSE_NONE;
+        if (a_drop) { child = true; ca = na; cb = nb; }                                   // {_Char, []} -> [[[]], []] (:91-93)
+        else if (ha && cha == chb) { child = true; ca = pa + 1; cb = b_drop ? FUSE_NONE : pb + 1; }
+        uint32_t cm = __ballot_sync(0xffffffffu, child);
+        if (child) { uint32_t at = nnext + (uint32_t)__popc(cm & ltm); QA[at] = ca; QB[at] = cb; }
+        nnext += (uint32_t)__popc(cm);
+        e -= take;
+    }
+    __syncwarp();
+    return nnext;
+}
+
+// one step of a general level: lane i looks at the i-th node from the top of the list and the run goes to the path that fits.
+// What a level looks like after the first split or two (profiles/tc_c2_r2d.txt, tc_c5_r2d.txt): nine nodes in ten hold one suffix
+// per side, most of the rest a handful, a few dozen hold 25-250 (a phrase or a period repeated in the block), and the root and
+// its first children thousands.
+EB_DEV bool fuse_step(FuseSh* s, uint16_t* sc) {
+    const int l = lane_id();
+    const uint32_t e = s->e;
+    const bool valid = (uint32_t)l < e;
+    FNode nd; nd.fo = nd.to = 0; nd.fc = nd.tc = 64;
+    if (valid) nd = s->ND[s->cur][e - 1 - (uint32_t)l];
+    FuseClock clk; clk.tab = s->clk; clk.t0 = 0;
+    const uint32_t tm = __ballot_sync(0xffffffffu, valid && nd.fc <= 1 && nd.tc <= 1);
+    const uint32_t tinyrun = tm == 0xffffffffu ? 32u : (uint32_t)__ffs(~tm) - 1u;
+    if (tinyrun >= 16 || (tinyrun > 0 && tinyrun == e)) {
+        clk.start();
+        if (!fuse_tiny(s, nd.fo, nd.fc, nd.to, nd.tc, tinyrun)) return false;
+        if (l == 0) s->e = e - tinyrun;
+        __syncwarp();
+        clk.stop(FPH_TINY);
+        return true;
+    }
+    uint32_t ia = min(nd.fc, 64u), ib = min(nd.tc, 64u);
+#pragma unroll
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        uint32_t x = __shfl_up_sync(0xffffffffu, ia, o2), y = __shfl_up_sync(0xffffffffu, ib, o2);
+        if (l >= o2) { ia += x; ib += y; }
+    }
+    const uint32_t okm = __ballot_sync(0xffffffffu, valid && ia <= 32 && ib <= 32);
+    const uint32_t G = okm == 0xffffffffu ? 32u : (uint32_t)__ffs(~okm) - 1u;
+    if (G > 0) {
+        clk.start();
+        if (!fuse_packed(s, nd.fo, nd.fc, nd.to, nd.tc, ia, ib, G)) return false;
+        if (l == 0) s->e = e - G;
+        __syncwarp();
+        clk.stop(FPH_SMALL);
+        return true;
+    }
+    const uint32_t tfo = __shfl_sync(0xffffffffu, nd.fo, 0), tfc = __shfl_sync(0xffffffffu, nd.fc, 0);
+    const uint32_t tto = __shfl_sync(0xffffffffu, nd.to, 0), ttc = __shfl_sync(0xffffffffu, nd.tc, 0);
+    clk.start();
+    bool ok;
+    const bool midp = tfc <= FUSE_MID && ttc <= FUSE_MID;
+    if (midp) ok = fuse_mid(s, tfo, tfc, tto, ttc);
+    else ok = fuse_tables(s, sc, tfo, tfc, tto, ttc);
+    if (l == 0) s->e = e - 1;
+    __syncwarp();
+    clk.stop(midp ? FPH_MID : FPH_BIG);
+    return ok;
 }
 
 // find_jump_points/2 :103-128 + any_position_pair/1 :73-77
 EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb, uint32_t& from, uint32_t& to) {
     Rng& g = c.rng;
-    uint64_t fcap = (uint64_t)na + 80, tcap = (uint64_t)nb + 80, ncap = (uint64_t)(na < nb ? na : nb) + 80;
-    uint32_t* F[2]; uint32_t* T[2]; FNode* ND[2];
-    for (int i = 0; i < 2; i++) { F[i] = (uint32_t*)temp_alloc(c, fcap * 4); T[i] = (uint32_t*)temp_alloc(c, tcap * 4); ND[i] = (FNode*)temp_alloc(c, ncap * sizeof(FNode)); }
-    uint32_t* tabs = (uint32_t*)temp_alloc(c, 6 * 256 * 4);
-    if (!F[0] || !F[1] || !T[0] || !T[1] || !ND[0] || !ND[1] || !tabs) return false;
-    FuseSide sa, sb; sa.s = a; sa.len = na; sa.cnt = tabs; sa.start = tabs + 256; sb.s = b; sb.len = nb; sb.cnt = tabs + 512; sb.start = tabs + 768;
-    uint32_t* sizeA = tabs + 1024; uint32_t* sizeB = tabs + 1280;
-    for (uint32_t i = lane_id(); i < 256; i += 32) { sa.cnt[i] = 0; sb.cnt[i] = 0; }
-    for (uint32_t i = lane_id(); i < na; i += 32) F[0][i] = i;
-    for (uint32_t i = lane_id(); i < nb; i += 32) T[0][i] = i;
-    __syncwarp();
-    int cur = 0; uint32_t ncur = 1;
-    { FNode r0; r0.fo = 0; r0.fc = na; r0.to = 0; r0.tc = nb; ND[0][0] = r0; }
+    FuseSh* s = &c.ws->fsh;
+    const uint64_t fcap = (uint64_t)na + 80, tcap = (uint64_t)nb + 80, ncap = (uint64_t)(na < nb ? na : nb) + 80;
+    {
+        uint32_t* F[2]; uint32_t* T[2]; FNode* ND[2];
+        for (int i = 0; i < 2; i++) { F[i] = (uint32_t*)temp_alloc(c, fcap * 4); T[i] = (uint32_t*)temp_alloc(c, tcap * 4); ND[i] = (FNode*)temp_alloc(c, ncap * sizeof(FNode)); }
+        uint32_t* tabs = (uint32_t*)temp_alloc(c, 6 * 256 * 4);
+        if (!F[0] || !F[1] || !T[0] || !T[1] || !ND[0] || !ND[1] || !tabs) return false;
+        for (uint32_t i = lane_id(); i < 256; i += 32) { tabs[i] = 0; tabs[512 + i] = 0; }      // the global class counters rest at zero
+        for (uint32_t i = lane_id(); i < na; i += 32) F[0][i] = i;
+        for (uint32_t i = lane_id(); i < nb; i += 32) T[0][i] = i;
+        __syncwarp();
+        if (lane_id() == 0) {
+            s->a = a; s->b = b; s->na = na; s->nb = nb;
+            for (int i = 0; i < 2; i++) { s->F[i] = F[i]; s->T[i] = T[i]; s->ND[i] = ND[i]; }
+            s->fcap = (uint32_t)fcap; s->tcap = (uint32_t)tcap; s->ncap = (uint32_t)ncap; s->tabs = tabs;
+            s->cur = 0; s->ncur = 1;
+            s->clk = c.ar.mut_ns ? c.ar.mut_ns + 2 * M_COUNT : nullptr;
+            FNode r0; r0.fo = 0; r0.fc = na; r0.to = 0; r0.tc = nb; ND[0][0] = r0;
+        }
+        __syncwarp();
+    }
     int64_t fuel = 100000;
     bool compact = false;
-    FuseClock clk; clk.tab = c.ar.mut_ns ? c.ar.mut_ns + 2 * M_COUNT : nullptr; clk.t0 = 0;
     for (;;) {
         bool stop = fuel < 0;
         if (!stop) stop = g.rand(8) == 0;
-        uint32_t nnext = 0;
         if (!stop && compact) {
-            // ---- every node of this level holds at most one suffix per side (and so will all their descendants): the level is
-            // two flat arrays, PA[k] / PB[k] = the node's source / target position (NONE = no suffix), kept in the F / T ping-pong
-            // buffers; a step reads 32 nodes with two coalesced loads and two byte gathers, nothing depends on the previous step
-            // but the output offset. Same rules as the general path written out for one-element lists.
-            const int nx = cur ^ 1;
-            clk.start();
-            const uint32_t* PA = F[cur]; const uint32_t* PB = T[cur]; uint32_t* QA = F[nx]; uint32_t* QB = T[nx];
-            const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
-            for (uint32_t e = ncur; e > 0;) {
-                uint32_t take = e < 32 ? e : 32;
-                bool act = (uint32_t)l < take;
-                uint32_t pa = FUSE_NONE, pb = FUSE_NONE;
-                if (act) { pa = PA[e - 1 - (uint32_t)l]; pb = PB[e - 1 - (uint32_t)l]; }
-                bool ha = pa != FUSE_NONE && pa < na, hb = pb != FUSE_NONE && pb < nb;
-                uint32_t cha = ha ? a[pa] : 0x100u, chb = hb ? b[pb] : 0x200u;
-                bool a_drop = ha && pa + 1 == na, b_drop = hb && pb + 1 == nb;
-                bool child = false; uint32_t ca = FUSE_NONE, cb = FUSE_NONE;
-                if (a_drop) { child = true; ca = na; cb = nb; }                                   // {_Char, []} -> [[[]], []] (:91-93)
-                else if (ha && cha == chb) { child = true; ca = pa + 1; cb = b_drop ? FUSE_NONE : pb + 1; }
-                uint32_t cm = __ballot_sync(0xffffffffu, child);
-                if (child) { uint32_t at = nnext + (uint32_t)__popc(cm & ltm); QA[at] = ca; QB[at] = cb; }
-                nnext += (uint32_t)__popc(cm);
-                e -= take;
-            }
-            __syncwarp();
+            FuseClock clk; clk.tab = s->clk; clk.t0 = 0; clk.start();
+            const uint32_t nnext = fuse_flat_level(s);
             clk.stop(FPH_COMPACT);
             if (nnext == 0) stop = true;
-            else { fuel -= (int64_t)nnext; cur = nx; ncur = nnext; continue; }
+            else { fuel -= (int64_t)nnext; if (lane_id() == 0) { s->cur ^= 1; s->ncur = nnext; } __syncwarp(); continue; }
         }
         if (!stop) {
-            const int nx = cur ^ 1; uint32_t fo = 0, to = 0;
-            uint32_t maxsz = 0;                                              // largest suffix list among the children of this level
-            // nodes are stored in emission order; the reference's list is that order reversed
-            uint32_t e = ncur;
-            const int l = lane_id(); const uint32_t ltm = (1u << l) - 1u;
-            FuseOut o; o.F = F[nx]; o.T = T[nx]; o.ND = ND[nx]; o.fcap = (uint32_t)fcap; o.tcap = (uint32_t)tcap; o.ncap = (uint32_t)ncap;
-            while (e > 0) {
-                // Lane i looks at the i-th node from the top of the list. What the level looks like after the first split or two
-                // (profiles/tc_c2_r2d.txt, tc_c5_r2d.txt): nine nodes in ten hold one suffix per side, most of the rest a handful,
-                // a few dozen hold 25-250 (a phrase or a period repeated in the block), and the root and its first children thousands.
-                const bool valid = (uint32_t)l < e;
-                FNode nd; nd.fo = nd.to = 0; nd.fc = nd.tc = 64;
-                if (valid) nd = ND[cur][e - 1 - (uint32_t)l];
-                // (0) a run of TINY nodes (at most one suffix per side): the rules written out for one-element lists, one node per
-                //     lane, a handful of instructions.
-                const uint32_t tm = __ballot_sync(0xffffffffu, valid && nd.fc <= 1 && nd.tc <= 1);
-                const uint32_t tinyrun = tm == 0xffffffffu ? 32u : (uint32_t)__ffs(~tm) - 1u;
-                if (tinyrun >= 16 || (tinyrun > 0 && tinyrun == e)) {
-                    clk.start();
-                    bool act = (uint32_t)l < tinyrun;
-                    uint32_t pa = FUSE_NONE, pb = FUSE_NONE;
-                    if (act && nd.fc) pa = F[cur][nd.fo];
-                    if (act && nd.tc) pb = T[cur][nd.to];
-                    bool ha = pa < na, hb = pb < nb;                       // NONE and the [] suffix contribute nothing
-                    uint32_t cha = ha ? a[pa] : 0x100u, chb = hb ? b[pb] : 0x200u;
-                    bool child = false; uint32_t ca = 0, cb = 0, tcn = 1;
-                    if (ha && pa + 1 == na) { child = true; ca = na; cb = nb; }                    // {_Char, []} -> [[[]], []] (:91-93)
-                    else if (cha == chb) { child = true; ca = pa + 1; cb = pb + 1; if (pb + 1 == nb) tcn = 0; }
-                    uint32_t cm = __ballot_sync(0xffffffffu, child);
-                    uint32_t cn = (uint32_t)__popc(cm);
-                    if ((uint64_t)fo + cn > fcap || (uint64_t)to + cn > tcap || (uint64_t)nnext + cn > ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
-                    if (child) {
-                        uint32_t at = (uint32_t)__popc(cm & ltm);
-                        F[nx][fo + at] = ca; T[nx][to + at] = cb;
-                        FNode q; q.fo = fo + at; q.fc = 1; q.to = to + at; q.tc = tcn; ND[nx][nnext + at] = q;
-                    }
-                    if (cn) maxsz = max(maxsz, 1u);
-                    fo += cn; to += cn; nnext += cn; e -= tinyrun;
-                    __syncwarp();
-                    clk.stop(FPH_TINY);
-                    continue;
-                }
-                // (1) as many consecutive nodes as fit 32 suffixes per side together: one suffix per lane and side (fuse_packed)
-                uint32_t ia = min(nd.fc, 64u), ib = min(nd.tc, 64u);
-#pragma unroll
-                for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                    uint32_t x = __shfl_up_sync(0xffffffffu, ia, o2), y = __shfl_up_sync(0xffffffffu, ib, o2);
-                    if (l >= o2) { ia += x; ib += y; }
-                }
-                const uint32_t okm = __ballot_sync(0xffffffffu, valid && ia <= 32 && ib <= 32);
-                const uint32_t G = okm == 0xffffffffu ? 32u : (uint32_t)__ffs(~okm) - 1u;
-                if (G > 0) {
-                    clk.start();
-                    if (!fuse_packed(a, na, b, nb, F[cur], T[cur], nd, ia, ib, G, o, fo, to, nnext, maxsz)) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
-                    e -= G;
-                    clk.stop(FPH_SMALL);
-                    continue;
-                }
-                e--;
-                nd = ND[cur][e];
-                clk.start();
-                // (2a) one node of up to FUSE_MID suffixes per side: first bytes in registers, classes by min reduction (fuse_mid)
-                if (nd.fc <= FUSE_MID && nd.tc <= FUSE_MID) {
-                    if (!fuse_mid(a, na, b, nb, F[cur] + nd.fo, nd.fc, T[cur] + nd.to, nd.tc, o, fo, to, nnext, maxsz)) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
-                    clk.stop(FPH_MID);
-                    continue;
-                }
-                // (2b) a node with longer lists, counters in shared memory: warp-parallel classification, then the children taken
-                //      eight classes per lane
-                if (nd.fc < 65535u && nd.tc < 65535u) {
-                    uint32_t ma, mb;
-                    const uint32_t fa2 = fuse_classify_sm(a, na, F[cur] + nd.fo, nd.fc, F[nx], fo, c.ws->sc, sa.start, sizeA, ma);
-                    const uint32_t tb2 = fuse_classify_sm(b, nb, T[cur] + nd.to, nd.tc, T[nx], to, c.ws->sc, sb.start, sizeB, mb);
-                    uint32_t szs[8]; uint32_t nch_l = 0, nq_l = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        szs[i] = 0xffffffffu;                                                     // no child
-                        if ((ma >> i) & 1u) {
-                            uint32_t sz = sizeA[8 * l + i];
-                            if (sz == 0) { szs[i] = 0; nch_l++; nq_l++; }                         // {_Char, []} -> [[[]], []] (:91-93)
-                            else if ((mb >> i) & 1u) { szs[i] = sz; nch_l++; }                    // else notfound
-                        }
-                    }
-                    uint32_t cpre = nch_l, qpre = nq_l;
-#pragma unroll
-                    for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                        uint32_t x = __shfl_up_sync(0xffffffffu, cpre, o2), y = __shfl_up_sync(0xffffffffu, qpre, o2);
-                        if (l >= o2) { cpre += x; qpre += y; }
-                    }
-                    const uint32_t ctot = __shfl_sync(0xffffffffu, cpre, 31), qtot = __shfl_sync(0xffffffffu, qpre, 31);
-                    if ((uint64_t)fo + fa2 + qtot > fcap || (uint64_t)to + tb2 + qtot > tcap || (uint64_t)nnext + ctot > ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
-                    uint32_t ci = nnext + cpre - nch_l, qi = qpre - nq_l, big = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        if (szs[i] == 0xffffffffu) continue;
-                        FNode q; uint32_t ch = 8u * (uint32_t)l + (uint32_t)i;
-                        if (szs[i] == 0) {
-                            F[nx][fo + fa2 + qi] = na; T[nx][to + tb2 + qi] = nb;
-                            q.fo = fo + fa2 + qi; q.fc = 1; q.to = to + tb2 + qi; q.tc = 1; qi++; big = max(big, 1u);
-                        } else { q.fo = sa.start[ch]; q.fc = szs[i]; q.to = sb.start[ch]; q.tc = sizeB[ch]; big = max(big, max(q.fc, q.tc)); }
-                        ND[nx][ci++] = q;
-                    }
-                    maxsz = max(maxsz, __reduce_max_sync(0xffffffffu, big));
-                    fo += fa2 + qtot; to += tb2 + qtot; nnext += ctot;
-                    __syncwarp();
-                    clk.stop(FPH_BIG);
-                    continue;
-                }
-                // (2c) lists of 65 535 suffixes and more: the same through counters in global memory
-                uint32_t fa = fuse_classify(sa, F[cur] + nd.fo, nd.fc, F[nx], fo, sizeA);
-                uint32_t tb = fuse_classify(sb, T[cur] + nd.to, nd.tc, T[nx], to, sizeB);
-                for (int w = 0; w < 8; w++) {
-                    uint32_t m = sa.bits[w];
-                    while (m) {
-                        uint32_t bit = (uint32_t)__ffs(m) - 1; m &= m - 1; uint32_t ch = (uint32_t)w * 32 + bit;
-                        FNode ch_n;
-                        if (sizeA[ch] == 0) {       // {_Char, []} -> [[[]], []]: the two empty suffixes, whatever B holds (:91-93)
-                            if (fo + fa + 1 > fcap || to + tb + 1 > tcap || nnext >= ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
-                            if (l == 0) { F[nx][fo + fa] = na; T[nx][to + tb] = nb; }
-                            ch_n.fo = fo + fa; ch_n.fc = 1; ch_n.to = to + tb; ch_n.tc = 1; fa++; tb++;
-                            if (l == 0) ND[nx][nnext] = ch_n;
-                            nnext++; continue;
-                        }
-                        if (!((sb.bits[w] >> bit) & 1u)) continue;                     // notfound
-                        if (nnext >= ncap) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
-                        ch_n.fo = sa.start[ch]; ch_n.fc = sizeA[ch]; ch_n.to = sb.start[ch]; ch_n.tc = sizeB[ch];
-                        if (l == 0) ND[nx][nnext] = ch_n;
-                        nnext++;
-                        maxsz = max(maxsz, max(ch_n.fc, ch_n.tc));
-                    }
-                }
-                fo += fa; to += tb;
-                __syncwarp();
-                clk.stop(FPH_BIG);
+            // nodes are stored in emission order; the reference's list is that order reversed: a level is split from the top
+            if (lane_id() == 0) { s->fo = 0; s->to = 0; s->nnext = 0; s->maxsz = 0; s->e = s->ncur; }
+            __syncwarp();
+            while (s->e > 0) {
+                if (!fuse_step(s, c.ws->sc)) { c.ws->status = CASE_OVERFLOW; c.ws->reason = 8; return false; }
             }
+            const uint32_t nnext = s->nnext;
             if (nnext == 0) stop = true;
             else {
-                fuel -= (int64_t)nnext; cur = nx; ncur = nnext;
+                fuel -= (int64_t)nnext;
+                const uint32_t maxsz = s->maxsz;
+                __syncwarp();
+                if (lane_id() == 0) { s->cur ^= 1; s->ncur = nnext; }
+                __syncwarp();
                 if (maxsz <= 1) {      // from here on every node is at most 1 x 1: flatten the level into position arrays
-                    const int l2 = lane_id(); const int ot = cur ^ 1;
-                    for (uint32_t k = (uint32_t)l2; k < ncur; k += 32) {
-                        FNode nd = ND[cur][k];
-                        F[ot][k] = nd.fc ? F[cur][nd.fo] : FUSE_NONE;
-                        T[ot][k] = nd.tc ? T[cur][nd.to] : FUSE_NONE;
+                    const int cur = s->cur, ot = cur ^ 1;
+                    const FNode* NDc = s->ND[cur]; const uint32_t* Fc = s->F[cur]; const uint32_t* Tc = s->T[cur]; uint32_t* Fo = s->F[ot]; uint32_t* To = s->T[ot];
+                    for (uint32_t k = (uint32_t)lane_id(); k < nnext; k += 32) {
+                        FNode nd = NDc[k];
+                        Fo[k] = nd.fc ? Fc[nd.fo] : FUSE_NONE;
+                        To[k] = nd.tc ? Tc[nd.to] : FUSE_NONE;
                     }
                     __syncwarp();
-                    cur = ot; compact = true;
+                    if (lane_id() == 0) s->cur = ot;
+                    __syncwarp();
+                    compact = true;
                 }
                 continue;
             }
         }
         // any_position_pair(Nodes)
+        const int cur = s->cur; const uint32_t ncur = s->ncur;
         if (compact) {
             uint32_t r = (uint32_t)g.rand_elem_idx(ncur);
-            uint32_t pa = F[cur][ncur - 1 - r], pb = T[cur][ncur - 1 - r];
+            uint32_t pa = s->F[cur][ncur - 1 - r], pb = s->T[cur][ncur - 1 - r];
             int64_t fi = g.rand_elem_idx(pa != FUSE_NONE ? 1 : 0);
             from = fi < 0 ? na : pa;
             int64_t ti = g.rand_elem_idx(pb != FUSE_NONE ? 1 : 0);
@@ -567,11 +619,11 @@ EB_DEV bool fuse_device(CaseCtx& c, const uint8_t* a, uint32_t na, const uint8_t
             return true;
         }
         uint32_t r = (uint32_t)g.rand_elem_idx(ncur);
-        FNode nd = ND[cur][ncur - 1 - r];
+        FNode nd = s->ND[cur][ncur - 1 - r];
         int64_t fi = g.rand_elem_idx(nd.fc);
-        from = fi < 0 ? na : F[cur][nd.fo + (uint32_t)fi];
+        from = fi < 0 ? na : s->F[cur][nd.fo + (uint32_t)fi];
         int64_t ti = g.rand_elem_idx(nd.tc);
-        to = ti < 0 ? nb : T[cur][nd.to + (uint32_t)ti];
+        to = ti < 0 ? nb : s->T[cur][nd.to + (uint32_t)ti];
         return true;
     }
 }

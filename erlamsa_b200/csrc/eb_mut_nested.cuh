@@ -390,8 +390,25 @@ EB_DEV JsScan js_tokenize(const uint8_t* S, uint32_t n, uint8_t* stk, uint32_t c
         if (o.natoms < acap) { JAtom t; t.kind = kind; t.a = a; t.b = b; t.match = 0; atoms[o.natoms] = t; } else o.status = 2;
         o.natoms++;
     };
-    auto PUSH = [&](uint32_t k) { if (sp < cap) stk[sp] = (uint8_t)k; else o.status = 2; sp++; };   // every lane stores the same byte
-    auto TOP = [&](uint32_t back) -> uint32_t { uint32_t v = stk[sp - 1 - back]; return v; };
+    // The context stack's top eight entries live in a register window (byte 0 = top); an entry goes to memory only when a ninth
+    // is pushed above it and comes back only when the window has been popped empty -- a token costs no memory round trip for
+    // the stack (it was three or four dependent ones).
+    uint64_t win = 0; uint32_t nwin = 0;
+    auto PUSH = [&](uint32_t k) {
+        if (nwin == 8) { if (sp - 8 < cap) stk[sp - 8] = (uint8_t)(win >> 56); nwin = 7; }   // every lane stores the same byte
+        win = (win << 8) | (uint64_t)k; nwin++;
+        if (sp >= cap) o.status = 2;
+        sp++;
+    };
+    auto POP = [&](uint32_t cnt) { sp -= cnt; if (nwin > cnt) { win >>= 8 * cnt; nwin -= cnt; } else { win = 0; nwin = 0; } };
+    auto TOP = [&](uint32_t back) -> uint32_t {
+        if (nwin <= back) {                                   // refill from below the window (everything there is in memory)
+            uint32_t m = sp < 8 ? sp : 8;
+            for (uint32_t t = nwin; t < m; t++) win |= (uint64_t)stk[sp - 1 - t] << (8 * t);
+            nwin = m;
+        }
+        return (uint32_t)(win >> (8 * back)) & 255u;
+    };
     auto notsep = [](uint32_t ch) { return ch != ' ' && ch != '\n' && ch != '\r' && ch != '\t' && ch != ',' && ch != ']' && ch != '}' && ch != ':'; };
     // push/4 :160-176
     auto push_value = [&](int kind, uint32_t a, uint32_t b) -> bool {
@@ -400,8 +417,8 @@ EB_DEV JsScan js_tokenize(const uint8_t* S, uint32_t n, uint8_t* stk, uint32_t c
             if (sp == 0) { o.ntop++; o.kind = kind; o.a = a; o.b = b; return true; }
             uint32_t h = TOP(0);
             if (h == JC_ELEMENTS || h == JC_MEMBERS) return true;
-            if (h == JC_PAIR_DELIM) { sp--; PUSH(JC_PAIR_START); PUSH(JC_PAIR_DELIM); return true; }
-            if (h == JC_PAIR_END && sp >= 2 && TOP(1) == JC_PAIR_START) { sp -= 2; kind = JV_CONTAINER; continue; }
+            if (h == JC_PAIR_DELIM) { POP(1); PUSH(JC_PAIR_START); PUSH(JC_PAIR_DELIM); return true; }
+            if (h == JC_PAIR_END && sp >= 2 && TOP(1) == JC_PAIR_START) { POP(2); kind = JV_CONTAINER; continue; }
             return false;
         }
     };
@@ -416,30 +433,30 @@ EB_DEV JsScan js_tokenize(const uint8_t* S, uint32_t n, uint8_t* stk, uint32_t c
         bool want_value = false;
         switch (topk) {
         case JC_ARRAY:
-            sp--; PUSH(JC_ARRAY_END);
-            if (S[i] == ']') { ATOM(JA_CARR, i, i + 1); i++; sp--; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
+            POP(1); PUSH(JC_ARRAY_END);
+            if (S[i] == ']') { ATOM(JA_CARR, i, i + 1); i++; POP(1); if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
             PUSH(JC_ELEMENTS); PUSH(JC_VALUE); continue;
         case JC_ELEMENTS:
-            if (S[i] == ']' && sp >= 2 && TOP(1) == JC_ARRAY_END) { ATOM(JA_CARR, i, i + 1); i++; sp -= 2; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
+            if (S[i] == ']' && sp >= 2 && TOP(1) == JC_ARRAY_END) { ATOM(JA_CARR, i, i + 1); i++; POP(2); if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
             if (S[i] == ',') { ATOM(JA_COMMA, i, i + 1); i++; PUSH(JC_VALUE); continue; }
             o.status = 1; return o;
         case JC_OBJECT:
-            sp--; PUSH(JC_OBJECT_END);
-            if (S[i] == '}') { ATOM(JA_COBJ, i, i + 1); i++; sp--; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
+            POP(1); PUSH(JC_OBJECT_END);
+            if (S[i] == '}') { ATOM(JA_COBJ, i, i + 1); i++; POP(1); if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
             PUSH(JC_MEMBERS); PUSH(JC_PAIR); continue;
         case JC_MEMBERS:
-            if (S[i] == '}' && sp >= 2 && TOP(1) == JC_OBJECT_END) { ATOM(JA_COBJ, i, i + 1); i++; sp -= 2; if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
+            if (S[i] == '}' && sp >= 2 && TOP(1) == JC_OBJECT_END) { ATOM(JA_COBJ, i, i + 1); i++; POP(2); if (!push_value(JV_CONTAINER, 0, 0)) { o.status = 1; return o; } continue; }
             if (S[i] == ',') { ATOM(JA_COMMA, i, i + 1); i++; PUSH(JC_PAIR); continue; }
             o.status = 1; return o;
         case JC_PAIR:
-            sp--;
-            if (S[i] == ':' && sp >= 1 && TOP(0) == JC_PAIR_DELIM) { o.irregular = 1; i++; sp--; PUSH(JC_PAIR_END); PUSH(JC_VALUE); continue; }
+            POP(1);
+            if (S[i] == ':' && sp >= 1 && TOP(0) == JC_PAIR_DELIM) { o.irregular = 1; i++; POP(1); PUSH(JC_PAIR_END); PUSH(JC_VALUE); continue; }
             PUSH(JC_PAIR_DELIM); PUSH(JC_VALUE); continue;
         case JC_PAIR_DELIM:
-            if (S[i] == ':') { ATOM(JA_COLON, i, i + 1); i++; sp--; PUSH(JC_PAIR_END); PUSH(JC_VALUE); continue; }
+            if (S[i] == ':') { ATOM(JA_COLON, i, i + 1); i++; POP(1); PUSH(JC_PAIR_END); PUSH(JC_VALUE); continue; }
             o.irregular = 1;                                             // a key followed by another value: pairs as keys, not laid out on the device
             PUSH(JC_PAIR_DELIM); PUSH(JC_VALUE); continue;
-        case JC_VALUE: sp--; want_value = true; break;
+        case JC_VALUE: POP(1); want_value = true; break;
         default: o.status = 2; return o;                                 // case_clause in ws/3: cannot be reached from the states above
         }
         if (!want_value) continue;
@@ -489,7 +506,9 @@ EB_DEV void mut_js(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     uint32_t acap = n / 2 + 16;                                          // denser than an atom every two bytes ("[[[[...") flags the case
     JAtom* atoms = (JAtom*)temp_alloc(c, (uint64_t)acap * sizeof(JAtom));
     if (!stk || !atoms) { r.delta = 0; return; }
+    FuseClock clk = phase_clock(c); clk.start();
     JsScan js = js_tokenize(p, n, stk, cap, atoms, acap);
+    clk.stop(PH_JS_TOK);
     if (js.status == 1) return;                                          // incorrect_json :728-730
     if (js.status == 2) { r.kind = RES_UNSUPPORTED; return; }
     if (js.ntop == 1 && js.kind == JV_CONTAINER) {

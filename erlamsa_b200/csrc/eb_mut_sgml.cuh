@@ -188,17 +188,29 @@ EB_DEV bool sg_pair(CaseCtx& c, SgDoc& d) {
     return true;
 }
 
-// element number (1-based, pre-order) -> token index; tag number -> token index
-EB_DEV uint32_t sg_elem_tok(const SgDoc& d, uint32_t want) {
-    uint32_t c = 0;
-    for (uint32_t i = 0; i < d.ntok; i++) if (sg_is_elem(d.tok[i]) && ++c == want) return i;
+// element number (1-based, pre-order) -> token index; tag number -> token index. 32 tokens per step: ballot of the
+// predicate, the wanted one is the (want - seen)-th set bit of the step that crosses it.
+template <typename Pred>
+__device__ __forceinline__ uint32_t sg_nth_tok(const SgDoc& d, uint32_t want, Pred pred) {
+    if (want == 0) return SG_NOMATCH;
+    const int l = lane_id(); uint32_t seen = 0;
+    for (uint32_t i0 = 0; i0 < d.ntok; i0 += 32) {
+        uint32_t i = i0 + (uint32_t)l;
+        uint32_t m = __ballot_sync(0xffffffffu, i < d.ntok && pred(d.tok[i]));
+        uint32_t k = (uint32_t)__popc(m);
+        if (seen + k >= want) {
+            for (uint32_t t = seen + 1; t < want; t++) m &= m - 1;
+            return i0 + (uint32_t)__ffs(m) - 1;
+        }
+        seen += k;
+    }
     return SG_NOMATCH;
 }
+EB_DEV uint32_t sg_elem_tok(const SgDoc& d, uint32_t want) { return sg_nth_tok(d, want, [](const STok& t) { return sg_is_elem(t); }); }
 EB_DEV uint32_t sg_tag_tok(const SgDoc& d, uint32_t want) {
-    uint32_t c = 0;
-    for (uint32_t i = 0; i < d.ntok; i++) if (d.tok[i].kind == ST_OPEN && (d.tok[i].flags & SF_PAIRED) && ++c == want) return i;
-    return SG_NOMATCH;
+    return sg_nth_tok(d, want, [](const STok& t) { return t.kind == ST_OPEN && (t.flags & SF_PAIRED) != 0; });
 }
+
 __device__ __forceinline__ uint32_t sg_range_hi(const SgDoc& d, uint32_t i) { return (d.tok[i].kind == ST_OPEN && (d.tok[i].flags & SF_PAIRED)) ? d.tok[i].match : i; }
 
 // ---------------------------------------------------------------- folder (:290-331), per token
@@ -327,12 +339,17 @@ EB_DEV void mut_sgm(CaseCtx& c, const uint8_t* p, uint32_t n, MutResult& r) {
     d.tok = (STok*)temp_alloc(c, (uint64_t)d.tok_cap * sizeof(STok));
     d.par = (SPar*)temp_alloc(c, (uint64_t)d.par_cap * sizeof(SPar));
     if (!d.tok || !d.par) { r.delta = 0; return; }
+    FuseClock clk = phase_clock(c); clk.start();
     int k = sg_tokenize(c, d);
+    clk.stop(PH_SGM_TOK);
     if (ws->status != CASE_OK) return;
     if (k == 1) return;                                                  // throw(incorrect_sgml) -> {_, Ll, Meta, -1} :754-756
     if (k == 2) { ws->status = CASE_DIED; return; }                      // function_clause: not what sgml_mutate/2 catches
     if (k == 3) { r.kind = RES_UNSUPPORTED; return; }
-    if (!sg_pair(c, d)) { r.kind = RES_UNSUPPORTED; return; }
+    clk.start();
+    const bool paired = sg_pair(c, d);
+    clk.stop(PH_SGM_PAIR);
+    if (!paired) { r.kind = RES_UNSUPPORTED; return; }
     const uint32_t N = d.N, NT = d.NT;
     SgPlan pl; pl.which = (int)g.rand(12); pl.a_lo = pl.a_hi = pl.b_lo = pl.b_hi = SG_NOMATCH; pl.times = 0; pl.x_lo = pl.x_hi = 0;
     pl.perm_tok = SG_NOMATCH; pl.perm = nullptr; pl.wrap = false;

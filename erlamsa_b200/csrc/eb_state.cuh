@@ -23,6 +23,21 @@ struct MutRow { double score; int32_t pri; uint8_t name; uint8_t fn; uint16_t pa
 struct Blk { const uint8_t* p; uint32_t len; uint32_t cnt; };
 struct StSlot { const uint8_t* hp; const uint8_t* tp; uint32_t hl; uint32_t tl; };
 
+// fuse search (eb_mut_fuse.cuh): a node = (source suffixes, target suffixes) as two ranges of the level's position arrays
+struct FNode { uint32_t fo, fc, to, tc; };
+// ... and the search state of the warp, kept in shared memory so that the node paths (separate functions) exchange it without
+// going through the stack
+struct FuseSh {
+    const uint8_t* a; const uint8_t* b; uint32_t na, nb;
+    uint32_t* F[2]; uint32_t* T[2]; FNode* ND[2];      // ping-pong: positions per side, nodes
+    uint32_t fcap, tcap, ncap;
+    uint32_t* tabs;                                    // class tables in global memory (starts, sizes; counters for very long lists)
+    int cur; uint32_t ncur;                            // the level being split
+    uint32_t e;                                        // its nodes not yet taken (from the top)
+    uint32_t fo, to, nnext, maxsz;                     // the level being built
+    unsigned long long* clk;                           // profiling aid
+};
+
 struct WarpState {
     MutRow rows[M_COUNT];
     MutRow tried[M_COUNT];
@@ -53,6 +68,7 @@ struct WarpState {
     uint32_t round;          // mux_fuzzers rounds so far in this case (Philox counter slots, eb_rng.cuh)
     uint64_t donor;          // this case's donor index (thread seed hash, see mut_fuse)
     uint16_t sc[SC_MAX];
+    FuseSh fsh;
     uint32_t qpend;          // countdown of this warp's outstanding scan jobs (eb_jobs.cuh)
     uint32_t status; uint32_t reason;
     int n_used, n_failed; int used[16];
@@ -70,6 +86,19 @@ struct CaseCtx {
     int snand_kind;          // mask function bound to `snand` when the current table was built (mutations/1 :1313)
     JobQ* q;                 // the CTA's job queue (nullptr: no worker warps, everything inline)
 };
+
+// profiling aid (EB200_CASE_TIMES=1): nanoseconds and steps per phase, eight (ns, count) pairs after the per-mutator table
+enum { FPH_BIG = 0, FPH_MID, FPH_SMALL, FPH_TINY, FPH_COMPACT, PH_SGM_TOK, PH_SGM_PAIR, PH_JS_TOK, FPH_COUNT };
+struct FuseClock {
+    unsigned long long* tab; unsigned long long t0;
+    __device__ __forceinline__ void start() { if (tab) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0)); }
+    __device__ __forceinline__ void stop(int ph) {
+        if (!tab) return;
+        unsigned long long t1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (lane_id() == 0) { atomicAdd(&tab[2 * ph], t1 - t0); atomicAdd(&tab[2 * ph + 1], 1ull); }
+    }
+};
+__device__ __forceinline__ FuseClock phase_clock(const CaseCtx& c) { FuseClock k; k.tab = c.ar.mut_ns ? c.ar.mut_ns + 2 * M_COUNT : nullptr; k.t0 = 0; return k; }
 
 // ------------------------------------------------------------------ arenas
 EB_DEV uint8_t* scratch_alloc(CaseCtx& c, uint64_t bytes) {

@@ -72,8 +72,8 @@ if N.lib().eb200_debug_mutator_times(eng._ctx, mt):
     for i in sorted(range(41), key=lambda i: -mt[2 * i]):
         if mt[2 * i + 1]:
             print("  %-6s total %10.1f ms  calls %7d  mean %9.1f us" % (MC[i], mt[2 * i] / 1e6, mt[2 * i + 1], mt[2 * i] / 1e3 / mt[2 * i + 1]))
-    print("fuse search by phase:")
-    for j, name in enumerate(("tables (> 256 per side)", "registers (25..256)", "lane per node (2..24)", "one suffix per side", "flat levels")):
+    print("fuse search by phase / document mutators by phase:")
+    for j, name in enumerate(("class tables (> 128 per side)", "registers (33..128)", "packed (<= 32 per side)", "one suffix per side", "flat levels", "sgm: tokenize", "sgm: pair tags", "js: tokenize")):
         if mt[82 + 2 * j + 1]:
             print("  %-26s total %10.1f ms  steps %8d  mean %9.2f us" % (name, mt[82 + 2 * j] / 1e6, mt[82 + 2 * j + 1], mt[82 + 2 * j] / 1e3 / mt[82 + 2 * j + 1]))
 # time by mutator TRIED is not recorded; failures dominate when `used` is short and n_failed large
