@@ -101,31 +101,37 @@ EB_DEV uint32_t fuse_classify_sm(const uint8_t* s, uint32_t len, const uint32_t*
     const int l = lane_id(); const uint32_t lt = (1u << l) - 1u;
 #pragma unroll
     for (int i = 0; i < 8; i++) tbl[8 * l + i] = 0;
-    // the suffix holding only the block's last byte is dropped when it is the FIRST of its class ([[]] -> [], :68-70)
-    uint32_t sq = 0xffffffffu, sch = 0x100u;
-    for (uint32_t q0 = 0; q0 < k; q0 += 32) {
-        uint32_t q = q0 + l; uint32_t p = q < k ? src[q] : 0xffffffffu;
-        uint32_t hit = __ballot_sync(0xffffffffu, q < k && p + 1 == len);
-        if (hit) { sq = q0 + (uint32_t)__ffs(hit) - 1; sch = s[len - 1]; break; }
-    }
-    bool special_dropped = false;
-    if (sq != 0xffffffffu) {
-        uint32_t before = 0;
-        for (uint32_t q0 = 0; q0 < sq; q0 += 32) {
-            uint32_t q = q0 + l; uint32_t p = q < sq ? src[q] : 0xffffffffu;
-            before |= __ballot_sync(0xffffffffu, q < sq && p < len && s[p] == sch);
-            if (before) break;
-        }
-        special_dropped = before == 0;
-    }
     __syncwarp();
-    for (uint32_t q0 = 0; q0 < k; q0 += 32) {                          // count
-        uint32_t q = q0 + l; uint32_t p = q < k ? src[q] : 0xffffffffu;
-        bool counted = q < k && p < len && !(special_dropped && q == sq);   // the [] suffix contributes nothing (:68)
-        uint32_t ch = counted ? s[p] : 0u;
-        uint32_t peers = __match_any_sync(0xffffffffu, counted ? ch : 0x100u + (uint32_t)l);
-        if (counted && (peers & lt) == 0) tbl[ch] = (uint16_t)(tbl[ch] + (uint32_t)__popc(peers));
-        __syncwarp();
+    // Both passes take the list 128 suffixes at a time: four position loads in flight, then four byte gathers -- two memory round
+    // trips per 128 suffixes instead of two per 32.
+    // The suffix holding only the block's last byte is dropped when it is the FIRST of its class ([[]] -> [], :68-70): decided when
+    // the count pass meets it -- "first" = the class counter is still zero and no lower lane of the step holds the same byte.
+    uint32_t sq = 0xffffffffu, sch = 0x100u; bool special_dropped = false;
+    for (uint32_t q0 = 0; q0 < k; q0 += 128) {                         // count
+        uint32_t p[4], ch[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { uint32_t q = q0 + 32u * (uint32_t)j + (uint32_t)l; p[j] = q < k ? src[q] : 0xffffffffu; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) ch[j] = p[j] < len ? (uint32_t)s[p[j]] : 0x100u;      // the [] suffix contributes nothing (:68)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (q0 + 32u * (uint32_t)j < k) {
+                bool counted = ch[j] < 0x100u;
+                const uint32_t sp = __ballot_sync(0xffffffffu, counted && p[j] + 1 == len);
+                if (sp) {
+                    const int ls = __ffs(sp) - 1;
+                    const uint32_t c0 = __shfl_sync(0xffffffffu, ch[j], ls);
+                    const uint32_t same = __ballot_sync(0xffffffffu, counted && ch[j] == c0);
+                    if (tbl[c0] == 0 && (same & ((1u << ls) - 1u)) == 0) {
+                        special_dropped = true; sq = q0 + 32u * (uint32_t)j + (uint32_t)ls; sch = c0;
+                        if (l == ls) counted = false;
+                    }
+                }
+                const uint32_t peers = __match_any_sync(0xffffffffu, counted ? ch[j] : 0x100u + (uint32_t)l);
+                if (counted && (peers & lt) == 0) tbl[ch[j]] = (uint16_t)(tbl[ch[j]] + (uint32_t)__popc(peers));
+                __syncwarp();
+            }
+        }
     }
     uint32_t cn[8]; uint32_t mine = 0;
 #pragma unroll
@@ -144,18 +150,26 @@ EB_DEV uint32_t fuse_classify_sm(const uint8_t* s, uint32_t len, const uint32_t*
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
-    for (uint32_t q0 = 0; q0 < k; q0 += 32) {                          // place: first arrival lands last in its class
-        uint32_t q = q0 + l; uint32_t p = q < k ? src[q] : 0xffffffffu;
-        bool placed = q < k && p < len && !(special_dropped && q == sq);
-        uint32_t ch = placed ? s[p] : 0u;
-        uint32_t peers = __match_any_sync(0xffffffffu, placed ? ch : 0x100u + (uint32_t)l);
-        uint32_t end = placed ? tbl[ch] : 0u;
-        __syncwarp();
-        if (placed) {
-            dst[base + end - 1 - (uint32_t)__popc(peers & lt)] = p + 1;
-            if ((peers & lt) == 0) tbl[ch] = (uint16_t)(end - (uint32_t)__popc(peers));
+    for (uint32_t q0 = 0; q0 < k; q0 += 128) {                         // place: first arrival lands last in its class
+        uint32_t p[4], ch[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { uint32_t q = q0 + 32u * (uint32_t)j + (uint32_t)l; p[j] = q < k ? src[q] : 0xffffffffu; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) ch[j] = p[j] < len ? (uint32_t)s[p[j]] : 0x100u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (q0 + 32u * (uint32_t)j < k) {
+                const bool placed = ch[j] < 0x100u && !(special_dropped && q0 + 32u * (uint32_t)j + (uint32_t)l == sq);
+                const uint32_t peers = __match_any_sync(0xffffffffu, placed ? ch[j] : 0x100u + (uint32_t)l);
+                const uint32_t end = placed ? tbl[ch[j]] : 0u;
+                __syncwarp();
+                if (placed) {
+                    dst[base + end - 1 - (uint32_t)__popc(peers & lt)] = p[j] + 1;
+                    if ((peers & lt) == 0) tbl[ch[j]] = (uint16_t)(end - (uint32_t)__popc(peers));
+                }
+                __syncwarp();
+            }
         }
-        __syncwarp();
     }
     return total;
 }

@@ -94,7 +94,51 @@ EB_DEV void js_emit_atom(JEmit& e, const JDoc& d, uint32_t i) {
     default: bld_copy(e.b, d.S + a.a, a.b - a.a); break;                  // scalars verbatim; brackets, commas and colons are their own text
     }
 }
-EB_DEV void js_emit_range(JEmit& e, const JDoc& d, uint32_t lo, uint32_t hi) { for (uint32_t i = lo; i <= hi && i < d.nat; i++) js_emit_atom(e, d, i); }
+// a run of atoms, 32 per step: every lane sizes its own atom (override or source text, quotes included), one warp scan gives the
+// output offsets, short atoms are copied by their lane and long ones by the whole warp -- the serial walk paid a dependent
+// table load and a warp copy of a few bytes per atom, twice (sizing pass, writing pass).
+EB_DEV void js_emit_range(JEmit& e, const JDoc& d, uint32_t lo, uint32_t hi) {
+    if (d.nat == 0 || lo >= d.nat || lo > hi) return;
+    if (hi >= d.nat) hi = d.nat - 1;
+    const int l = lane_id();
+    Bld& b = e.b;
+    for (uint32_t i0 = lo; i0 <= hi; i0 += 32) {
+        const uint32_t i = i0 + (uint32_t)l; const bool act = i <= hi && i >= i0;
+        const uint8_t* src = nullptr; uint32_t len = 0, pre = 0, post = 0;
+        if (act) {
+            const JAtom a = d.at[i];
+            if (d.ov && d.ov[i].on) { src = d.ov[i].ptr; len = d.ov[i].len; if (a.kind == JA_STR) { pre = 1; post = 1; } }
+            else if (a.kind == JA_STR) { src = d.S + a.a - 1; len = a.b - a.a + 2; }
+            else if (a.kind == JA_JUNK) { src = d.S + a.a - 1; len = d.n - (a.a - 1); post = 2; }
+            else { src = d.S + a.a; len = a.b - a.a; }                  // scalars verbatim; brackets, commas and colons are their own text
+        }
+        unsigned long long incl = (unsigned long long)pre + len + post;
+        const unsigned long long mine = incl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long x = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += x; }
+        const unsigned long long step = __shfl_sync(0xffffffffu, incl, 31);
+        if ((unsigned long long)b.n + step > 0x7fffffffull) { b.ovf = 1; return; }
+        if (b.p) {
+            const uint32_t at = b.n + (uint32_t)(incl - mine);
+            constexpr uint32_t SHORT = 48;
+            if (act) {
+                if (pre && at < b.cap) b.p[at] = '"';
+                if (len <= SHORT) for (uint32_t k = 0; k < len; k++) if (at + pre + k < b.cap) b.p[at + pre + k] = src[k];
+                for (uint32_t k = 0; k < post; k++) if (at + pre + len + k < b.cap) b.p[at + pre + len + k] = '"';
+            }
+            uint32_t longs = __ballot_sync(0xffffffffu, act && len > SHORT);
+            while (longs) {
+                const int t = __ffs(longs) - 1; longs &= longs - 1;
+                const uint8_t* sp = (const uint8_t*)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)src, t);
+                const uint32_t sl = __shfl_sync(0xffffffffu, len, t), sa = __shfl_sync(0xffffffffu, at + pre, t);
+                for (uint32_t k = (uint32_t)l; k < sl; k += 32) if (sa + k < b.cap) b.p[sa + k] = sp[k];
+            }
+        }
+        b.n += (uint32_t)step;
+        if (hi - i0 < 32) break;                                          // (also keeps i0 += 32 from wrapping)
+    }
+    __syncwarp();
+}
 
 struct JPlan { int which; uint32_t a, b; uint32_t times; uint32_t x; };   // a, b, x: element indices
 EB_DEV void js_emit_plan(JEmit& e, const JDoc& d, const JPlan& pl) {
