@@ -301,3 +301,18 @@ def test_philox_mode_runs_and_differs(engine):
     c, _ = engine.fuzz_batch(blobs, {"mutations": {"bd": 1, "bf": 1, "num": 1}, "patterns": {"od": 1}, "seed": (1, 2, 3)})
     assert a == b            # deterministic
     assert a != c            # a different stream than AS183
+
+
+@pytest.mark.xfail(strict=False, reason="open issue (DESIGN.md section 9): tests/wide_diff.py saw 1 of 240 whole-table nd cases differ between two "
+                                        "runs of the same build once; the 128-register build of the general kernel differs on b64's nested rounds")
+def test_run_to_run_determinism_whole_table_nd(engine):
+    """the same batch twice through the same engine: every byte and every draw count must repeat"""
+    import erlamsa_b200
+    muts = {c: p for c, p in erlamsa_b200.default_mutations() if c in erlamsa_b200.supported_mutations()}
+    blobs = corpus.mixed_corpus(0xE21A0100, 240)
+    opts = {"mutations": muts, "patterns": {"nd": 1}, "seed": (2, 7, 1), "max_case_out": CAP}
+    a, ma = engine.fuzz_batch(blobs, dict(opts), n_cases=len(blobs))
+    for _ in range(3):
+        b, mb = engine.fuzz_batch(blobs, dict(opts), n_cases=len(blobs))
+        bad = [k for k in range(len(blobs)) if a[k] != b[k] or ma[k].draws != mb[k].draws or ma[k].status != mb[k].status]
+        assert not bad, "cases that did not repeat: %r" % bad[:8]
