@@ -32,11 +32,16 @@ pri_vector(Table, Selected) ->
 mutator_table() -> [Name || {_, _, _, Name, _} <- erlamsa_mutations:mutations()].
 pattern_table() -> [Name || {_, _, Name, _} <- erlamsa_patterns:patterns()].
 
-%% the engine implements the `direct` and `random` generators; anything else in the list keeps the Erlang path
-generator_pris(Gens) ->
+%% What make_generator_fun/4 (src/erlamsa_gen.erl:204-237) keeps of the generator list when paths == [direct] and an input is given:
+%% direct and random. stdin, file and jump are dropped there whatever their priority (so the DEFAULT list is fine); genfuz is
+%% dropped too unless an external generator module is set -- then the Erlang path runs. An unknown name fails in the reference,
+%% so it goes there as well.
+generator_pris(Gens, Opts) ->
     M = maps:from_list(Gens),
-    case maps:keys(M) -- [direct, random] of
-        [] -> {ok, {maps:get(direct, M, -1), maps:get(random, M, -1)}};
+    Unknown = maps:keys(M) -- [random, jump, direct, file, genfuz, stdin],
+    External = maps:is_key(genfuz, M) andalso maps:get(external_generator, Opts, nil) =/= nil,
+    case {Unknown, External} of
+        {[], false} -> {ok, {maps:get(direct, M, -1), maps:get(random, M, -1)}};
         _ -> unsupported
     end.
 
@@ -44,8 +49,8 @@ generator_pris(Gens) ->
 supported(Opts) ->
     maps:get(paths, Opts, ["-"]) =:= [direct] andalso maps:get(output, Opts, "-") =:= return
         andalso maps:get(external_mutations, Opts, nil) =:= nil andalso maps:get(external_post, Opts, nil) =:= nil
-        andalso maps:get(sequence_muta, Opts, false) =:= false andalso maps:is_key(seed, Opts)
-        andalso generator_pris(maps:get(generators, Opts, erlamsa_gen:default())) =/= unsupported.
+        andalso maps:get(sequence_muta, Opts, false) =:= false andalso is_tuple(maps:get(seed, Opts, nil))
+        andalso generator_pris(maps:get(generators, Opts, erlamsa_gen:default()), Opts) =/= unsupported.
 
 %% one case, by the reference, with the seeds the batch semantics give it: case I draws the I-th gen_predictable_seed() of
 %% the parent stream (skip => I - 1 makes the reference burn the first I - 1 without running them). This is O(I) cheap
@@ -62,7 +67,7 @@ fuzz_batch(Corpus, Opts) when is_list(Corpus), Corpus =/= [] ->
     Skip = maps:get(skip, Opts, 0),
     MutaPri = pri_vector(mutator_table(), maps:get(mutations, Opts, erlamsa_mutations:default([]))),
     PatPri = pri_vector(pattern_table(), maps:get(patterns, Opts, erlamsa_patterns:default())),
-    {ok, Gens} = generator_pris(maps:get(generators, Opts, erlamsa_gen:default())),
+    {ok, Gens} = generator_pris(maps:get(generators, Opts, erlamsa_gen:default()), Opts),
     {Host, Port} = erlamsa_mutations:get_ssrf_ep(),
     case fuzz_batch_nif(Corpus, N - Skip, Seed, MutaPri, PatPri, Skip + 1, maps:get(blockscale, Opts, 1.0) * 1.0,
                         {iolist_to_binary(Host), Port}, Gens, maps:get(gpu_device, Opts, 0)) of
