@@ -163,3 +163,66 @@ def test_faas_batch_endpoint_answers_what_the_reference_would_case_by_case():
     bad_env = from_py([("http_erlamsa_token", "bad")])
     in_evaluator(lambda: call(ref, "erlamsa_b200_esi", "batch", "sid", bad_env, from_py([ord(c) for c in body])))
     assert sent[0].startswith(b"erlamsa-status: 401") and sent[1] == b""
+
+
+def test_otp_dump_tool_runs_and_reproduces_the_committed_vectors(tmp_path):
+    """tools/dump_reference_vectors.erl is the one-command recipe for whoever has a real OTP; its Erlang had never been executed.
+    Here its own text (shebang and -mode line stripped, a -module line added) runs under the evaluator with file:consult/1,
+    file:open/2 and io:format/3 backed by Python, over a sample of tests/golden/reference_cases.term, and its output goes
+    through the same check the OTP hook applies (tests/test_reference_vectors.py::test_otp_run_matches_committed_vectors)."""
+    import hashlib
+    import json
+    from erlref.terms import from_py, to_py
+    src = open(os.path.join(ROOT, "tools", "dump_reference_vectors.erl")).read().split("\n")
+    body = [ln for ln in src if not ln.startswith("#!") and not ln.startswith("-mode(")]
+    (tmp_path / "dump_reference_vectors.erl").write_text("-module(dump_reference_vectors).\n-export([main/1]).\n" + "\n".join(body))
+    vec = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))["vectors"]
+
+    def plist(d):
+        return "default" if d is None else "[" + ",".join("{%s,%d}" % (k, v) for k, v in d.items()) + "]"
+    lines, want = [], {}
+    for v in vec[::5]:                                                   # every fifth configuration, its first two cases
+        extra = []
+        if "generators" in v["extra"]:
+            extra.append("{generators,%s}" % plist(v["extra"]["generators"]))
+        if "blockscale" in v["extra"]:
+            extra.append("{blockscale,%r}" % float(v["extra"]["blockscale"]))
+        for k in range(min(2, v["n_cases"])):
+            i = v["first_case"] + k
+            lines.append('{"%s",%d,"%s",%d,{%d,%d,%d},%s,%s,[%s]}' % (v["name"], k, v["blobs"][(i - 1) % len(v["blobs"])], i, v["seed"][0], v["seed"][1], v["seed"][2],
+                                                                     plist(v["mutations"]), plist(v["patterns"]), ",".join(extra)))
+            want[(v["name"], k)] = (v["status"][k], v["digests"][k])
+    ref = refrun.Reference()
+    rt = ref.rt
+    rt.src_dirs.append(str(tmp_path))
+    out = []
+
+    def flat(x, acc):
+        if isinstance(x, (bytes, bytearray)):
+            acc += x
+        elif isinstance(x, int):
+            acc.append(x)
+        else:
+            for y in x:
+                flat(y, acc)
+        return acc
+    rt.register("code", "add_patha", 1, lambda p: "true")
+    rt.register("file", "consult", 1, lambda p: ("ok", from_py([rt.eval(ln) for ln in lines])))
+    rt.register("file", "open", 2, lambda p, m: ("ok", "the_fd"))
+    fmt = rt.bifs[("io_lib", "format", 2)].fn
+    rt.register("io", "format", 3, lambda fd, f, a: out.append(bytes(flat(fmt(f, a), bytearray())).decode("latin-1")) or "ok")
+
+    def s(x):
+        return from_py([ord(c) for c in x])
+    in_evaluator(lambda: call(ref, "dump_reference_vectors", "main", from_py([s("ebin"), s("cases.term"), s("out.txt")])))
+    got = {}
+    for ln in "".join(out).split("\n"):
+        f = ln.split()
+        if len(f) >= 3:
+            got[(f[0], int(f[1]))] = (f[2], bytes.fromhex(f[3]) if len(f) > 3 else b"")
+    assert set(got) == set(want) and len(want) >= 20
+    for key, (st, dig) in want.items():
+        if st != "ok":
+            continue
+        assert got[key][0] == "ok", (key, got[key][0])
+        assert [len(got[key][1]), hashlib.sha256(got[key][1]).hexdigest()] == list(dig), key

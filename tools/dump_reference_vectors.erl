@@ -9,6 +9,8 @@
 %%   escript tools/dump_reference_vectors.erl /path/to/erlamsa/ebin tests/golden/reference_cases.term tests/golden/otp_vectors.txt
 %%   python -m pytest tests/test_reference_vectors.py -k otp  # compares otp_vectors.txt with the committed vectors
 %%
+%% (This script's own code is exercised in CI by tests/test_erlang_shim.py, which runs it under the Erlang evaluator of oracle/erlref.)
+%%
 %% Each case is erlamsa_main:fuzzer(#{paths => [direct], output => return, input => Blob, seed => Seed, n => I, skip => I-1,
 %% maxrunningtime => 600000, ...}) -- the call tests/golden/make_reference_vectors.py makes.
 -mode(compile).
