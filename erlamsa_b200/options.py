@@ -3,9 +3,11 @@
 * mutator / pattern codes and default priorities: reference src/erlamsa_mutations.erl:1291-1331,
   src/erlamsa_patterns.erl:395-404 (read back from the native library so there is one table);
 * the `-m` / `-p` grammar "code=pri,code,..." of erlamsa_cmdparse:string_to_actions/3
-  (reference src/erlamsa_cmdparse.erl:233-257): a bare code means priority 1;
+  (reference src/erlamsa_cmdparse.erl:233-257): a bare code takes its priority from the default table;
 * the option-map keys read by erlamsa_main:fuzzer/1 (reference src/erlamsa_main.erl:127-163).
 """
+import re
+
 from . import _native as N
 
 
@@ -42,8 +44,12 @@ def supported_patterns():
 
 
 def string_to_actions(s, what, defaults):
-    """"bd=2,num,sr=3" -> [("bd",2),("num",1),("sr",3)]; "default" keeps the table. Unknown names raise,
-    like the reference's `Unknown <what>` failure (src/erlamsa_cmdparse.erl:244-251)."""
+    """erlamsa_cmdparse:string_to_actions/3 (src/erlamsa_cmdparse.erl:232-257): "bd=2,num,sr=3" -> [("sr",3),("num",DefaultPri),("bd",2)].
+    A name without "=N" takes its priority from the DEFAULT table (`-m sgm` means sgm=10, not sgm=1); tokens are cut the way
+    string:tokens/2 cuts them (empty pieces vanish, "bd=2=3" has three pieces and falls back to the default priority); the list
+    comes back reversed, so that -- turned into a map, as make_mutator/2 and make_pattern/1 do -- the FIRST of two entries for
+    one name wins. An unknown name or a priority that is not an integer raises, where the reference fails with
+    "No such <what>!" / "Invalid <what> list specification!". Extension: the single word "default" keeps the table."""
     if s == "default":
         return list(defaults)
     known = dict(defaults)
@@ -51,10 +57,19 @@ def string_to_actions(s, what, defaults):
     for tok in s.split(","):
         if not tok:
             continue
-        name, _, pri = tok.partition("=")
+        parts = [x for x in tok.split("=") if x]
+        if not parts:
+            raise ValueError("Invalid %s list specification!" % what)
+        name = parts[0]
         if name not in known:
             raise ValueError("Unknown %s: %s" % (what, name))
-        out.append((name, int(pri) if pri else 1))
+        if len(parts) == 2:
+            if not re.fullmatch(r"[+-]?[0-9]+", parts[1]):
+                raise ValueError("Invalid %s list specification!" % what)
+            out.append((name, int(parts[1])))
+        else:
+            out.append((name, known[name]))
+    out.reverse()
     return out
 
 

@@ -226,3 +226,36 @@ def test_otp_dump_tool_runs_and_reproduces_the_committed_vectors(tmp_path):
             continue
         assert got[key][0] == "ok", (key, got[key][0])
         assert [len(got[key][1]), hashlib.sha256(got[key][1]).hexdigest()] == list(dig), key
+
+
+def test_option_string_grammar_of_the_python_mirror_is_the_references(ref):
+    """erlamsa_b200.options.string_to_actions against erlamsa_cmdparse:string_to_actions/3 run by the evaluator, on random -m / -p strings
+    (bare names, name=N, duplicates, empty pieces, unknown names, bad priorities): same list, or both refuse"""
+    import random
+    from erlref.terms import from_py, to_py
+    from erlamsa_b200.options import string_to_actions
+    r = random.Random(5)
+    dm = [(str(c), int(p)) for c, p in to_py(in_evaluator(lambda: call(ref, "erlamsa_mutations", "default", from_py([]))))]
+    dp = [(str(c), int(p)) for c, p in to_py(in_evaluator(lambda: call(ref, "erlamsa_patterns", "default")))]
+    n_ok = n_bad = 0
+    for it in range(300):
+        table, what = (dm, "mutations") if it % 2 == 0 else (dp, "patterns")
+        names = [c for c, _ in table]
+        toks = []
+        for _ in range(r.randrange(0, 6)):
+            name = r.choice(names) if r.random() < 0.9 else r.choice(["nosuch", "", "x1"])
+            k = r.random()
+            toks.append(name if k < 0.4 else "%s=%d" % (name, r.randrange(0, 40)) if k < 0.85 else name + r.choice(["=", "=2=3", "=x", "=+4", "=-1", "= 5"]))
+        s = ",".join(toks)
+        want = in_evaluator(lambda: call(ref, "erlamsa_cmdparse", "string_to_actions", from_py([ord(c) for c in s]), from_py([ord(c) for c in what]), from_py(table)))
+        try:
+            got = string_to_actions(s, what, table)
+        except ValueError:
+            got = None
+        if want[0] == "ok":
+            assert got == [(str(c), int(p)) for c, p in to_py(want[1])], (s, got, want)
+            n_ok += 1
+        else:
+            assert got is None, (s, got, want)
+            n_bad += 1
+    assert n_ok > 100 and n_bad > 30

@@ -7,8 +7,14 @@ import corpus
 def test_string_to_actions_grammar():
     import erlamsa_b200 as E
     d = E.default_mutations()
-    assert E.string_to_actions("bd,num=3,sr=2", "mutation", d) == [("bd", 1), ("num", 3), ("sr", 2)]
+    # erlamsa_cmdparse:string_to_actions/3: reversed list; a bare code takes its DEFAULT priority (sgm = 10, num = 3, bd = 1)
+    assert E.string_to_actions("bd,num=3,sr=2", "mutation", d) == [("sr", 2), ("num", 3), ("bd", 1)]
+    assert E.string_to_actions("sgm,num,bd=7", "mutation", d) == [("bd", 7), ("num", 3), ("sgm", 10)]
+    assert dict(E.string_to_actions("bd=2,bd=5", "mutation", d)) == {"bd": 2}          # as a map the FIRST entry wins (maps:from_list of the reversed list)
+    assert E.string_to_actions("bd=2=3,,num=", "mutation", d) == [("num", 3), ("bd", 1)]  # string:tokens/2 pieces
     assert E.string_to_actions("default", "mutation", d) == d
+    with pytest.raises(ValueError):
+        E.string_to_actions("bd=x", "mutation", d)
     with pytest.raises(ValueError):
         E.string_to_actions("bd,nope", "mutation", d)
 
