@@ -71,7 +71,10 @@ def fuzzer(opts):
         for x in outs:
             sys.stdout.buffer.write(x)
         return []
-    for k, x in enumerate(outs):                                          # file_writer/1: one file per case, numbered from skip + 1
+    # file_writer/1: one file per case, numbered from skip + 1. (The reference also OPENS -- creates, empty -- the files of the skipped
+    # case numbers 1..skip before discarding the descriptor, src/erlamsa_main.erl:188-191; that side effect is not reproduced: with
+    # skip used for sharding it would mean millions of empty files.)
+    for k, x in enumerate(outs):
         name = _file_name(output, skip + 1 + k)
         d = os.path.dirname(name)
         if d:
