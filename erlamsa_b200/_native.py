@@ -12,6 +12,7 @@ ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.environ.get("EB200_LIB") or os.path.join(PKG_DIR, "liberlamsa_b200.so")   # EB200_LIB: A/B builds of the same engine
 SRC = os.path.join(PKG_DIR, "csrc", "eb_engine.cu")
 SRC_WIDE = os.path.join(PKG_DIR, "csrc", "eb_wide.cu")   # the general kernel once more, for 512 threads / 128 registers
+SRC_ASYNC = os.path.join(PKG_DIR, "csrc", "eb_async.cpp")   # submit / collect lanes (host code only)
 
 N_MUTATORS = 41
 N_PATTERNS = 10
@@ -50,7 +51,7 @@ def build(force=False):
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    subprocess.check_call([nvcc] + NVCC_FLAGS + [SRC, SRC_WIDE, "-o", LIB_PATH])
+    subprocess.check_call([nvcc] + NVCC_FLAGS + [SRC, SRC_WIDE, SRC_ASYNC, "-o", LIB_PATH])
     return LIB_PATH
 
 
@@ -75,6 +76,10 @@ def lib():
                                           vp, C.c_uint64, vp, vp, vp, vp, C.POINTER(Stats)]
     L.eb200_fuzz_batch_into.argtypes = [vp, C.POINTER(Opts), vp, vp, C.c_uint64, C.c_uint64,
                                         vp, C.c_uint64, vp, vp, vp, C.POINTER(Stats)]
+    L.eb200_submit_device.argtypes = [vp, C.POINTER(Opts), vp, vp, C.c_uint64, C.c_uint64, C.c_uint64,
+                                      vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]
+    L.eb200_collect.argtypes = [vp, vp, C.POINTER(Stats)]
+    L.eb200_async_lanes.argtypes = [vp]
     L.eb200_free.argtypes = [vp]
     L.eb200_host_alloc.argtypes = [vp, C.c_uint64]
     L.eb200_host_alloc.restype = vp
@@ -94,5 +99,6 @@ EXPORTED_SYMBOLS = [
     "eb200_fuzz_batch_device", "eb200_mutator_code", "eb200_mutator_default_pri", "eb200_mutator_supported",
     "eb200_pattern_code", "eb200_pattern_default_pri", "eb200_pattern_supported",
     "eb200_strerror", "eb200_last_cuda_error", "eb200_version",
+    "eb200_submit_device", "eb200_collect", "eb200_async_lanes",
     "eb200_sample_donors", "eb200_debug_case_times", "eb200_debug_mutator_times", "eb200_host_alloc", "eb200_host_free", "eb200_numa_node",
 ]

@@ -73,7 +73,10 @@ struct eb200_ctx {
     int numa_node = -1;                    // of the GPU (sysfs), -1 unknown
     bool want_case_times = false; uint64_t case_times_n = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // host-path pipeline (created on first use)
+    void* async_state = nullptr;           // lanes of eb200_submit_device / eb200_collect (eb_async.cpp), created on first submit
 };
+// eb_async.cpp: the submit / collect pair is host code over the entry points of this file; it hangs its lanes on the context here
+extern "C" void eb200_async_teardown(void* state);
 
 // apply-kernel configurations (words per thread, loads in flight per thread, min CTAs/SM); index 0 ships,
 // the others are kept for A/B measurements (env EB200_APPLY_VARIANT)
@@ -240,6 +243,7 @@ int eb200_init(int device, eb200_ctx** out) {
 
 void eb200_shutdown(eb200_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->async_state) { eb200_async_teardown(ctx->async_state); ctx->async_state = nullptr; }   // joins the lane threads first
     cudaSetDevice(ctx->device);
     for (DevBuf* b : {&ctx->cases, &ctx->out_len, &ctx->sz16, &ctx->tile_sum, &ctx->tile_case, &ctx->slot_off, &ctx->temp, &ctx->counters, &ctx->segs, &ctx->scratch, &ctx->data, &ctx->off, &ctx->out, &ctx->out_off, &ctx->meta, &ctx->case_status, &ctx->retry_list, &ctx->case_usec}) b->release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -826,6 +830,10 @@ const char* eb200_strerror(int code) {
     }
 }
 const char* eb200_last_cuda_error(eb200_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
+// internal hooks for eb_async.cpp (not in the public header)
+void** eb200_ctx_async_slot(eb200_ctx* ctx) { return ctx ? &ctx->async_state : nullptr; }
+int eb200_ctx_device(eb200_ctx* ctx) { return ctx ? ctx->device : -1; }
+void eb200_ctx_set_error(eb200_ctx* ctx, const char* msg) { if (ctx && msg) ctx->last_err = msg; }
 const char* eb200_version(void) { return "erlamsa_b200 0.1 (sm_100a)"; }
 
 }  // extern "C"

@@ -88,3 +88,23 @@ class Engine:
             raise self._err(rc)
         self.last_stats = st
         return st
+
+    def submit_device(self, opts, d_data, d_off, n_blobs, data_bytes, n_cases, d_out, out_capacity, d_out_off, d_out_len, d_meta=0):
+        """Asynchronous device path (eb200_submit_device): queues the batch on one of the context's lanes and returns a ticket
+        at once. Every buffer must stay alive, and must not be shared with another batch in flight, until collect(ticket)."""
+        o = opts if isinstance(opts, N.Opts) else make_opts(opts)
+        t = C.c_void_p()
+        rc = N.lib().eb200_submit_device(self._ctx, C.byref(o), d_data, d_off, n_blobs, data_bytes, n_cases,
+                                         d_out, out_capacity, d_out_off, d_out_len, d_meta or None, C.byref(t))
+        if rc != 0:
+            raise self._err(rc)
+        return t
+
+    def collect(self, ticket):
+        """Blocks until the batch behind `ticket` is complete; returns its stats (raises what the synchronous call would have)."""
+        st = N.Stats()
+        rc = N.lib().eb200_collect(self._ctx, ticket, C.byref(st))
+        if rc != 0:
+            raise self._err(rc)
+        self.last_stats = st
+        return st

@@ -46,8 +46,8 @@ extern "C" {
 
 /* eb200_opts.rng_mode */
 #define EB200_RNG_AS183   0   /* OTP `random` (AS183), draw-for-draw identical to the reference */
-#define EB200_RNG_PHILOX  1   /* Philox4x32-10 keyed (seed, case id), counter = draw index: same decision logic,
-                                 distribution-equivalent, no serial state */
+#define EB200_RNG_PHILOX  1   /* Philox4x32-10 keyed (seed, case id) with fixed counter slots (round, who draws, index): same
+                                 decision logic, distribution-equivalent, no serial state -- per-byte draws are lane-parallel */
 
 /* eb200_meta.status (per case) */
 #define EB200_CASE_OK            0
@@ -177,6 +177,29 @@ int  eb200_fuzz_batch_device(eb200_ctx* ctx, const eb200_opts* opts,
                              uint64_t n_cases,
                              uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_off, uint64_t* d_out_len,
                              eb200_meta* d_meta, void* stream, eb200_stats* stats);
+
+/*
+ * Asynchronous pair for the device path (the submit / collect shape sketched in SURVEY.md 8b). eb200_submit_device takes the
+ * arguments of eb200_fuzz_batch_device (minus stream and stats), copies the options, queues the batch and returns at once with a
+ * ticket; eb200_collect blocks until that batch is complete, fills `stats` and returns the batch's own result code (what the
+ * synchronous call would have returned). A context runs submitted batches on EB200_ASYNC_LANES (default 2, at most 4) lanes --
+ * each lane has its own arenas, its own CUDA stream and a host thread -- so while one batch's host side reads its counters back
+ * the next batch's kernel is already running: the stream synchronisations of the synchronous call no longer idle the GPU.
+ *   - batches in flight must not overlap in d_out / d_out_off / d_out_len / d_meta, and a batch must not read what another
+ *     batch in flight writes: lanes are independent streams, there is no ordering between tickets;
+ *   - every buffer of a batch stays valid until its ticket is collected; each ticket is collected exactly once
+ *     (EB200_ERR_ARG for a foreign or already collected ticket); eb200_shutdown waits for batches still queued;
+ *   - results are bit-identical to eb200_fuzz_batch_device (the lanes call it); submit / collect of one context may be called
+ *     from any host thread.
+ */
+typedef struct eb200_ticket eb200_ticket;
+int  eb200_submit_device(eb200_ctx* ctx, const eb200_opts* opts,
+                         const uint8_t* d_data, const uint64_t* d_off, uint64_t n_blobs, uint64_t data_bytes,
+                         uint64_t n_cases,
+                         uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_off, uint64_t* d_out_len,
+                         eb200_meta* d_meta, eb200_ticket** ticket);
+int  eb200_collect(eb200_ctx* ctx, eb200_ticket* ticket, eb200_stats* stats);
+int  eb200_async_lanes(eb200_ctx* ctx);        /* lanes created so far (0 before the first submit) */
 
 /* name surface of the reference (-m / -p codes, src/erlamsa_cmdparse.erl:233-257) */
 const char* eb200_mutator_code(int idx);       /* "sgm", "js", "uw", ... "nil"; NULL when out of range */

@@ -1,0 +1,34 @@
+"""eb200_submit_device / eb200_collect (erlamsa_b200/csrc/eb_async.cpp) on the CPU: the file is host code over the engine's
+synchronous entry point, so it is compiled against a stand-in cuda_runtime.h and a mock engine (tests/mock_cuda/) and its ticket
+protocol, lane overlap, error propagation and teardown are exercised -- once plainly, once under ThreadSanitizer.
+The GPU side (async results == synchronous results, bit for bit) is tests/test_zzz_async_gpu.py."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOCK = os.path.join(ROOT, "tests", "mock_cuda")
+SRC = [os.path.join(ROOT, "erlamsa_b200", "csrc", "eb_async.cpp"), os.path.join(MOCK, "async_harness.cpp")]
+
+
+def build(tmp, extra):
+    exe = os.path.join(tmp, "async_harness" + ("_tsan" if extra else ""))
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-Wall", "-Werror", "-I" + MOCK, "-I" + os.path.join(ROOT, "include")] + extra + SRC + ["-lpthread", "-o", exe])
+    return exe
+
+
+def test_async_lanes_protocol(tmp_path):
+    r = subprocess.run([build(str(tmp_path), [])], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+def test_async_lanes_under_thread_sanitizer(tmp_path):
+    try:
+        exe = build(str(tmp_path), ["-fsanitize=thread"])
+    except subprocess.CalledProcessError:
+        pytest.skip("no ThreadSanitizer runtime in this toolchain")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    if "FATAL: ThreadSanitizer" in r.stderr and "unexpected memory mapping" in r.stderr:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory on this kernel")
+    assert r.returncode == 0 and "OK" in r.stdout and "WARNING: ThreadSanitizer" not in r.stderr, r.stdout + r.stderr
