@@ -54,6 +54,7 @@ struct Opts {
     int gen_random_pri = 1;
     int gen_file_pri = -1;      // paths = files (src/erlamsa_gen.erl:104-121): case picks blob erand(N), lazily split into random-size blocks
     int gen_stdin_pri = -1;     // paths = ["-"] with n == 1 (:92-102): the blob is the stdin data, split lazily like a file
+    int gen_jump_pri = -1;      // >= 2 paths (:123-150): the case's one block = a random slice of a random block of one file ++ the same of another
     std::string ssrf_host = "localhost";   // get_ssrf_ep/0 default, src/erlamsa_mutations.erl:697-702
     int ssrf_port = 51234;
     // cross-seed donor pool for sed_fuse_old (BASELINE config C5; not a reference option, see fuse_old in mutations.hpp)

@@ -178,7 +178,7 @@ struct CaseRunner {
 struct Fuzzer {
     Opts opts; Rng parent; Mutations muts; std::vector<MutNode> fs0;
     std::vector<std::pair<int, int>> sorted_pats; int pat_sum = 0;
-    int generator = 0;   // 0 direct, 1 random, 2 file, 3 stdin (n == 1)
+    int generator = 0;   // 0 direct, 1 random, 2 file, 3 stdin (n == 1), 4 jump
     const uint8_t* corpus_data = nullptr; const uint64_t* corpus_off = nullptr; uint64_t corpus_n = 0;   // for the file generator's path choice
 
     explicit Fuzzer(const Opts& o) : opts(o), muts(parent, opts) {
@@ -188,6 +188,7 @@ struct Fuzzer {
         // make_generator :233-236 + mux_generators :194-199 for paths == [direct]
         std::vector<std::pair<int, int>> gs;                       // {pri, kind}; option order: random, ..., direct
         if (opts.gen_random_pri >= 0) gs.push_back({opts.gen_random_pri, 1});
+        if (opts.gen_jump_pri >= 0) gs.push_back({opts.gen_jump_pri, 4});       // erlamsa_gen:generators/0 :239-246 lists jump between random and direct
         if (opts.gen_direct_pri >= 0) gs.push_back({opts.gen_direct_pri, 0});
         if (opts.gen_file_pri >= 0) gs.push_back({opts.gen_file_pri, 2});
         if (opts.gen_stdin_pri >= 0) gs.push_back({opts.gen_stdin_pri, 3});
@@ -231,6 +232,22 @@ struct Fuzzer {
         finish(rng, n, ll);
         return ll;
     }
+    // jump_somewhere/2 :123-132, forced at the pattern's first uncons/2 (every pattern starts with Ip = rand(24), then uncons/2, whose
+    // function clause calls the fun and whose binary clause makes the result a one-block list, src/erlamsa_utils.erl:89-93): both files
+    // are streamed to the end -- one rand_block_size draw per block and the finish/1 draws, stream_port/5 is not lazy -- and one block
+    // of each is picked; then S1, S2, L1, L2 in that order. rand_elem([]) is [] and size([]) raises: the case's process dies.
+    Bin jump_block(Rng& rng, const Bin& f1, const Bin& f2) {
+        Blocks l1 = stream_blocks(rng, f1);
+        if (l1.empty()) throw CaseDied("jump_somewhere: size([])");
+        const Bin d1 = l1[rng.erand(l1.size()) - 1];
+        Blocks l2 = stream_blocks(rng, f2);
+        // (Data1 is bound before Ll2() runs, but size(Data1) is only evaluated after both: an empty second list dies all the same)
+        if (l2.empty()) throw CaseDied("jump_somewhere: size([])");
+        const Bin d2 = l2[rng.erand(l2.size()) - 1];
+        uint64_t s1 = rng.rand(d1.size()), s2 = rng.rand(d2.size());
+        uint64_t n1 = rng.erand(d1.size() - s1), n2 = rng.erand(d2.size() - s2);
+        return d1.substr(s1, n1) + d2.substr(s2, n2);
+    }
     Blocks generate(Rng& rng, const Bin& input) {
         Blocks ll;
         if (generator == 0) {   // direct_generator :161-164 (split_binary's first clause never matches)
@@ -261,7 +278,14 @@ struct Fuzzer {
         try {
             Blocks ll;
             CaseRunner cr{rng, opts, m, fs0, meta, sorted_pats, pat_sum};
-            if (generator == 2 || generator == 3) {
+            if (generator == 4) {          // jump_streamer :135-150: Path1, Path2 = rand_elem(Paths), the block itself comes later
+                if (!corpus_data || corpus_n < 2) throw Unsupported("jump generator needs two or more files");
+                uint64_t p1 = rng.erand(corpus_n) - 1, p2 = rng.erand(corpus_n) - 1;
+                Bin in1((const char*)corpus_data + corpus_off[p1], corpus_off[p1 + 1] - corpus_off[p1]);
+                Bin in2((const char*)corpus_data + corpus_off[p2], corpus_off[p2 + 1] - corpus_off[p2]);
+                Rng* rp = &rng;
+                cr.lazy = [this, rp, in1, in2]() { Blocks one; one.push_back(jump_block(*rp, in1, in2)); return one; };
+            } else if (generator == 2 || generator == 3) {
                 Bin in = input;
                 if (generator == 2) {      // file_streamer :106-121: P = erand(N) picks the path
                     if (!corpus_data || !corpus_n) throw Unsupported("file generator without a corpus");
@@ -300,6 +324,7 @@ struct eo_opts_c {
     uint64_t max_case_out;
     const uint8_t* donor_pool; const uint32_t* donor_len; uint64_t n_donors; uint32_t donor_stride; uint32_t pad;
     int32_t gen_file_pri, gen_stdin_pri;
+    int32_t gen_jump_pri, pad2;
 };
 struct eo_meta_c {
     int32_t pattern, generator, n_used, n_failed;
@@ -317,7 +342,7 @@ static eo::Opts conv(const eo_opts_c* c) {
     o.gen_direct_pri = c->gen_direct_pri; o.gen_random_pri = c->gen_random_pri;
     o.ssrf_host = std::string(c->ssrf_host, strnlen(c->ssrf_host, 64)); o.ssrf_port = c->ssrf_port;
     if (c->max_case_out) o.max_case_out = c->max_case_out;
-    o.gen_file_pri = c->gen_file_pri; o.gen_stdin_pri = c->gen_stdin_pri;
+    o.gen_file_pri = c->gen_file_pri; o.gen_stdin_pri = c->gen_stdin_pri; o.gen_jump_pri = c->gen_jump_pri;
     o.donor_pool = c->donor_pool; o.donor_len = c->donor_len; o.n_donors = c->n_donors; o.donor_stride = c->donor_stride;
     return o;
 }
@@ -334,7 +359,7 @@ void eo_default_opts(eo_opts_c* c) {
     c->blockscale = 1.0;
     for (int i = 0; i < eo::M_COUNT; i++) c->muta_pri[i] = o.muta_pri[i];
     for (int i = 0; i < eo::P_COUNT; i++) c->pat_pri[i] = o.pat_pri[i];
-    c->gen_direct_pri = 500; c->gen_random_pri = 1; c->gen_file_pri = -1; c->gen_stdin_pri = -1;
+    c->gen_direct_pri = 500; c->gen_random_pri = 1; c->gen_file_pri = -1; c->gen_stdin_pri = -1; c->gen_jump_pri = -1;
     strcpy(c->ssrf_host, "localhost"); c->ssrf_port = 51234;
 }
 

@@ -24,7 +24,8 @@ class Opts(C.Structure):
                 ("gen_direct_pri", C.c_int32), ("gen_random_pri", C.c_int32),
                 ("ssrf_host", C.c_char * 64), ("ssrf_port", C.c_int32), ("max_case_out", C.c_uint64),
                 ("donor_pool", C.c_void_p), ("donor_len", C.c_void_p), ("n_donors", C.c_uint64), ("donor_stride", C.c_uint32), ("pad", C.c_uint32),
-                ("gen_file_pri", C.c_int32), ("gen_stdin_pri", C.c_int32)]
+                ("gen_file_pri", C.c_int32), ("gen_stdin_pri", C.c_int32),
+                ("gen_jump_pri", C.c_int32), ("pad2", C.c_int32)]
 
 
 class Meta(C.Structure):
@@ -91,6 +92,7 @@ def make_opts(seed=(1, 2, 3), mutations=None, patterns=None, blockscale=1.0, gen
         o.gen_random_pri = g.get("random", -1)
         o.gen_file_pri = g.get("file", -1)
         o.gen_stdin_pri = g.get("stdin", -1)
+        o.gen_jump_pri = g.get("jump", -1)
     o.ssrf_host = ssrf_host.encode()
     o.ssrf_port = ssrf_port
     o.max_case_out = max_case_out

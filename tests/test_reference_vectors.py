@@ -167,3 +167,31 @@ def test_engine_matches_reference_file_and_stdin_generators(v, engine):
         json.dump(seen, open(p, "w"), indent=0, sort_keys=True)
     assert not bad, "engine differs from the reference at %r" % bad[:8]
     assert flagged == EXPECTED_FLAGS.get(v["name"], {}), "flagged set changed: %r" % flagged
+
+
+# ---------------------------------------------------------------- jump generator (reference_vectors_jump.json): oracle only
+JUMP_PATH = os.path.join(HERE, "golden", "reference_vectors_jump.json")
+JVEC = json.load(open(JUMP_PATH))["vectors"] if os.path.exists(JUMP_PATH) else []
+
+
+@pytest.mark.parametrize("v", JVEC, ids=[v["name"] for v in JVEC])
+def test_oracle_matches_reference_jump_generator(v, oracle):
+    """src/erlamsa_gen.erl:123-150 -- the engine does not implement this generator (its host mirror refuses the option), the oracle
+    does: every case the reference completes agrees in bytes and draw count, every case whose worker dies there dies here."""
+    blobs = [bytes.fromhex(b) for b in v["files"]]
+    bad = []
+    for idx, i in enumerate(v["cases"]):
+        outs, meta = oracle.fuzzer(blobs, mutations=v["mutations"], patterns=v["patterns"], seed=tuple(v["seed"]), generators=v["generators"], n_cases=1,
+                                   first_case=i, max_case_out=1 << 26, **v["extra"])
+        if v["status"][idx] == "ok":
+            if meta[0].status != 0 or digest(outs[0]) != v["digests"][idx] or meta[0].draws != v["draws"][idx]:
+                bad.append((i, meta[0].status, len(outs[0]), v["digests"][idx][0], meta[0].draws, v["draws"][idx]))
+        elif v["status"][idx] == "died" and meta[0].status != 2:
+            bad.append((i, "reference died", meta[0].status))
+    assert not bad, bad[:8]
+
+
+def test_engine_mirror_refuses_the_jump_generator():
+    import erlamsa_b200
+    with pytest.raises(Exception):
+        erlamsa_b200.make_opts({"generators": {"jump": 100, "file": 1000}})
