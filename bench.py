@@ -44,6 +44,17 @@ WORKLOADS = {
 }
 
 
+def config_of(workload, n_cases, size, rng):
+    """the `config` object of the JSON line: static per workload, so that both arms (--impl ours | reference) print the same one"""
+    desc = WORKLOADS[workload][5]
+    gb = n_cases * size / 1e9
+    l2 = ("inputs larger than L2 (%.2f GB of seeds read and about as much written per step, a new window of case ids every step; 126 MB L2)" % gb
+          if n_cases * size > (126 << 20) else
+          "inputs (%.3f GB per step) fit the 126 MB L2: this workload is bound by the per-case program, not by memory -- see hbm_frac" % gb)
+    return {"workload": desc, "cases_per_gpu_per_step": n_cases, "seed_bytes": size, "rng": rng, "l2_policy": l2,
+            "parallelism": "cases sharded by id, no collective" if workload != "c5" else "cases sharded by id; one all-gather of the donor pool per step"}
+
+
 def ncu_traffic(workload, fused):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture of this
     workload (profiles/<kernel>_<tag>.txt, `ncu --set full`, one launch); None when there is no capture for it."""
@@ -312,9 +323,8 @@ def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local,
         "metric": "mutated testcases/sec", "value": (total_cases - nflag) / (ms * 1e-3), "unit": "cases/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": desc, "cases_per_gpu_per_step": n_cases, "seed_bytes": size, "rng": args.rng,
-                   "l2_policy": "inputs larger than L2 (%.2f GB in + %.2f GB out per step, 126 MB L2)" % (data_bytes / 1e9, out_len_sum / 1e9),
-                   "parallelism": "cases sharded by id, no collective" if workload != "c5" else "cases sharded by id; one all-gather of the donor pool per step"},
+        "config": config_of(workload, n_cases, size, args.rng),
+        "bytes_per_step": {"in": data_bytes, "out": out_len_sum},
         "gb_per_s_mutated": (data_bytes + out_len_sum) * world * steps / (ms * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(workload, fused) if not n_override else None,
@@ -451,7 +461,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "mutated testcases/sec", "value": v, "unit": "cases/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic", "config": {"workload": desc, "sample": sample},
+        "dtype": "u8", "data": "synthetic", "config": config_of(args.workload, args.cases or n_cases, size, args.rng), "sample": sample,
         "cpu_baseline": {"value": v, "unit": "cases/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "cases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
