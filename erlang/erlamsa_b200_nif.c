@@ -90,6 +90,7 @@ static ERL_NIF_TERM fuzz_batch_nif(ErlNifEnv* env, int argc, const ERL_NIF_TERM 
     for (int i = 0; i < 3; i++) { ErlNifSInt64 v; if (!enif_get_int64(env, seed[i], &v)) return err(env, "badarg"); o.seed[i] = v; }
     if (!get_int_list(env, argv[3], o.muta_pri, EB200_N_MUTATORS) || !get_int_list(env, argv[4], o.pat_pri, EB200_N_PATTERNS)) return err(env, "badarg");
     if (!enif_get_uint64(env, argv[5], &first_case) || !enif_get_double(env, argv[6], &blockscale)) return err(env, "badarg");
+    if (first_case == 0 || n_cases > 0xffffffffull) return err(env, "badarg");      /* case numbers are 1-based; the arrays below are sized from n_cases */
     o.first_case = first_case; o.blockscale = blockscale;
     {   /* SSRF endpoint: erlamsa_mutations:get_ssrf_ep/0 (reference src/erlamsa_mutations.erl:697-726) */
         ErlNifBinary host; int port;
