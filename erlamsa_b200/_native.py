@@ -28,7 +28,7 @@ class Opts(C.Structure):
                 ("ssrf_host", C.c_char * 64), ("ssrf_port", C.c_int32), ("rng_mode", C.c_int32),
                 ("first_case", C.c_uint64), ("max_case_out", C.c_uint64), ("scratch_bytes", C.c_uint64),
                 ("donor_pool", C.c_void_p), ("donor_len", C.c_void_p), ("n_donors", C.c_uint64), ("donor_stride", C.c_uint32), ("reserved0", C.c_uint32),
-                ("gen_file_pri", C.c_int32), ("gen_stdin_pri", C.c_int32)]
+                ("gen_file_pri", C.c_int32), ("gen_stdin_pri", C.c_int32), ("gen_jump_pri", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class Meta(C.Structure):
@@ -80,6 +80,7 @@ def lib():
                                       vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]
     L.eb200_collect.argtypes = [vp, vp, C.POINTER(Stats)]
     L.eb200_async_lanes.argtypes = [vp]
+    L.eb200_debug_parent_draws.argtypes = [C.POINTER(Opts), C.c_uint64, C.c_uint64, C.POINTER(C.c_int64)]
     L.eb200_free.argtypes = [vp]
     L.eb200_host_alloc.argtypes = [vp, C.c_uint64]
     L.eb200_host_alloc.restype = vp
@@ -100,5 +101,5 @@ EXPORTED_SYMBOLS = [
     "eb200_pattern_code", "eb200_pattern_default_pri", "eb200_pattern_supported",
     "eb200_strerror", "eb200_last_cuda_error", "eb200_version",
     "eb200_submit_device", "eb200_collect", "eb200_async_lanes",
-    "eb200_sample_donors", "eb200_debug_case_times", "eb200_debug_mutator_times", "eb200_host_alloc", "eb200_host_free", "eb200_numa_node",
+    "eb200_debug_parent_draws", "eb200_sample_donors", "eb200_debug_case_times", "eb200_debug_mutator_times", "eb200_host_alloc", "eb200_host_free", "eb200_numa_node",
 ]

@@ -159,14 +159,16 @@ static int compute_batch_params(const eb200_opts* o, uint64_t n_blobs, uint64_t 
     }
     bp.n_rows = n;
     for (int i = n - 1; i >= 0; i--) { uint64_t s = par.rand(10); bp.row_score[i] = (int)(s < 2 ? 2 : s); }   // mutators_mutator :1390-1395
-    std::vector<std::pair<int, int>> gs;                                 // make_generator for paths == [direct]
+    std::vector<std::pair<int, int>> gs;                                 // make_generator :233-236, in the order of erlamsa_gen:generators/0
     if (o->gen_random_pri >= 0) gs.push_back({o->gen_random_pri, 1});
+    if (o->gen_jump_pri >= 0 && n_blobs > 1) gs.push_back({o->gen_jump_pri, 4});   // `jump when length(Args) > 1` :220
     if (o->gen_direct_pri >= 0) gs.push_back({o->gen_direct_pri, 0});
     if (o->gen_file_pri >= 0) gs.push_back({o->gen_file_pri, 2});
     if (o->gen_stdin_pri >= 0) { if (n_cases != 1 || o->first_case > 1) return EB200_ERR_UNSUPPORTED; gs.push_back({o->gen_stdin_pri, 3}); }
     if (gs.empty()) return EB200_ERR_ARG;
     { auto sg = sort_by_priority(gs); int sum = 0; for (auto& g : sg) sum += g.first;
-      int g = choose_pri(sg, (int64_t)par.rand((uint64_t)sum)); if (g < 0) return EB200_ERR_ARG; bp.generator = g; }
+      int g = choose_pri(sg, (int64_t)par.rand((uint64_t)sum)); if (g < 0) return EB200_ERR_ARG; bp.generator = g;
+      if (g == 4) return EB200_ERR_UNSUPPORTED; }                        // the draw is the reference's; the jump generator itself is not on the device
     std::vector<std::pair<int, int>> ps;                                 // make_pattern: foldl prepends -> reversed table
     for (int i = P_COUNT - 1; i >= 0; i--) if (o->pat_pri[i] >= 0) {
         if (o->pat_pri[i] > 0 && !pat_supported(i)) return EB200_ERR_UNSUPPORTED;
@@ -199,7 +201,7 @@ void eb200_default_opts(eb200_opts* o) {
     o->blockscale = 1.0;
     for (int i = 0; i < EB200_N_MUTATORS; i++) o->muta_pri[i] = kMutPri[i];
     for (int i = 0; i < EB200_N_PATTERNS; i++) o->pat_pri[i] = kPatPri[i];
-    o->gen_direct_pri = 500; o->gen_random_pri = 1; o->gen_file_pri = -1; o->gen_stdin_pri = -1;
+    o->gen_direct_pri = 500; o->gen_random_pri = 1; o->gen_file_pri = -1; o->gen_stdin_pri = -1; o->gen_jump_pri = -1;
     strcpy(o->ssrf_host, "localhost"); o->ssrf_port = 51234;
     o->rng_mode = EB200_RNG_AS183; o->first_case = 1;
 }
@@ -830,6 +832,13 @@ const char* eb200_strerror(int code) {
     }
 }
 const char* eb200_last_cuda_error(eb200_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
+int eb200_debug_parent_draws(const eb200_opts* opts, uint64_t n_blobs, uint64_t n_cases, int64_t out[8]) {
+    if (!opts || !out || n_blobs == 0) return EB200_ERR_ARG;
+    BatchParams bp; int rc = compute_batch_params(opts, n_blobs, n_cases, bp);
+    out[0] = bp.generator; out[1] = bp.snand_kind; out[2] = bp.n_rows; out[3] = bp.n_pats;
+    out[4] = bp.parent_a1; out[5] = bp.parent_a2; out[6] = bp.parent_a3; out[7] = 0;
+    return rc;
+}
 // internal hooks for eb_async.cpp (not in the public header)
 void** eb200_ctx_async_slot(eb200_ctx* ctx) { return ctx ? &ctx->async_state : nullptr; }
 int eb200_ctx_device(eb200_ctx* ctx) { return ctx ? ctx->device : -1; }

@@ -59,8 +59,11 @@ def fuzzer(opts):
             with open(p, "rb") as f:
                 blobs.append(f.read())
         n = int(opts.get("n", 1))
-        if "generators" not in o:                                         # defaults for file paths; `jump` has no device implementation
-            o["generators"] = {"file": 1000, "random": 1}
+        if "generators" not in o:
+            # what make_generator keeps of erlamsa_gen:default/0 for file paths (src/erlamsa_gen.erl:204-237): jump only with two or
+            # more paths. jump takes part in the parent's generator draw as in the reference; a run whose draw lands on it (100 in
+            # 1101) is refused by the engine (EngineError: no device implementation) instead of silently becoming another run.
+            o["generators"] = {"random": 1, "jump": 100, "file": 1000} if len(paths) > 1 else {"random": 1, "file": 1000}
     for k in ("paths", "output", "input", "n", "skip", "stdin_data"):
         o.pop(k, None)
     o["first_case"] = skip + 1

@@ -105,7 +105,8 @@ def make_opts(opts=None):
         o.gen_random_pri = int(g.get("random", -1))
         o.gen_file_pri = int(g.get("file", -1))
         o.gen_stdin_pri = int(g.get("stdin", -1))
-        unknown = set(g) - {"direct", "random", "file", "stdin"}
+        o.gen_jump_pri = int(g.get("jump", -1))      # takes part in the parent's draw; a run that lands on it is refused by the engine
+        unknown = set(g) - {"direct", "random", "file", "stdin", "jump"}
         if unknown:
             raise ValueError("generator(s) without a device implementation: %s" % ", ".join(sorted(unknown)))
     o.ssrf_host = str(opts.get("ssrf_host", "localhost")).encode()[:63]

@@ -85,9 +85,14 @@ typedef struct eb200_opts {
     /* option `generators` for paths that are files / stdin (reference src/erlamsa_gen.erl:59-121, :232-236): `file` (1000) makes every
      * case pick its blob with erand(n_blobs) and cuts it lazily into random-size blocks (256..4095 x blockscale); `stdin` (100000) is
      * the same over blob (I-1) mod n_blobs and is only the reference's behaviour for n == 1 (with n > 1 the reference pre-reads stdin
-     * in the parent process: EB200_ERR_UNSUPPORTED). -1 = not selected (default). `jump` is not implemented. */
+     * in the parent process: EB200_ERR_UNSUPPORTED). -1 = not selected (default). */
     int32_t  gen_file_pri;
     int32_t  gen_stdin_pri;
+    /* `jump` (100; src/erlamsa_gen.erl:123-150, kept by make_generator only when there are two or more paths): it takes part in the
+     * parent's generator draw exactly as in the reference (rand over the priority sum, :194-199), so that a run whose draw lands on
+     * file / random is the reference's run; a run whose draw lands on jump has no device implementation: EB200_ERR_UNSUPPORTED. */
+    int32_t  gen_jump_pri;
+    int32_t  reserved1;
 } eb200_opts;
 
 typedef struct eb200_meta {
@@ -200,6 +205,13 @@ int  eb200_submit_device(eb200_ctx* ctx, const eb200_opts* opts,
                          eb200_meta* d_meta, eb200_ticket** ticket);
 int  eb200_collect(eb200_ctx* ctx, eb200_ticket* ticket, eb200_stats* stats);
 int  eb200_async_lanes(eb200_ctx* ctx);        /* lanes created so far (0 before the first submit) */
+
+/* Host-only aid (no CUDA call, works without a GPU): the parent-process part of erlamsa_main:fuzzer/1 that every batch entry point
+ * restates before it launches anything (src/erlamsa_main.erl:127-163). out[0] = generator chosen
+ * (0 direct, 1 random, 2 file, 3 stdin, 4 jump), out[1] = snand mask kind, out[2] = table rows, out[3] = patterns, out[4..6] = the
+ * parent's AS183 state after its draws (the first case's thread seed is the next three erand(99999)). Returns what the batch call
+ * would return for these options (EB200_ERR_UNSUPPORTED when the draw lands on jump). */
+int eb200_debug_parent_draws(const eb200_opts* opts, uint64_t n_blobs, uint64_t n_cases, int64_t out[8]);
 
 /* name surface of the reference (-m / -p codes, src/erlamsa_cmdparse.erl:233-257) */
 const char* eb200_mutator_code(int idx);       /* "sgm", "js", "uw", ... "nil"; NULL when out of range */

@@ -28,7 +28,7 @@ def test_files_in_files_out(tmp_path, engine, oracle):
     res = erlamsa_main.fuzzer({"paths": paths, "output": str(tmp_path / "out" / "case-%n.fuzz"), "n": n, "seed": (1, 2, 3), "mutations": muts, "patterns": pats,
                                "max_case_out": 1 << 24})
     assert res == []
-    want, wm = oracle.fuzzer(files, mutations=muts, patterns=pats, seed=(1, 2, 3), generators={"file": 1000, "random": 1}, n_cases=n, max_case_out=1 << 24)
+    want, wm = oracle.fuzzer(files, mutations=muts, patterns=pats, seed=(1, 2, 3), generators={"random": 1, "jump": 100, "file": 1000}, n_cases=n, max_case_out=1 << 24)   # the mirror's (= the reference's) defaults for several paths
     for k in range(n):
         got = (tmp_path / "out" / ("case-%d.fuzz" % (k + 1))).read_bytes()
         assert wm[k].status == 0 and got == want[k], k

@@ -191,7 +191,14 @@ def test_oracle_matches_reference_jump_generator(v, oracle):
     assert not bad, bad[:8]
 
 
-def test_engine_mirror_refuses_the_jump_generator():
+def test_engine_refuses_a_run_whose_generator_draw_lands_on_jump():
+    """the option is accepted (it takes part in the parent's draw, tests/test_parent_draws.py); with jump as the only generator the
+    draw can only land on it, and the engine's host code answers EB200_ERR_UNSUPPORTED before anything is launched"""
+    import ctypes as C
     import erlamsa_b200
-    with pytest.raises(Exception):
-        erlamsa_b200.make_opts({"generators": {"jump": 100, "file": 1000}})
+    from erlamsa_b200 import _native as N
+    o = erlamsa_b200.make_opts({"generators": {"jump": 100}, "seed": (1, 2, 3)})
+    out = (C.c_int64 * 8)()
+    assert N.lib().eb200_debug_parent_draws(C.byref(o), 2, 1, out) == -3 and out[0] == 4
+    with pytest.raises(ValueError):
+        erlamsa_b200.make_opts({"generators": {"genfuz": 10000}})
