@@ -32,7 +32,8 @@ def test_async_pair_equals_synchronous_call(engine):
     blobs = corpus.mixed_corpus(0xA51C, 600, max_len=3000)
     n = len(blobs)
     data, off, nbytes = _pack(torch, blobs, dev)
-    muts = {"bd": 1, "bf": 1, "bi": 1, "ber": 1, "num": 3, "ld": 1, "lr2": 1, "sr": 1, "sd": 1, "ui": 1}
+    # no repeat mutators: every result stays near its input size, so no case depends on how full the shared overflow region is
+    muts = {"bd": 1, "bf": 1, "bi": 1, "ber": 1, "num": 3, "ld": 1, "lr2": 1, "sd": 1, "ui": 1}
     nb = 5
     cap = 4 * nbytes + (64 << 20)
     msz = C.sizeof(N.Meta)
