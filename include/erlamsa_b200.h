@@ -63,7 +63,10 @@ typedef struct eb200_opts {
     double   blockscale;                    /* option `blockscale` (default 1.0) */
     int32_t  muta_pri[EB200_N_MUTATORS];    /* option `mutations` [{Code,Pri}]: priority per table row, -1 = not selected */
     int32_t  pat_pri[EB200_N_PATTERNS];     /* option `patterns`  [{Code,Pri}]: -1 = not selected */
-    int32_t  gen_direct_pri;                /* option `generators`: direct (500), -1 = not selected */
+    /* option `generators`: priorities only. make_generator walks the option list as given and sort_by_priority keeps that order among
+     * EQUAL priorities (src/erlamsa_gen.erl:233-236, src/erlamsa_utils.erl:114-117); here equal priorities are resolved as if the list
+     * were in the order of erlamsa_gen:generators/0 (random, jump, direct, file, stdin) -- the reference's defaults have no ties. */
+    int32_t  gen_direct_pri;                /* direct (500), -1 = not selected */
     int32_t  gen_random_pri;                /* option `generators`: random (1),  -1 = not selected */
     char     ssrf_host[64];                 /* cm_host / cm_host_user; default "localhost" */
     int32_t  ssrf_port;                     /* cm_port; default 51234 */

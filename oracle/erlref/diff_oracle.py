@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Differential run: the reference's own source (oracle/erlref evaluator) vs the C++ oracle (oracle/src), on random
 (seed, input, options) triples.  Every divergence is a bug in one of the two to be argued from the .erl text.
-usage: python -m erlref.diff_oracle [--n 2000] [--seed 1] [--procs 8] [--mode default|single|pattern]"""
+usage: python -m erlref.diff_oracle [--n 2000] [--seed 1] [--procs 8] [--mode default|single|pattern|mixed|paths]
+mode paths: fuzzer(#{paths => Files, ...}) -- the file, jump and random generators over random sets of in-memory files, random block scale"""
 import argparse
 import os
 import sys
@@ -68,6 +69,44 @@ def make_case(idx, mode, base_seed):
     return blob, seed, case_no, muts, pats
 
 
+def make_paths_case(idx, base_seed):
+    """random file set + generator list for the file / jump / random generators (src/erlamsa_gen.erl:59-150)"""
+    import corpus
+    r = corpus.rng(base_seed * 1000003 + idx)
+    nf = int(r.integers(1, 6))
+    files = []
+    for _ in range(nf):
+        kind = int(r.integers(0, 6))
+        n = int(r.integers(0, 600)) if r.random() < 0.5 else int(r.integers(600, 12000))
+        if kind == 0:
+            files.append(corpus.random_bytes(r, n))
+        elif kind == 1:
+            files.append(corpus.numeric_text(r, n))
+        elif kind == 2:
+            files.append(corpus.text_lines(r, n))
+        elif kind == 3:
+            files.append(corpus.structured_text(r, max(n, 1)))
+        elif kind == 4:
+            files.append(b"" if r.random() < 0.3 else b"ab"[: int(r.integers(1, 3))])
+        else:
+            files.append(corpus.sgml_doc(r, max(n, 16)))
+    g = int(r.integers(0, 4))
+    # lists in the order of erlamsa_gen:generators/0 (random, jump, direct, file, ...): make_generator walks the option list as given and
+    # sort_by_priority keeps that order among equal priorities; the engine's options carry priorities only, i.e. they mean this order
+    gens = [{"random": 1, "file": 1000}, {"random": 1, "jump": 100, "file": 1000}, {"jump": 100}, {"random": int(r.integers(0, 5)), "jump": int(r.integers(1, 50)), "file": int(r.integers(1, 50))}][g]
+    if nf < 2 and g == 2:
+        gens = {"random": 1, "jump": 100, "file": 1000}      # jump alone with one path leaves "No generators!"
+    seed = (int(r.integers(0, 100000)), int(r.integers(0, 100000)), int(r.integers(0, 100000)))
+    case_no = int(r.integers(1, 30))
+    light = ["bd", "bei", "bf", "bi", "ber", "br", "num", "ld", "lds", "lr2", "lri", "lr", "ls", "lp", "sr", "sd", "sp", "fn", "fo", "ft", "ui", "uw", "ab", "ad", "len", "lis", "lrs"]
+    k = int(r.integers(1, 9))
+    muts = {light[int(i)]: int(r.integers(1, 5)) for i in r.choice(len(light), size=k, replace=False)}
+    kp = int(r.integers(1, 5))
+    pats = {PAT_CODES[int(i)]: int(r.integers(1, 4)) for i in r.choice(10, size=kp, replace=False)}
+    extra = {"blockscale": [0.25, 0.5, 2.0][int(r.integers(0, 3))]} if r.random() < 0.25 else {}
+    return files, gens, seed, case_no, muts, pats, extra
+
+
 _ref = None
 TIME_LIMIT = 45
 
@@ -80,7 +119,10 @@ def work(args):
     import oracle_lib as O
     if _ref is None:
         _ref = Reference()
-    blob, seed, case_no, muts, pats = make_case(idx, mode, base_seed)
+    if mode == "paths":
+        files, gens, seed, case_no, muts, pats, extra = make_paths_case(idx, base_seed)
+    else:
+        blob, seed, case_no, muts, pats = make_case(idx, mode, base_seed)
 
     import signal
 
@@ -92,7 +134,10 @@ def work(args):
     signal.signal(signal.SIGALRM, on_alarm)
     signal.alarm(TIME_LIMIT)
     try:
-        rr = _ref.case(blob, case_no, seed, muts, pats)     # main thread of the pool worker: the alarm can interrupt it
+        if mode == "paths":
+            rr = _ref.case_paths(files, case_no, seed, muts, pats, generators=gens, **extra)
+        else:
+            rr = _ref.case(blob, case_no, seed, muts, pats)     # main thread of the pool worker: the alarm can interrupt it
     except Timeout:
         _ref = None                                         # evaluator state may be inconsistent: start afresh
         return (idx, "skip", "ref=timeout", muts, pats)
@@ -100,7 +145,17 @@ def work(args):
         return (idx, "evaluator-error", repr(e)[:300], muts, pats)
     finally:
         signal.alarm(0)
-    outs, meta = O.fuzzer([blob], mutations=muts, patterns=pats, seed=seed, n_cases=1, first_case=case_no, max_case_out=cap)
+    if mode == "paths":
+        ogens = dict(gens)
+        if len(files) < 2:
+            ogens.pop("jump", None)                       # make_generator_fun: `jump when length(Args) > 1`, otherwise dropped
+        if not ogens:
+            return (idx, "skip", "no generator left", muts, pats)
+        outs, meta = O.fuzzer(files, mutations=muts, patterns=pats, seed=seed, generators=ogens, n_cases=1, first_case=case_no, max_case_out=cap, **extra)
+        if rr.status == "died" and meta[0].status == 2:
+            return (idx, "ok", "", None, None)            # the worker dies on both sides (e.g. jump over an empty block list)
+    else:
+        outs, meta = O.fuzzer([blob], mutations=muts, patterns=pats, seed=seed, n_cases=1, first_case=case_no, max_case_out=cap)
     m = meta[0]
     if rr.status != "ok" or m.status != 0:
         # both sides must agree that the case is outside the comparable class
