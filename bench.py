@@ -275,12 +275,22 @@ def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local,
     e2e = None
     if want_e2e and not args.no_e2e:
         e2e_cases = min(n_cases, args.e2e_cases) if args.e2e_cases else n_cases
-        # host buffers: pinned and on the GPU's NUMA node (eb200_host_alloc), as the NIF's staging rings are
-        in_bytes = e2e_cases * size + 64
-        out_bytes = e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + ((3 << 30) if workload == "c2" else (128 << 20))
-        p_in = N.lib().eb200_host_alloc(eng._ctx, in_bytes)
-        p_out = N.lib().eb200_host_alloc(eng._ctx, out_bytes)
-        assert p_in and p_out, "pinned host allocation failed"
+        # host buffers: pinned and on the GPU's NUMA node (eb200_host_alloc), as the NIF's staging rings are. The whole config's step
+        # needs ~14 GB of pinned memory per rank on C3; if the box cannot pin that much (8 ranks at once), halve the step and say so.
+        p_in = p_out = None
+        while True:
+            in_bytes = e2e_cases * size + 64
+            out_bytes = e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + ((3 << 30) if workload == "c2" else (128 << 20))
+            p_in = N.lib().eb200_host_alloc(eng._ctx, in_bytes)
+            p_out = N.lib().eb200_host_alloc(eng._ctx, out_bytes) if p_in else None
+            if p_in and p_out:
+                break
+            if p_in:
+                N.lib().eb200_host_free(eng._ctx, p_in)
+            assert e2e_cases > 8192, "pinned host allocation failed"
+            e2e_cases //= 2
+        if world > 1:      # every rank runs the same e2e step size
+            t = torch.tensor([e2e_cases], device=dev, dtype=torch.int64); dist.all_reduce(t, op=dist.ReduceOp.MIN); e2e_cases = int(t.item())
         hb = torch.frombuffer((C.c_uint8 * in_bytes).from_address(p_in), dtype=torch.uint8)
         hb[: e2e_cases * size].copy_(data[: e2e_cases * size])
         hoff = (C.c_uint64 * (e2e_cases + 1))(*[i * size for i in range(e2e_cases + 1)])

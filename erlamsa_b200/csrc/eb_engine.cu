@@ -751,7 +751,8 @@ void* eb200_host_alloc(eb200_ctx* ctx, uint64_t bytes) {
             char buf[4096] = {0};
             if (fgets(buf, sizeof(buf), f)) {
                 CPU_ZERO(&node_set); int any = 0;
-                for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+                char* save = nullptr;     // strtok_r: lanes and NIF threads may allocate at the same time
+                for (char* tok = strtok_r(buf, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
                     int a = 0, b = 0; int n = sscanf(tok, "%d-%d", &a, &b); if (n == 1) b = a; if (n < 1) continue;
                     for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &node_set); any = 1; }
                 }
