@@ -1168,9 +1168,22 @@ def install(rt):
     R("zlib", "compress", 1, lambda b: rt.unsupported("zlib:compress"))
     R("zlib", "open", 0, lambda: Ref())
     R("zlib", "close", 1, lambda _z: "ok")
-    R("zlib", "inflateInit", 1, lambda _z: "ok")
-    R("zlib", "inflateInit", 2, lambda _z, _w: "ok")
-    R("zlib", "inflate", 2, lambda _z, b: from_py([z_err(lambda: _zlib.decompress(e_iolist_to_binary(b), -15))]))
+    # inflateInit/1 is the ZLIB format (window bits 15: CMF/FLG header + adler32), not raw deflate; /2 takes the window bits
+    # (negative = raw). inflate/2 is a streaming call: output so far comes back without an error when the input just ends,
+    # invalid data raises data_error.
+    z_wbits = {}
+
+    def z_inflate_init(z, w=15):
+        z_wbits[id(z)] = w
+        return "ok"
+
+    def z_inflate(z, b):
+        d = _zlib.decompressobj(z_wbits.get(id(z), 15))
+        out = z_err(lambda: d.decompress(e_iolist_to_binary(b)))
+        return from_py([out] if out else [])
+    R("zlib", "inflateInit", 1, z_inflate_init)
+    R("zlib", "inflateInit", 2, z_inflate_init)
+    R("zlib", "inflate", 2, z_inflate)
     R("zlib", "inflateEnd", 1, lambda _z: "ok")
     R("zlib", "deflateInit", 1, lambda _z: "ok")
     R("zlib", "deflateInit", 2, lambda _z, _l: "ok")
