@@ -32,3 +32,15 @@ def test_async_lanes_under_thread_sanitizer(tmp_path):
     if "FATAL: ThreadSanitizer" in r.stderr and "unexpected memory mapping" in r.stderr:
         pytest.skip("ThreadSanitizer cannot map its shadow memory on this kernel")
     assert r.returncode == 0 and "OK" in r.stdout and "WARNING: ThreadSanitizer" not in r.stderr, r.stdout + r.stderr
+
+
+def test_python_binding_of_the_async_pair_against_a_mock_library(tmp_path):
+    """Engine.submit_device / Engine.collect (ctypes signatures, ticket handling, error mapping) driven the way the GPU test drives
+    them, against a stand-in library = the real eb_async.cpp over a mock engine whose device memory is host memory"""
+    import sys
+    lib = os.path.join(str(tmp_path), "libmock_erlamsa_b200.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-shared", "-fPIC", "-Wall", "-Werror", "-I" + MOCK, "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "erlamsa_b200", "csrc", "eb_async.cpp"), os.path.join(MOCK, "mock_lib.cpp"), "-lpthread", "-o", lib])
+    env = dict(os.environ, EB200_LIB=lib, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(MOCK, "async_binding_probe.py")], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
