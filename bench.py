@@ -7,7 +7,7 @@ is quoted on): 100 000 x 65 536 B uniform-random seeds, mutators bd,bei,bed,bf,b
 priority 1, pattern od, AS183-exact RNG. Every step mutates the NEXT window of case ids (first_case
 advances), so no step repeats work and the 6.5 GB corpus + 6.5 GB of outputs per step never fit L2.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3num|c2|c4|c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3num|c2|c4|c5] [--async-depth D]
 
 The default (C3) line also carries `parity_sample` (sampled case ids of the last timed step re-run through the oracle),
 `extra_workloads` (short C2 and C4 runs, value net of flagged cases, all-threads CPU port beside them) and, for c5, `collective`.
@@ -316,6 +316,42 @@ def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local,
                "note": "eb200_fuzz_batch_into: pinned NUMA-local host corpus -> H2D (chunks, 2 uploads ahead) -> eb_case_kernel -> D2H of outputs, offsets and lengths"}
         del hb
         N.lib().eb200_host_free(eng._ctx, p_in); N.lib().eb200_host_free(eng._ctx, p_out)
+    # ---- opt-in (--async-depth D): the same steps through eb200_submit_device / eb200_collect with D batches in flight, each with its
+    # own output arena. Lanes run on their own streams, so this is timed by the host clock between two device synchronisations and
+    # reported beside the device-timed synchronous number, never instead of it.
+    async_line = None
+    if args.async_depth > 0 and workload != "c5":
+        try:
+            D = args.async_depth
+            arenas = [(d_out, d_out_off, d_out_len)] + [(torch.empty(out_cap, dtype=torch.uint8, device=dev), torch.empty(n_cases + 1, dtype=torch.int64, device=dev),
+                                                           torch.empty(n_cases, dtype=torch.int64, device=dev)) for _ in range(D - 1)]
+
+            def submit(i):
+                o = dict(base_opts); o["first_case"] = 1 + (20_000 + rank + world * i) * n_cases
+                a = arenas[i % D]
+                return eng.submit_device(o, data.data_ptr(), off.data_ptr(), n_cases, data_bytes, n_cases, a[0].data_ptr(), out_cap, a[1].data_ptr(), a[2].data_ptr())
+            for i in range(max(warmup, D)):
+                eng.collect(submit(i))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            q = []
+            for i in range(steps):
+                if len(q) == D:
+                    eng.collect(q.pop(0))
+                q.append(submit(100 + i))
+            while q:
+                eng.collect(q.pop(0))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+            async_line = {"depth": D, "lanes": N.lib().eb200_async_lanes(eng._ctx), "ms_per_step": dt / steps * 1e3, "value": n_cases * world * steps / dt, "unit": "cases/s",
+                          "timing": "host clock between device synchronisations, max over ranks; the synchronous call's device-timed ms_per_step is this line's own"}
+            del arenas
+        except Exception as e:      # an auxiliary measurement must never cost the line
+            async_line = {"error": repr(e)[:200]}
     del d_out, data
     torch.cuda.empty_cache()
     if rank != 0:
@@ -348,6 +384,8 @@ def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local,
     }
     if parity is not None:
         line["parity_sample"] = parity
+    if async_line is not None:
+        line["async_pair"] = async_line
     if workload == "c5":
         cm = sum(coll_ms) / max(len(coll_ms), 1)
         line["collective"] = {"op": "all_gather (NCCL) of the donor pool + lengths", "ms_per_step": cm, "share_of_step": cm / (ms / steps),
@@ -494,6 +532,7 @@ def main():
     ap.add_argument("--parity-cases", type=int, default=256)
     ap.add_argument("--e2e-cases", type=int, default=0, help="cases per e2e step (0 = the whole config)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--async-depth", type=int, default=0, help="also time the steps through eb200_submit_device / eb200_collect with this many batches in flight (0 = off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
