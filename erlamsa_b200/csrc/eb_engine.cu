@@ -179,6 +179,20 @@ static int compute_batch_params(const eb200_opts* o, uint64_t n_blobs, uint64_t 
     bp.n_pats = (int)sp.size(); bp.pat_sum = 0;
     for (int i = 0; i < bp.n_pats; i++) { bp.pat_pri[i] = sp[i].first; bp.pat_id[i] = sp[i].second; bp.pat_sum += sp[i].first; }
     bp.parent_a1 = par.a1; bp.parent_a2 = par.a2; bp.parent_a3 = par.a3;
+    if (o->case_stream_first) {
+        // A worker of the multi-threaded mode (erlamsa_main.erl:254-280): case I takes the (I - A)-th seed of the stream seeded with S.
+        // The device jumps to case I as x0 * a^(3(I-1)) per AS183 component, so x0 is S's seeded state REWOUND by 3(A-1) steps
+        // (each component is a multiplicative group modulo a prime: the inverse multiplier is a^(p-2)).
+        if (o->first_case < o->case_stream_first) return EB200_ERR_ARG;
+        Rng w; w.mode = 0; w.key = 0; w.ctr_hi = 0; w.draws = 0;
+        w.seed(o->case_stream_seed[0], o->case_stream_seed[1], o->case_stream_seed[2]);
+        auto powmod = [](uint64_t b, uint64_t e, uint64_t p) { uint64_t r = 1; b %= p; while (e) { if (e & 1) r = r * b % p; b = b * b % p; e >>= 1; } return r; };
+        auto rewind = [&](uint64_t x, uint64_t mul, uint64_t p, uint64_t steps) { return x * powmod(powmod(mul, p - 2, p), steps % (p - 1), p) % p; };
+        uint64_t steps = 3 * (o->case_stream_first - 1);
+        bp.parent_a1 = (int32_t)rewind((uint64_t)w.a1, 171, 30269, steps);
+        bp.parent_a2 = (int32_t)rewind((uint64_t)w.a2, 172, 30307, steps);
+        bp.parent_a3 = (int32_t)rewind((uint64_t)w.a3, 170, 30323, steps);
+    }
     bp.rng_mode = o->rng_mode;
     bp.philox_key = ((uint64_t)(uint32_t)o->seed[0] * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(uint32_t)o->seed[1] << 32) ^ (uint64_t)(uint32_t)o->seed[2] * 0xD1B54A32D192ED03ull;
     double bs = o->blockscale > 0 ? o->blockscale : 1.0;

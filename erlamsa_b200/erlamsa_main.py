@@ -10,6 +10,8 @@ CUDA engine, for the generators and outputs that are part of the hot path's surr
     output => return                                -> [binary()], empty results dropped like record_result/2 (:120-122)
     output => "out/fuzz-%n.bin"                     file writer (src/erlamsa_out.erl:103-123): %n = case number; returns []
                                                      like the reference does for non-direct outputs
+    workers => W, workers_same_seed => Bool         with a file output and n > 1: the reference's multi-threaded mode (:88-111,254-280) --
+                                                     every worker's case range is one engine batch seeded the way that worker process is
 
 `fuzz/1` is the spelling BASELINE.json's north star uses for the same entry.
 """
@@ -17,6 +19,7 @@ import os
 import sys
 
 from .engine import Engine
+from .workers import worker_plan
 
 _engine = None
 
@@ -39,7 +42,13 @@ def fuzzer(opts):
     output = opts.get("output", "-")
     if output != "return" and not isinstance(output, str):
         raise NotImplementedError("network / exec outputs stay in Erlang (SURVEY.md section 2)")
+    for k in ("sequence_muta", "external_mutations", "external_post", "external_generator"):
+        if opts.get(k):      # the Erlang shim routes these option maps to the untouched reference (erlang/erlamsa_b200.erl supported/1)
+            raise NotImplementedError("option `%s` has no device implementation" % k)
     o = dict(opts)
+    if "seed" not in o:      # the reference falls back to gen_urandom_seed/0 (src/erlamsa_rnd.erl:50-62); fixed here so that the workers' plan sees it
+        r = os.urandom(6)
+        o["seed"] = opts["seed"] = tuple(int.from_bytes(r[i:i + 2], "big") for i in (0, 2, 4))
     skip = int(opts.get("skip", 0))
     if paths == ["direct"]:
         inp = opts.get("input")
@@ -64,8 +73,17 @@ def fuzzer(opts):
             # more paths. jump takes part in the parent's generator draw as in the reference; a run whose draw lands on it (100 in
             # 1101) is refused by the engine (EngineError: no device implementation) instead of silently becoming another run.
             o["generators"] = {"random": 1, "jump": 100, "file": 1000} if len(paths) > 1 else {"random": 1, "file": 1000}
-    for k in ("paths", "output", "input", "n", "skip", "stdin_data"):
+    plan = worker_plan(opts["seed"], output, n, int(opts.get("workers", 1)), bool(opts.get("workers_same_seed", False))) 
+    for k in ("paths", "output", "input", "n", "skip", "stdin_data", "workers", "workers_same_seed"):
         o.pop(k, None)
+    if plan is not None:
+        # multi-threaded mode: file output only (threading_mode), so every case goes to its own file; cases <= skip are run (their seeds
+        # are drawn all the same) but not written
+        for wseed, first, cnt, stream_first in plan:
+            ow = dict(o, first_case=first, case_stream=(wseed, stream_first))
+            outs, _meta = _get_engine().fuzz_batch(blobs, ow, n_cases=cnt)
+            _write_files(output, [(first + k, x) for k, x in enumerate(outs) if first + k > skip])
+        return []
     o["first_case"] = skip + 1
     outs, _meta = _get_engine().fuzz_batch(blobs, o, n_cases=max(n - skip, 0))
     if output == "return":
@@ -77,14 +95,18 @@ def fuzzer(opts):
     # file_writer/1: one file per case, numbered from skip + 1. (The reference also OPENS -- creates, empty -- the files of the skipped
     # case numbers 1..skip before discarding the descriptor, src/erlamsa_main.erl:188-191; that side effect is not reproduced: with
     # skip used for sharding it would mean millions of empty files.)
-    for k, x in enumerate(outs):
-        name = _file_name(output, skip + 1 + k)
+    _write_files(output, [(skip + 1 + k, x) for k, x in enumerate(outs)])
+    return []
+
+
+def _write_files(template, numbered):
+    for i, x in numbered:
+        name = _file_name(template, i)
         d = os.path.dirname(name)
         if d:
             os.makedirs(d, exist_ok=True)
         with open(name, "wb") as f:
             f.write(x)
-    return []
 
 
 fuzz = fuzzer

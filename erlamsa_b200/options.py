@@ -109,6 +109,10 @@ def make_opts(opts=None):
         unknown = set(g) - {"direct", "random", "file", "stdin", "jump"}
         if unknown:
             raise ValueError("generator(s) without a device implementation: %s" % ", ".join(sorted(unknown)))
+    if opts.get("case_stream") is not None:       # (worker seed, number of the worker's first case): one worker of `workers` > 1
+        (a, b, c), first = opts["case_stream"]
+        o.case_stream_seed[0], o.case_stream_seed[1], o.case_stream_seed[2] = int(a), int(b), int(c)
+        o.case_stream_first = int(first)
     o.ssrf_host = str(opts.get("ssrf_host", "localhost")).encode()[:63]
     o.ssrf_port = int(opts.get("ssrf_port", 51234))
     o.rng_mode = {"as183": 0, "philox": 1}[opts.get("rng", "as183")]

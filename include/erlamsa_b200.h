@@ -96,6 +96,14 @@ typedef struct eb200_opts {
      * file / random is the reference's run; a run whose draw lands on jump has no device implementation: EB200_ERR_UNSUPPORTED. */
     int32_t  gen_jump_pri;
     int32_t  reserved1;
+    /* Multi-threaded mode of the reference (option `workers` > 1 with a file / network output, run_fuzzing_loop/7, src/erlamsa_main.erl:
+     * 254-280): every worker process is re-seeded with its own seed S (the W-th gen_predictable_seed() of the re-seeded parent, or the
+     * run's seed with `workers_same_seed`) and draws the thread seed of ITS first case, number A, as the first three draws of that
+     * stream, while the mutator table, generator and pattern list made by the parent are shared. One worker = one batch with
+     * case_stream_seed = S, case_stream_first = A (> 0 switches it on) and first_case >= A: case I takes the (I - A)-th seed of
+     * the stream. 0 = the single-threaded numbering (case I = the I-th seed of the parent stream). */
+    int64_t  case_stream_seed[3];
+    uint64_t case_stream_first;
 } eb200_opts;
 
 typedef struct eb200_meta {

@@ -1010,11 +1010,25 @@ def install(rt):
     rt.vfs = {}
     rt.stdin = FileHandle(b"")
 
-    def f_open(path, _modes):
+    rt.vfs_out = {}                       # files written by the run (erlamsa_out:file_writer/1, -o "dir/%n"): name -> bytes
+
+    class OutHandle(object):
+        def __init__(self, name):
+            self.name = name
+            rt.vfs_out[name] = b""
+
+    def f_open(path, modes):
         name = chars_to_str(path)
+        if "write" in [m for m in to_py(modes) if isinstance(m, str)]:
+            return ("ok", OutHandle(name))
         if name not in rt.vfs:
             return ("error", "enoent")
         return ("ok", FileHandle(rt.vfs[name]))
+
+    def f_write(fd, data):
+        if isinstance(fd, OutHandle):
+            rt.vfs_out[fd.name] += e_iolist_to_binary(data)
+        return "ok"
 
     def f_read(fd, n):
         h = rt.stdin if fd == "standard_io" else fd
@@ -1028,7 +1042,7 @@ def install(rt):
     R("file", "open", 2, f_open)
     R("file", "read", 2, f_read)
     R("file", "close", 1, lambda _fd: "ok")
-    R("file", "write", 2, lambda _fd, _d: "ok")
+    R("file", "write", 2, f_write)
     R("file", "write_file", 2, lambda _p, _d: "ok")
     R("file", "write_file", 3, lambda _p, _d, _m: "ok")
     R("timer", "sleep", 1, lambda _t: "ok")
@@ -1072,10 +1086,16 @@ def install(rt):
 
     # erlamsa_logger is a process-based logger outside the hot path: calls are no-ops here
     rt.logged_data = []
+    rt.logged_cases = {}                   # case number I -> written bytes (the [I, N] argument list of the same call)
 
     def log_data(*a):
         if a and type(a[-1]) is bytes:
             rt.logged_data.append(a[-1])       # erlamsa_main logs every written test case (:199): the harness reads it back here
+            if len(a) >= 2:
+                try:
+                    rt.logged_cases[to_py(a[-2])[0]] = a[-1]
+                except Exception:
+                    pass
         return "ok"
     for ar in (2, 3, 4, 5):
         R("erlamsa_logger", "log", ar, lambda *a: "ok")
@@ -1200,6 +1220,11 @@ def install(rt):
     R("zip", "unzip", 2, lambda data, _o: rt.unsupported("zip:unzip") if (type(data) is bytes and b"PK\x05\x06" in data) else ("error", "bad_eocd"))
     R("zip", "zip", 3, lambda *_a: rt.unsupported("zip:zip"))
 
+    # re: only what erlamsa_out:file_writer/1 does with its "%n" template (compile/1, split/2: binaries, empty trailing piece kept)
+    import re as _re
+    R("re", "compile", 1, lambda p: ("ok", ("re_pattern", _re.compile(_re.escape(e_iolist_to_binary(p)) if e_iolist_to_binary(p) == b"%n" else e_iolist_to_binary(p)))))
+    R("re", "split", 2, lambda subj, mp: from_py(list(mp[1].split(e_iolist_to_binary(subj)))))
+
     class Unsupported(RuntimeError):
         pass
     rt.Unsupported = Unsupported
@@ -1209,4 +1234,4 @@ def install(rt):
     rt.unsupported = unsupported
 
     rt.python_only_modules = {"erlang", "lists", "maps", "random", "gb_trees", "io_lib", "io", "file", "timer", "crypto", "math", "ets",
-                              "inet", "erlamsa_logger", "string", "base64", "zlib", "zip", "os"}
+                              "inet", "erlamsa_logger", "string", "base64", "zlib", "zip", "os", "re"}

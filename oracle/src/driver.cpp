@@ -325,6 +325,7 @@ struct eo_opts_c {
     const uint8_t* donor_pool; const uint32_t* donor_len; uint64_t n_donors; uint32_t donor_stride; uint32_t pad;
     int32_t gen_file_pri, gen_stdin_pri;
     int32_t gen_jump_pri, pad2;
+    int64_t case_stream_seed[3]; uint64_t case_stream_first;   // --workers: see eo_fuzzer
 };
 struct eo_meta_c {
     int32_t pattern, generator, n_used, n_failed;
@@ -376,7 +377,16 @@ static void* run_thread(void* p) {
         eo::Fuzzer f(conv(a->opts));
         f.corpus_data = a->data; f.corpus_off = a->off; f.corpus_n = a->n_blobs;
         eo::Meta skip;
-        for (uint64_t i = 1; i < a->first_case; i++) { int64_t ts[3]; f.parent.gen_predictable_seed(ts); }
+        uint64_t stream_first = 1;
+        if (a->opts->case_stream_first) {
+            // multi-threaded mode, run_fuzzing_loop/7 (src/erlamsa_main.erl:254-280): a worker process is re-seeded with its own seed S and
+            // FuzzingLoop draws the thread seed of its first case (number A) as the FIRST draws of that stream; the mutator table, the
+            // generator and the pattern list were made by the parent before and are shared
+            f.parent.seed(a->opts->case_stream_seed[0], a->opts->case_stream_seed[1], a->opts->case_stream_seed[2]);
+            stream_first = a->opts->case_stream_first;
+            if (a->first_case < stream_first) throw std::runtime_error("first_case before the worker's first case");
+        }
+        for (uint64_t i = stream_first; i < a->first_case; i++) { int64_t ts[3]; f.parent.gen_predictable_seed(ts); }
         a->out_off[0] = 0;
         for (uint64_t k = 0; k < a->n_cases; k++) {
             uint64_t b = (a->first_case - 1 + k) % a->n_blobs;

@@ -25,7 +25,8 @@ class Opts(C.Structure):
                 ("ssrf_host", C.c_char * 64), ("ssrf_port", C.c_int32), ("max_case_out", C.c_uint64),
                 ("donor_pool", C.c_void_p), ("donor_len", C.c_void_p), ("n_donors", C.c_uint64), ("donor_stride", C.c_uint32), ("pad", C.c_uint32),
                 ("gen_file_pri", C.c_int32), ("gen_stdin_pri", C.c_int32),
-                ("gen_jump_pri", C.c_int32), ("pad2", C.c_int32)]
+                ("gen_jump_pri", C.c_int32), ("pad2", C.c_int32),
+                ("case_stream_seed", C.c_int64 * 3), ("case_stream_first", C.c_uint64)]
 
 
 class Meta(C.Structure):
@@ -71,7 +72,7 @@ def lib():
 
 
 def make_opts(seed=(1, 2, 3), mutations=None, patterns=None, blockscale=1.0, generators=None,
-              ssrf_host="localhost", ssrf_port=51234, max_case_out=0, donors=None):
+              ssrf_host="localhost", ssrf_port=51234, max_case_out=0, donors=None, case_stream=None):
     """mutations / patterns: None = reference defaults, else dict or list of (code, pri) -- the
     reference's `[{Code, Pri}]` option lists (src/erlamsa_main.erl:129,156)."""
     o = Opts()
@@ -93,6 +94,9 @@ def make_opts(seed=(1, 2, 3), mutations=None, patterns=None, blockscale=1.0, gen
         o.gen_file_pri = g.get("file", -1)
         o.gen_stdin_pri = g.get("stdin", -1)
         o.gen_jump_pri = g.get("jump", -1)
+    if case_stream is not None:
+        # (worker seed {A,B,C}, number of the worker's first case): --workers, src/erlamsa_main.erl:254-280
+        (o.case_stream_seed[0], o.case_stream_seed[1], o.case_stream_seed[2]), o.case_stream_first = case_stream
     o.ssrf_host = ssrf_host.encode()
     o.ssrf_port = ssrf_port
     o.max_case_out = max_case_out
