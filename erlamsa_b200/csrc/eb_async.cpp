@@ -9,7 +9,6 @@
 //
 // Host code only: nothing here launches a kernel of its own.
 #include <cuda_runtime.h>
-#include <atomic>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -36,7 +35,7 @@ struct Job {
     uint8_t* d_out; uint64_t out_capacity; uint64_t* d_out_off; uint64_t* d_out_len; eb200_meta* d_meta;
     eb200_stats stats;
     int rc = EB200_OK;
-    bool done = false, collected = false;
+    bool done = false;
     std::string err;
     struct Lane* lane = nullptr;
 };
