@@ -20,6 +20,15 @@
 // ~47k SASS instructions whose instruction-cache misses were a third of all stall samples
 // (profiles/decide_r1a). Calls are cheap next to an FP64 RNG draw.
 #define EB_DEV __device__ __noinline__
+// The general program's scalar parts are executed by all 32 lanes, which read-modify-write the same shared words (counters of the
+// block-run / segment tables): right only while the warp is converged. EB_RECONVERGE() marks the entry of every such helper. It is
+// empty in the shipped kernel -- whose results are pinned by the GPU suite -- and a __syncwarp() in the 128-register build of
+// eb_wide.cu (the experiment that says whether a lost reconvergence explains that build's differences).
+#ifdef EB_WIDE_RECONVERGE
+#define EB_RECONVERGE() __syncwarp()
+#else
+#define EB_RECONVERGE()
+#endif
 
 namespace eb {
 

@@ -24,17 +24,20 @@ EB_DEV bool active_is_single_empty(const WarpState* ws) {   // Ll =:= [<<>>]
     return ws->vhead ? ws->vlen == 0 : ws->runs[0].len == 0;
 }
 EB_DEV void runs_insert_front(WarpState* ws, Blk b) {
+    EB_RECONVERGE();
     if (b.cnt == 0) return;
     if (ws->nruns >= MAX_RUNS) { ws->status = CASE_OVERFLOW; ws->reason = 4; return; }
     for (int i = ws->nruns; i > 0; i--) ws->runs[i] = ws->runs[i - 1];
     ws->runs[0] = b; ws->nruns++;
 }
 EB_DEV void runs_push_back(WarpState* ws, Blk b) {
+    EB_RECONVERGE();
     if (b.cnt == 0) return;
     if (ws->nruns >= MAX_RUNS) { ws->status = CASE_OVERFLOW; ws->reason = 4; return; }
     ws->runs[ws->nruns++] = b;
 }
 EB_DEV void pop_head(WarpState* ws) {
+    EB_RECONVERGE();
     if (ws->runs[0].cnt > 1) { ws->runs[0].p += ws->runs[0].len; ws->runs[0].cnt--; return; }
     for (int i = 1; i < ws->nruns; i++) ws->runs[i - 1] = ws->runs[i];
     ws->nruns--;
@@ -144,6 +147,7 @@ EB_DEV void mux_fuzzers(CaseCtx& c) {
                 Seg s0 = seg_copy(ws->rrun[0].p, ws->rrun[0].len);
                 changed = !(ws->rrun[0].len == n && segs_equal_prefix(&s0, 1, p, n));
             }
+            EB_RECONVERGE();
             if (!changed) { ws->n_failed++; continue; }
             if (r.kind == RES_SEGS && ws->tlen > c.bp->max_case_out) { ws->status = CASE_OVERFLOW; ws->reason = 5; return; }
             if (ws->n_used < 16) ws->used[ws->n_used] = row.name;
@@ -394,6 +398,7 @@ EB_DEV void run_case_machine(CaseCtx& c, int pat) {
             if (ws->status != CASE_OK) return;
             if (found) {
                 w.mark = ws->olen;
+                EB_RECONVERGE();
                 ws->wrap[ws->nwrap++] = w;
                 Blk blob; blob.p = p0 + b0; blob.len = bl; blob.cnt = 1;
                 pop_head(ws); runs_insert_front(ws, blob);

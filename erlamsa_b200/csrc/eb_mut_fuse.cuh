@@ -703,6 +703,7 @@ EB_DEV void mut_fuse(CaseCtx& c, int id, const uint8_t* p, uint32_t n, MutResult
     r.delta = g.rand_delta();
     if (swap == 0) { ws->fo_p = p; ws->fo_n = n; }
     // flush_bvecs(A, flush_bvecs(B, T)): two re-chunked regions -> handed back as block runs
+    EB_RECONVERGE();
     ws->rrun_n = 0;
     { uint32_t k = an / AVG_BLOCK_SIZE; Blk f; f.p = ab; f.len = AVG_BLOCK_SIZE; f.cnt = k; if (k) ws->rrun[ws->rrun_n++] = f;
       Blk l; l.p = ab + (uint64_t)k * AVG_BLOCK_SIZE; l.len = an - k * AVG_BLOCK_SIZE; l.cnt = 1; ws->rrun[ws->rrun_n++] = l; }

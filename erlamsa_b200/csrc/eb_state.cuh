@@ -132,6 +132,7 @@ __device__ __forceinline__ Seg seg_fill(uint8_t b, uint32_t len) { Seg s; s.src 
 // candidate list (tseg) builder; zero-length segments are dropped, adjacent copies coalesce
 __device__ __forceinline__ void t_reset(WarpState* ws) { ws->ntseg = 0; ws->tlen = 0; }
 EB_DEV void t_push(WarpState* ws, Seg s) {
+    EB_RECONVERGE();
     if (s.len == 0) return;
     int n = ws->ntseg;
     if (n > 0 && s.kind() == SEG_COPY && ws->tseg[n - 1].kind() == SEG_COPY && ws->tseg[n - 1].src + ws->tseg[n - 1].len == s.src) {
@@ -242,6 +243,7 @@ EB_DEV void segs_write_stream(JobQ* q, const Seg* s, int n, uint8_t* dst, const 
 // append to the output edit script; when the script is full it is folded into one scratch buffer
 EB_DEV void o_push(CaseCtx& c, Seg s) {
     WarpState* ws = c.ws;
+    EB_RECONVERGE();
     if (s.len == 0) return;
     int n = ws->noseg;
     if (n > 0 && s.kind() == SEG_COPY && ws->oseg[n - 1].kind() == SEG_COPY && ws->oseg[n - 1].src + ws->oseg[n - 1].len == s.src

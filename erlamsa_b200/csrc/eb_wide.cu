@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstddef>
 #define EB_CASE_THREADS 512
+#define EB_WIDE_RECONVERGE 1        // EB_RECONVERGE() = __syncwarp() in this build only (eb_common.cuh)
 #define eb ebw                      // every device symbol of this translation unit lives in its own namespace
 #include "../../include/erlamsa_b200.h"
 #include "eb_fast.cuh"
