@@ -170,6 +170,9 @@ struct CaseRunner {
         }
         // P_CP: mutate_once_compressed :217-260, non-compressed input only
         if (maybe_compressed(bin)) throw Unsupported("cp pattern on compressed-looking data");
+        // a block too short to hold the two header bytes: zlib:inflate/2 is a streaming call and answers [] instead of raising, so the
+        // reference takes the compressed branch (mutates <<>> and deflates it) -- not restated, and the engine passes the block through
+        if (bin.size() < 2) throw Unsupported("cp pattern on a block shorter than a zlib header");
         split_big(bin, rest);
         return mutate_once_loop(cont_pat(next), ip, bin, rest);
     }
