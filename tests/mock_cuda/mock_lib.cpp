@@ -47,7 +47,23 @@ int eb200_fuzz_batch_device(eb200_ctx*, const eb200_opts* o, const uint8_t* d_da
     if (st) { memset(st, 0, sizeof(*st)); st->n_cases = n_cases; st->kernels_launched = 5; st->bytes_out = pos; }
     return EB200_OK;
 }
-int eb200_fuzz_batch(eb200_ctx*, const eb200_opts*, const uint8_t*, const uint64_t*, uint64_t, uint64_t, uint8_t**, uint64_t*, uint64_t*, eb200_meta*, eb200_stats*) { return EB200_ERR_NO_DEVICE; }
+// host-buffer batch of the mock: case I = first_case + k gives blob (I-1) mod n_blobs with every byte XOR (I + case_stream_seed[0] + 7 * case_stream_first)
+int eb200_fuzz_batch(eb200_ctx*, const eb200_opts* o, const uint8_t* data, const uint64_t* off, uint64_t n_blobs, uint64_t n_cases, uint8_t** out_data, uint64_t* out_off,
+                     uint64_t* out_len, eb200_meta* meta, eb200_stats* st) {
+    uint64_t first = o->first_case ? o->first_case : 1, total = 0;
+    for (uint64_t k = 0; k < n_cases; k++) { uint64_t b = (first - 1 + k) % n_blobs; total += off[b + 1] - off[b]; }
+    uint8_t* out = (uint8_t*)malloc(total ? total : 1); uint64_t pos = 0;
+    for (uint64_t k = 0; k < n_cases; k++) {
+        uint64_t i = first + k, b = (i - 1) % n_blobs, len = off[b + 1] - off[b];
+        uint8_t x = (uint8_t)(i + (uint64_t)o->case_stream_seed[0] + 7 * o->case_stream_first);
+        for (uint64_t j = 0; j < len; j++) out[pos + j] = data[off[b] + j] ^ x;
+        out_off[k] = pos; out_len[k] = len; pos += len;
+        if (meta) memset(&meta[k], 0, sizeof(eb200_meta));
+    }
+    out_off[n_cases] = pos; *out_data = out;
+    if (st) { memset(st, 0, sizeof(*st)); st->n_cases = n_cases; }
+    return EB200_OK;
+}
 int eb200_fuzz_batch_into(eb200_ctx*, const eb200_opts*, const uint8_t*, const uint64_t*, uint64_t, uint64_t, uint8_t*, uint64_t, uint64_t*, uint64_t*, eb200_meta*, eb200_stats*) { return EB200_ERR_NO_DEVICE; }
 int eb200_sample_donors(eb200_ctx*, const uint8_t*, const uint64_t*, uint64_t, uint64_t, uint32_t, uint8_t*, uint32_t*, void*) { return EB200_ERR_NO_DEVICE; }
 void* eb200_host_alloc(eb200_ctx*, uint64_t) { return nullptr; }

@@ -44,3 +44,6 @@ def test_python_binding_of_the_async_pair_against_a_mock_library(tmp_path):
     env = dict(os.environ, EB200_LIB=lib, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     r = subprocess.run([sys.executable, os.path.join(MOCK, "async_binding_probe.py")], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+    # the same stand-in library under the host mirror's multi-threaded mode (erlamsa_main.py + workers.py): plan, batches, file numbering, skip
+    r = subprocess.run([sys.executable, os.path.join(MOCK, "workers_mirror_probe.py")], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
