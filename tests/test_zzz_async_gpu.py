@@ -6,7 +6,8 @@ import pytest
 
 import corpus
 
-pytestmark = pytest.mark.gpu
+# the timeout's thread method ends the run instead of hanging it if a lane never comes back (a blocked C call cannot be interrupted by a signal)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method="thread")]
 
 
 def _pack(torch, blobs, dev):
