@@ -273,49 +273,54 @@ def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local,
 
     # ---- e2e: the C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
+    e2e_error = None
     if want_e2e and not args.no_e2e:
-        e2e_cases = min(n_cases, args.e2e_cases) if args.e2e_cases else n_cases
-        # host buffers: pinned and on the GPU's NUMA node (eb200_host_alloc), as the NIF's staging rings are. The whole config's step
-        # needs ~14 GB of pinned memory per rank on C3; if the box cannot pin that much (8 ranks at once), halve the step and say so.
-        p_in = p_out = None
-        while True:
-            in_bytes = e2e_cases * size + 64
-            out_bytes = e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + ((3 << 30) if workload == "c2" else (128 << 20))
-            p_in = N.lib().eb200_host_alloc(eng._ctx, in_bytes)
-            p_out = N.lib().eb200_host_alloc(eng._ctx, out_bytes) if p_in else None
-            if p_in and p_out:
-                break
-            if p_in:
-                N.lib().eb200_host_free(eng._ctx, p_in)
-            assert e2e_cases > 8192, "pinned host allocation failed"
-            e2e_cases //= 2
-        if world > 1:      # every rank runs the same e2e step size
-            t = torch.tensor([e2e_cases], device=dev, dtype=torch.int64); dist.all_reduce(t, op=dist.ReduceOp.MIN); e2e_cases = int(t.item())
-        hb = torch.frombuffer((C.c_uint8 * in_bytes).from_address(p_in), dtype=torch.uint8)
-        hb[: e2e_cases * size].copy_(data[: e2e_cases * size])
-        hoff = (C.c_uint64 * (e2e_cases + 1))(*[i * size for i in range(e2e_cases + 1)])
-        ho_off = (C.c_uint64 * (e2e_cases + 1))(); ho_len = (C.c_uint64 * e2e_cases)()
-        st2 = N.Stats()
-        o = erlamsa_b200.make_opts(base_opts)
-        times = []
-        for i in range(args.e2e_steps + 1):
-            o.first_case = 1 + (10_000 + rank + world * i) * n_cases
-            t0 = time.perf_counter()
-            rc = N.lib().eb200_fuzz_batch_into(eng._ctx, C.byref(o), p_in, C.cast(hoff, C.c_void_p), e2e_cases, e2e_cases,
-                                               p_out, out_bytes, C.cast(ho_off, C.c_void_p), C.cast(ho_len, C.c_void_p), None, C.byref(st2))
-            t1 = time.perf_counter()
-            assert rc == 0, rc
-            if i > 0:
-                times.append(t1 - t0)
-        dt = max(times)
-        if world > 1:
-            t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
-        h2d_b, d2h_b = e2e_cases * size + 8 * (e2e_cases + 1), int(sum(ho_len)) + 16 * e2e_cases + 8
-        e2e = {"value": e2e_cases * world / dt, "unit": "cases/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
-               "cases_per_step": e2e_cases * world, "pcie_gb_per_s_each_way": [h2d_b / dt / 1e9, d2h_b / dt / 1e9], "numa_node_of_gpu": N.lib().eb200_numa_node(eng._ctx),
-               "note": "eb200_fuzz_batch_into: pinned NUMA-local host corpus -> H2D (chunks, 2 uploads ahead) -> eb_case_kernel -> D2H of outputs, offsets and lengths"}
-        del hb
-        N.lib().eb200_host_free(eng._ctx, p_in); N.lib().eb200_host_free(eng._ctx, p_out)
+        try:
+            e2e_cases = min(n_cases, args.e2e_cases) if args.e2e_cases else n_cases
+            # host buffers: pinned and on the GPU's NUMA node (eb200_host_alloc), as the NIF's staging rings are. The whole config's step
+            # needs ~14 GB of pinned memory per rank on C3; if the box cannot pin that much (8 ranks at once), halve the step and say so.
+            p_in = p_out = None
+            while True:
+                in_bytes = e2e_cases * size + 64
+                out_bytes = e2e_cases * size + e2e_cases * size // 12 + 512 * e2e_cases + ((3 << 30) if workload == "c2" else (128 << 20))
+                p_in = N.lib().eb200_host_alloc(eng._ctx, in_bytes)
+                p_out = N.lib().eb200_host_alloc(eng._ctx, out_bytes) if p_in else None
+                if p_in and p_out:
+                    break
+                if p_in:
+                    N.lib().eb200_host_free(eng._ctx, p_in)
+                assert e2e_cases > 8192, "pinned host allocation failed"
+                e2e_cases //= 2
+            if world > 1:      # every rank runs the same e2e step size
+                t = torch.tensor([e2e_cases], device=dev, dtype=torch.int64); dist.all_reduce(t, op=dist.ReduceOp.MIN); e2e_cases = int(t.item())
+            hb = torch.frombuffer((C.c_uint8 * in_bytes).from_address(p_in), dtype=torch.uint8)
+            hb[: e2e_cases * size].copy_(data[: e2e_cases * size])
+            hoff = (C.c_uint64 * (e2e_cases + 1))(*[i * size for i in range(e2e_cases + 1)])
+            ho_off = (C.c_uint64 * (e2e_cases + 1))(); ho_len = (C.c_uint64 * e2e_cases)()
+            st2 = N.Stats()
+            o = erlamsa_b200.make_opts(base_opts)
+            times = []
+            for i in range(args.e2e_steps + 1):
+                o.first_case = 1 + (10_000 + rank + world * i) * n_cases
+                t0 = time.perf_counter()
+                rc = N.lib().eb200_fuzz_batch_into(eng._ctx, C.byref(o), p_in, C.cast(hoff, C.c_void_p), e2e_cases, e2e_cases,
+                                                   p_out, out_bytes, C.cast(ho_off, C.c_void_p), C.cast(ho_len, C.c_void_p), None, C.byref(st2))
+                t1 = time.perf_counter()
+                assert rc == 0, rc
+                if i > 0:
+                    times.append(t1 - t0)
+            dt = max(times)
+            if world > 1:
+                t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+            h2d_b, d2h_b = e2e_cases * size + 8 * (e2e_cases + 1), int(sum(ho_len)) + 16 * e2e_cases + 8
+            e2e = {"value": e2e_cases * world / dt, "unit": "cases/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+                   "cases_per_step": e2e_cases * world, "pcie_gb_per_s_each_way": [h2d_b / dt / 1e9, d2h_b / dt / 1e9], "numa_node_of_gpu": N.lib().eb200_numa_node(eng._ctx),
+                   "note": "eb200_fuzz_batch_into: pinned NUMA-local host corpus -> H2D (chunks, 2 uploads ahead) -> eb_case_kernel -> D2H of outputs, offsets and lengths"}
+            del hb
+            N.lib().eb200_host_free(eng._ctx, p_in); N.lib().eb200_host_free(eng._ctx, p_out)
+        except Exception as e:      # the device-timed line above stands on its own: report, do not lose it
+            e2e, e2e_error = None, repr(e)[:300]
+
     # ---- opt-in (--async-depth D): the same steps through eb200_submit_device / eb200_collect with D batches in flight, each with its
     # own output arena. Lanes run on their own streams, so this is timed by the host clock between two device synchronisations and
     # reported beside the device-timed synchronous number, never instead of it.
@@ -377,7 +382,7 @@ def measure(torch, dist, eng, args, workload, steps, warmup, rank, world, local,
                      "traffic_source": "ncu --set full capture, profiles/" + TRAFFIC_PROFILE[bool(fused)],
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": dom_ms},
         "kernel_ms": {"decide": sum(decide_ms) / len(decide_ms), "scan": sum(scan_ms) / len(scan_ms), "apply": avg_apply},
-        "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+        "gpu_launches": launches, "clocks": clocks, "e2e": e2e if e2e_error is None else {"error": e2e_error},
         # cases the engine did not mutate (paths without a device implementation, per-case output cap: output = input, reported
         # per case in eb200_meta.status) are NOT counted in `value`; worker crashes the reference has too (died) are
         "flagged_cases": dict(flagged, of=n_cases * steps, note="rank 0; unsupported + overflow are subtracted from value"),
@@ -418,7 +423,12 @@ def run_ours(args):
     if args.workload == "c3" and not args.no_extra and not args.cases:
         extra = {}
         for wl, n_x in (("c2", 0), ("c4", 0)):
-            x = measure(torch, dist, eng, args, wl, 2, 3, rank, world, local, n_override=n_x, want_e2e=False)
+            try:
+                x = measure(torch, dist, eng, args, wl, 2, 3, rank, world, local, n_override=n_x, want_e2e=False)
+            except Exception as e:      # a short extra run must never cost the headline line
+                if rank == 0:
+                    extra[wl] = {"error": repr(e)[:300]}
+                continue
             if rank == 0:
                 n_cases, size, kind, muts, pats, desc = WORKLOADS[wl]
                 muts = {c: 1 for c in muts} if muts is not None else {c: p for c, p in erlamsa_b200.default_mutations() if c in erlamsa_b200.supported_mutations()}
